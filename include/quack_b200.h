@@ -1,0 +1,175 @@
+/*
+ * quack_b200.h -- C-ABI of the B200-native replacement for quack's per-read statistics
+ * accumulation (the body of read_fastq(), reference quack.c:180-228).
+ *
+ * The reference has no plugin/FFI layer: the seam is the plain C call
+ *     sequence_data *read_fastq(char *fastq_file, int *kmers);          (quack.c:180)
+ * made once per mate from main() (quack.c:911, 917), fed by kseq_read() (klib/kseq.h:177)
+ * and by the table read_adapters() builds (quack.c:154-178), and consumed by transform()
+ * and draw() (quack.c:230, 295).  This header is what a host program binds instead of that
+ * loop: the host keeps the record reader and the renderer, packs records into batches
+ *     seq[]    concatenated base bytes   (kseq_t.seq.s,  l bytes per read, no padding)
+ *     qual[]   concatenated quality bytes(kseq_t.qual.s, same offsets as seq[])
+ *     offset[] u32 start of each read in seq[]/qual[]   (ascending)
+ *     length[] u32 read length                          (kseq_read() return value)
+ * and gets back the accumulator in the reference's own memory layout:
+ *     uint64_t rows[max_length][97]  ==  base_information bases[max_length]  (quack.c:134-139)
+ *       [0..90] scores[q-33]   [91..94] content[A,T,C,G]   [95] length_count   [96] kmer_count
+ * so it can be handed to transform()/draw() (or their restatement) unchanged.
+ *
+ * Everything is plain pointers and sizes; no CUDA or torch types cross this boundary.
+ * All entry points return 0 on success or a negative qb_status; qb_last_error() gives the
+ * message.  There is no CPU fallback: without a usable CUDA device qb_create() fails.
+ */
+#ifndef QUACK_B200_H
+#define QUACK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB_ROW_U64 97        /* sizeof(base_information)/8, quack.c:134-139 */
+#define QB_N_SCORES 91       /* scores[91] */
+#define QB_COL_CONTENT 91    /* content[4]: A,T,C,G (lookup[] order, quack.c:148-150) */
+#define QB_COL_LENGTH 95     /* length_count */
+#define QB_COL_KMER 96       /* kmer_count */
+#define QB_KMER_SIZE 10      /* quack.c:155, 184 */
+#define QB_KEY_SPACE (1u << 20)
+
+typedef enum {
+  QB_OK = 0,
+  QB_ERR_CUDA = -1,        /* a CUDA runtime call failed (message has the CUDA error string) */
+  QB_ERR_NCCL = -2,        /* an NCCL call failed */
+  QB_ERR_ARG = -3,         /* bad argument */
+  QB_ERR_CAPACITY = -4,    /* batch exceeds the ring slot, or a read exceeds len_cap */
+  QB_ERR_NOMEM = -5,
+  QB_ERR_LAYOUT = -6       /* offsets not ascending / reads overlap */
+} qb_status;
+
+typedef enum {
+  QB_KERNEL_AUTO = 0,      /* fused kernel when len_cap fits its shared-memory histogram */
+  QB_KERNEL_SIMPLE = 1,    /* one warp per read, global atomics: any len_cap, slow */
+  QB_KERNEL_FUSED = 2      /* TMA-staged tiles, joint (base,score) shared-memory histogram */
+} qb_kernel;
+
+typedef struct qb_ctx qb_ctx;       /* one per process; owns devices, streams, accumulators */
+typedef struct qb_dbatch qb_dbatch; /* a batch resident in device memory */
+
+typedef struct {
+  int n_devices;              /* GPUs driven by this process (>= 1) */
+  const int *device_ids;      /* NULL -> 0..n_devices-1 */
+  uint32_t len_cap;           /* longest read accepted; rows allocated per mate */
+  int n_mates;                /* 1 (-u) or 2 (-1/-2): independent accumulators */
+  int adapters_enabled;       /* 0: no -a (reference then counts kmer_count[10] per read with
+                                 l > 10, quack.c:210-217); 1: use adapter_keys */
+  const uint32_t *adapter_keys; /* distinct 20-bit keys, first base most significant: exactly the
+                                   indices read_adapters() sets in kmers[] (quack.c:165-172) */
+  uint32_t n_adapter_keys;
+  uint64_t batch_bytes;       /* capacity of one ring slot for seq[] (and for qual[]); 0 -> 64 MiB */
+  uint32_t batch_reads;       /* capacity of one ring slot in reads; 0 -> batch_bytes/32 */
+  int ring_depth;             /* slots per device (>= 2 to overlap H2D with compute); 0 -> 3 */
+  int kernel;                 /* qb_kernel */
+} qb_config;
+
+/* One pinned host slot of the ring (filled by the record reader, then submitted). */
+typedef struct {
+  uint8_t *seq;
+  uint8_t *qual;
+  uint32_t *offset;
+  uint32_t *length;
+  uint64_t cap_bytes;
+  uint32_t cap_reads;
+  int device_index;           /* which of the ctx's devices this slot feeds */
+  int slot;
+} qb_batch;
+
+/* ---- lifetime ---- */
+int qb_create(const qb_config *cfg, qb_ctx **out);
+void qb_destroy(qb_ctx *ctx);
+const char *qb_last_error(const qb_ctx *ctx); /* ctx may be NULL: error of a failed qb_create */
+int qb_device_count(void);                    /* CUDA devices visible, <0 on error */
+
+/* ---- streaming path (replaces the while loop of read_fastq, quack.c:193-221) ---- */
+/* Blocks until a slot of the ring is free (its previous kernel finished) and hands its pinned
+ * host buffers to the caller.  Slots rotate over the devices round-robin.  Thread-safe. */
+int qb_acquire(qb_ctx *ctx, qb_batch *out);
+/* Queues H2D copies of the first n_bytes / n_reads of the slot and the statistics kernel on the
+ * slot's stream, and returns without waiting.  max_len = longest read in the batch (0 = unknown). */
+int qb_submit(qb_ctx *ctx, const qb_batch *b, int mate, uint32_t n_reads, uint64_t n_bytes,
+              uint32_t max_len);
+/* Same, from caller-owned host memory (pinned memory copies asynchronously): takes the next free
+ * device slot itself.  Must respect the slot capacities. */
+int qb_submit_from(qb_ctx *ctx, int mate, const uint8_t *seq, const uint8_t *qual,
+                   const uint32_t *offset, const uint32_t *length, uint32_t n_reads,
+                   uint64_t n_bytes, uint32_t max_len);
+/* Convenience for callers with one big host array: splits at read boundaries into slot-sized
+ * batches (rebasing offsets) and submits them all.  Offsets must be ascending. */
+int qb_accumulate_host(qb_ctx *ctx, int mate, const uint8_t *seq, const uint8_t *qual,
+                       const uint32_t *offset, const uint32_t *length, uint64_t n_reads);
+/* Waits for all queued work of every device. */
+int qb_sync(qb_ctx *ctx);
+
+/* ---- result (what read_fastq() returns, quack.c:222-227) ---- */
+/* Synchronises, sums the per-device accumulators (one NCCL reduce to the first device / rank 0
+ * when more than one GPU took part), and copies rows[0..max_length) to rows_out in the
+ * base_information layout.  max_length = longest read, n_reads = number_of_sequences.
+ * With qb_comm_init_rank() only rank 0 receives the summed result; other ranks get their own
+ * partial rows.  rows_cap is in rows (positions). */
+int qb_finish(qb_ctx *ctx, int mate, uint64_t *rows_out, uint64_t rows_cap, uint64_t *max_length,
+              uint64_t *n_reads);
+/* Zeroes the accumulators of one mate (all devices) so a context can be reused. */
+int qb_reset(qb_ctx *ctx, int mate);
+/* Diagnostics: quality bytes outside [33,123] seen (undefined behaviour in the reference). */
+int qb_invalid_quality_count(qb_ctx *ctx, int mate, uint64_t *out);
+
+/* ---- multi-process multi-GPU (one process per GPU, e.g. under torchrun) ---- */
+#define QB_NCCL_ID_BYTES 128
+int qb_nccl_unique_id(uint8_t id_out[QB_NCCL_ID_BYTES]);             /* call on rank 0, broadcast */
+int qb_comm_init_rank(qb_ctx *ctx, int n_ranks, int rank, const uint8_t id[QB_NCCL_ID_BYTES]);
+
+/* ---- device-resident batches (config 5: kernel-only sweep; bench.py `value`) ---- */
+int qb_dbatch_upload(qb_ctx *ctx, int device_index, const uint8_t *seq, const uint8_t *qual,
+                     const uint32_t *offset, const uint32_t *length, uint32_t n_reads,
+                     uint64_t n_bytes, uint32_t max_len, qb_dbatch **out);
+/* Allocates an empty device batch and fills it on the device's own host-side generator output
+ * (see qb_gen_reads) without keeping a host copy. */
+int qb_dbatch_generate(qb_ctx *ctx, int device_index, uint64_t seed, int mate, uint64_t first_read,
+                       uint32_t n_reads, uint32_t len_min, uint32_t len_max, double adapter_rate,
+                       qb_dbatch **out);
+int qb_dbatch_run(qb_ctx *ctx, qb_dbatch *b, int mate);              /* async launch */
+/* iters launches timed with CUDA events on the launching stream; average ms per launch.
+ * flush_l2 != 0 writes a buffer larger than L2 between launches (outside the timed events). */
+int qb_dbatch_time(qb_ctx *ctx, qb_dbatch *b, int mate, int warmup, int iters, int flush_l2,
+                   float *ms_avg, float *ms_min);
+int qb_dbatch_info(const qb_dbatch *b, uint32_t *n_reads, uint64_t *n_bytes);
+void qb_dbatch_free(qb_ctx *ctx, qb_dbatch *b);
+/* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
+uint64_t qb_launch_count(const qb_ctx *ctx);
+/* Measured pinned H2D bandwidth of device_index in GB/s (best of `iters` copies of `bytes`). */
+int qb_measure_h2d(qb_ctx *ctx, int device_index, uint64_t bytes, int iters, double *gbs);
+
+/* ---- host helpers that define the kernel's inputs ---- */
+/* lookup[(c-65)&~32] of quack.c:150,201 extended to all byte values. */
+int qb_base_code(int c);
+/* Keys of one adapter record exactly as read_adapters() inserts them (quack.c:165-172): windows
+ * ending at i = 10..l-1.  Appends to keys[] (capacity cap), returns the number appended or
+ * QB_ERR_CAPACITY.  Duplicates are allowed in adapter_keys. */
+int qb_adapter_record_keys(const char *seq, size_t l, uint32_t *keys, size_t cap);
+/* Deterministic synthetic reads: read i of a file depends only on
+ * (seed, mate, i), so shards can be generated independently.  Fills n_reads reads starting at
+ * index first_read; lengths uniform in [len_min,len_max]; returns bytes written via *n_bytes.
+ * Buffers: seq/qual >= n_reads*len_max bytes; offset/length >= n_reads. */
+int qb_gen_reads(uint64_t seed, int mate, uint64_t first_read, uint32_t n_reads, uint32_t len_min,
+                 uint32_t len_max, double adapter_rate, uint8_t *seq, uint8_t *qual,
+                 uint32_t *offset, uint32_t *length, uint64_t *n_bytes);
+/* Pinned host memory for callers that stage their own batches (qb_submit_from). */
+void *qb_host_alloc(size_t bytes);
+void qb_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUACK_B200_H */

@@ -16,10 +16,11 @@
 int qo_base_code(int c) {
   unsigned b = (unsigned)c & 0xFFu;
   /* reference domain: lookup[20] indexed by (c-65)&~32 (quack.c:150, 201): index 2 (C) -> 2,
-   * index 6 (G) -> 3, index 19 (T) -> 1, all other indices 0..19 -> 0. */
-  if ((b & 0x5Bu) == 0x43u) return 2 + (int)((b >> 2) & 1u); /* C,c -> 2 ; G,g -> 3 */
-  if ((b & 0x1Fu) == 0x14u) return 1;                        /* T,t -> 1 */
-  return 0;
+   * index 6 (G) -> 3, index 19 (T) -> 1, all other indices 0..19 -> 0.  The bit tests below
+   * give exactly that on [A-Ta-t] and define the rest of the byte range. */
+  int cg = (b & 0x5Bu) == 0x43u;                                /* C,c,G,g */
+  int lo = (b & 0x1Fu) == 0x07u || (b & 0x1Fu) == 0x14u;        /* G,g / T,t */
+  return 2 * cg + lo;
 }
 
 /* ------------------------------------------------------------------ adapter table */

@@ -45,7 +45,7 @@ typedef struct {
 /* lookup[(c-65) & ~32], quack.c:148-150, 200-201.  Exact on the reference's defined
  * domain [A-Ta-t]: C/c->2, G/g->3, T/t->1, everything else (incl. N) -> 0.  Bytes outside
  * that domain index lookup[] out of bounds in the reference (UB); here they are defined as
- *   2+((b>>2)&1) if (b&0x5B)==0x43, else 1 if (b&0x1F)==0x14, else 0
+ *   2*[(b&0x5B)==0x43] + [(b&0x1F)==0x07 || (b&0x1F)==0x14]
  * which is the same rule the CUDA kernel uses, so both agree on all 256 byte values. */
 int qo_base_code(int c);
 

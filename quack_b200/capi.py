@@ -1,0 +1,282 @@
+"""ctypes mirror of include/quack_b200.h (same names, same argument meaning, same error codes).
+
+Raises at import-of-use time when the CUDA library has not been built: there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import lib_path
+
+ROW = 97
+COL_CONTENT, COL_LENGTH, COL_KMER = 91, 95, 96
+KERNEL_AUTO, KERNEL_SIMPLE, KERNEL_FUSED = 0, 1, 2
+NCCL_ID_BYTES = 128
+
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+
+
+class QbConfig(C.Structure):
+    _fields_ = [
+        ("n_devices", C.c_int), ("device_ids", C.POINTER(C.c_int)), ("len_cap", C.c_uint32),
+        ("n_mates", C.c_int), ("adapters_enabled", C.c_int), ("adapter_keys", _u32p),
+        ("n_adapter_keys", C.c_uint32), ("batch_bytes", C.c_uint64), ("batch_reads", C.c_uint32),
+        ("ring_depth", C.c_int), ("kernel", C.c_int),
+    ]
+
+
+class QbBatch(C.Structure):
+    _fields_ = [
+        ("seq", _u8p), ("qual", _u8p), ("offset", _u32p), ("length", _u32p),
+        ("cap_bytes", C.c_uint64), ("cap_reads", C.c_uint32), ("device_index", C.c_int), ("slot", C.c_int),
+    ]
+
+
+class QbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"quack_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(quack_b200 has no CPU fallback)")
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.qb_create.argtypes = [C.POINTER(QbConfig), C.POINTER(vp)]
+    L.qb_destroy.argtypes = [vp]
+    L.qb_destroy.restype = None
+    L.qb_last_error.argtypes = [vp]
+    L.qb_last_error.restype = C.c_char_p
+    L.qb_acquire.argtypes = [vp, C.POINTER(QbBatch)]
+    L.qb_submit.argtypes = [vp, C.POINTER(QbBatch), C.c_int, C.c_uint32, C.c_uint64, C.c_uint32]
+    L.qb_submit_from.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32]
+    L.qb_accumulate_host.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_uint64]
+    L.qb_sync.argtypes = [vp]
+    L.qb_finish.argtypes = [vp, C.c_int, vp, C.c_uint64, _u64p, _u64p]
+    L.qb_reset.argtypes = [vp, C.c_int]
+    L.qb_invalid_quality_count.argtypes = [vp, C.c_int, _u64p]
+    L.qb_nccl_unique_id.argtypes = [vp]
+    L.qb_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.qb_dbatch_upload.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32, C.POINTER(vp)]
+    L.qb_dbatch_generate.argtypes = [vp, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32,
+                                     C.c_uint32, C.c_double, C.POINTER(vp)]
+    L.qb_dbatch_run.argtypes = [vp, vp, C.c_int]
+    L.qb_dbatch_time.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                 C.POINTER(C.c_float)]
+    L.qb_dbatch_info.argtypes = [vp, _u32p, _u64p]
+    L.qb_dbatch_free.argtypes = [vp, vp]
+    L.qb_dbatch_free.restype = None
+    L.qb_launch_count.argtypes = [vp]
+    L.qb_launch_count.restype = C.c_uint64
+    L.qb_measure_h2d.argtypes = [vp, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
+    L.qb_base_code.argtypes = [C.c_int]
+    L.qb_adapter_record_keys.argtypes = [C.c_char_p, C.c_size_t, _u32p, C.c_size_t]
+    L.qb_gen_reads.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
+                               vp, vp, vp, vp, _u64p]
+    L.qb_host_alloc.argtypes = [C.c_size_t]
+    L.qb_host_alloc.restype = vp
+    L.qb_host_free.argtypes = [vp]
+    L.qb_host_free.restype = None
+    L.qb_microbench.argtypes = [C.c_char_p, C.c_size_t]
+    L.qb_adapter_filter_info.argtypes = [vp, _u32p, C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def base_code(c: int) -> int:
+    return lib().qb_base_code(c)
+
+
+def adapter_record_keys(seq: bytes) -> np.ndarray:
+    """Keys read_adapters() inserts for one FASTA record (reference quack.c:165-172)."""
+    out = np.zeros(max(len(seq), 1), dtype=np.uint32)
+    n = lib().qb_adapter_record_keys(seq, len(seq), out.ctypes.data_as(_u32p), len(out))
+    if n < 0:
+        raise QbError(n, "qb_adapter_record_keys")
+    return out[:n]
+
+
+def gen_reads(seed: int, mate: int, first_read: int, n_reads: int, len_min: int, len_max: int,
+              adapter_rate: float):
+    """Deterministic synthetic reads.  Returns (seq, qual, offset, length) numpy arrays."""
+    seq = np.zeros(n_reads * len_max + 64, dtype=np.uint8)
+    qual = np.zeros(n_reads * len_max + 64, dtype=np.uint8)
+    off = np.zeros(n_reads, dtype=np.uint32)
+    ln = np.zeros(n_reads, dtype=np.uint32)
+    nb = C.c_uint64()
+    rc = lib().qb_gen_reads(seed, mate, first_read, n_reads, len_min, len_max, adapter_rate, seq.ctypes.data,
+                            qual.ctypes.data, off.ctypes.data, ln.ctypes.data, C.byref(nb))
+    if rc:
+        raise QbError(rc, "qb_gen_reads")
+    return seq[: nb.value], qual[: nb.value], off, ln
+
+
+class Result:
+    def __init__(self, rows, max_length, n_reads):
+        self.rows, self.max_length, self.n_reads = rows, max_length, n_reads
+
+
+class DeviceBatch:
+    def __init__(self, ctx: "Context", handle):
+        self.ctx, self.h = ctx, handle
+
+    @property
+    def info(self):
+        n, b = C.c_uint32(), C.c_uint64()
+        lib().qb_dbatch_info(self.h, C.byref(n), C.byref(b))
+        return n.value, b.value
+
+    def run(self, mate: int = 0):
+        self.ctx._chk(lib().qb_dbatch_run(self.ctx.h, self.h, mate))
+
+    def time(self, mate: int = 0, warmup: int = 3, iters: int = 10, flush_l2: bool = False):
+        avg, mn = C.c_float(), C.c_float()
+        self.ctx._chk(lib().qb_dbatch_time(self.ctx.h, self.h, mate, warmup, iters, int(flush_l2), C.byref(avg),
+                                           C.byref(mn)))
+        return avg.value, mn.value
+
+    def free(self):
+        if self.h:
+            lib().qb_dbatch_free(self.ctx.h, self.h)
+            self.h = None
+
+
+class Context:
+    """qb_ctx: what the host program creates once per run in place of calling read_fastq() per mate."""
+
+    def __init__(self, len_cap: int, n_mates: int = 1, adapter_keys=None, n_devices: int = 1, device_ids=None,
+                 batch_bytes: int = 0, batch_reads: int = 0, ring_depth: int = 0, kernel: int = KERNEL_AUTO):
+        cfg = QbConfig()
+        cfg.n_devices = n_devices
+        self._ids = (C.c_int * n_devices)(*device_ids) if device_ids is not None else None
+        cfg.device_ids = self._ids
+        cfg.len_cap = len_cap
+        cfg.n_mates = n_mates
+        cfg.adapters_enabled = 0 if adapter_keys is None else 1
+        self._keys = None
+        if adapter_keys is not None:
+            self._keys = np.ascontiguousarray(adapter_keys, dtype=np.uint32)
+            cfg.adapter_keys = self._keys.ctypes.data_as(_u32p)
+            cfg.n_adapter_keys = len(self._keys)
+        cfg.batch_bytes, cfg.batch_reads, cfg.ring_depth, cfg.kernel = batch_bytes, batch_reads, ring_depth, kernel
+        self.len_cap = len_cap
+        h = C.c_void_p()
+        rc = lib().qb_create(C.byref(cfg), C.byref(h))
+        if rc:
+            raise QbError(rc, lib().qb_last_error(None).decode())
+        self.h = h
+
+    def _chk(self, rc: int):
+        if rc:
+            raise QbError(rc, lib().qb_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            lib().qb_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def acquire(self) -> QbBatch:
+        b = QbBatch()
+        self._chk(lib().qb_acquire(self.h, C.byref(b)))
+        return b
+
+    def submit(self, b: QbBatch, mate: int, n_reads: int, n_bytes: int, max_len: int = 0):
+        self._chk(lib().qb_submit(self.h, C.byref(b), mate, n_reads, n_bytes, max_len))
+
+    def submit_from(self, mate, seq_ptr, qual_ptr, off_ptr, len_ptr, n_reads, n_bytes, max_len=0):
+        self._chk(lib().qb_submit_from(self.h, mate, seq_ptr, qual_ptr, off_ptr, len_ptr, n_reads, n_bytes, max_len))
+
+    def accumulate_host(self, mate: int, seq, qual, offset, length):
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        qual = np.ascontiguousarray(qual, dtype=np.uint8)
+        offset = np.ascontiguousarray(offset, dtype=np.uint32)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        self._chk(lib().qb_accumulate_host(self.h, mate, seq.ctypes.data, qual.ctypes.data, offset.ctypes.data,
+                                           length.ctypes.data, len(offset)))
+
+    def sync(self):
+        self._chk(lib().qb_sync(self.h))
+
+    def reset(self, mate: int = 0):
+        self._chk(lib().qb_reset(self.h, mate))
+
+    def finish(self, mate: int = 0) -> Result:
+        rows = np.zeros((self.len_cap, ROW), dtype=np.uint64)
+        ml, n = C.c_uint64(), C.c_uint64()
+        self._chk(lib().qb_finish(self.h, mate, rows.ctypes.data, self.len_cap, C.byref(ml), C.byref(n)))
+        return Result(rows[: ml.value].copy(), int(ml.value), int(n.value))
+
+    def invalid_quality_count(self, mate: int = 0) -> int:
+        v = C.c_uint64()
+        self._chk(lib().qb_invalid_quality_count(self.h, mate, C.byref(v)))
+        return int(v.value)
+
+    def comm_init_rank(self, n_ranks: int, rank: int, nccl_id: bytes):
+        buf = (C.c_uint8 * NCCL_ID_BYTES).from_buffer_copy(nccl_id)
+        self._chk(lib().qb_comm_init_rank(self.h, n_ranks, rank, buf))
+
+    def upload(self, seq, qual, offset, length, max_len: int = 0, device_index: int = 0) -> DeviceBatch:
+        seq = np.ascontiguousarray(seq, dtype=np.uint8)
+        qual = np.ascontiguousarray(qual, dtype=np.uint8)
+        offset = np.ascontiguousarray(offset, dtype=np.uint32)
+        length = np.ascontiguousarray(length, dtype=np.uint32)
+        h = C.c_void_p()
+        self._chk(lib().qb_dbatch_upload(self.h, device_index, seq.ctypes.data, qual.ctypes.data, offset.ctypes.data,
+                                         length.ctypes.data, len(offset), len(seq), max_len, C.byref(h)))
+        return DeviceBatch(self, h)
+
+    def generate(self, seed, mate, first_read, n_reads, len_min, len_max, adapter_rate, device_index=0) -> DeviceBatch:
+        h = C.c_void_p()
+        self._chk(lib().qb_dbatch_generate(self.h, device_index, seed, mate, first_read, n_reads, len_min, len_max,
+                                           adapter_rate, C.byref(h)))
+        return DeviceBatch(self, h)
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().qb_launch_count(self.h))
+
+    def measure_h2d(self, nbytes: int = 256 << 20, iters: int = 5, device_index: int = 0) -> float:
+        g = C.c_double()
+        self._chk(lib().qb_measure_h2d(self.h, device_index, nbytes, iters, C.byref(g)))
+        return g.value
+
+    def adapter_filter_info(self):
+        m, f = C.c_uint32(), C.c_double()
+        lib().qb_adapter_filter_info(self.h, C.byref(m), C.byref(f))
+        return m.value, f.value
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * NCCL_ID_BYTES)()
+    rc = lib().qb_nccl_unique_id(buf)
+    if rc:
+        raise QbError(rc, "qb_nccl_unique_id")
+    return bytes(buf)
+
+
+def microbench() -> str:
+    buf = C.create_string_buffer(1 << 16)
+    rc = lib().qb_microbench(buf, len(buf))
+    if rc:
+        raise QbError(rc, "qb_microbench")
+    return buf.value.decode()

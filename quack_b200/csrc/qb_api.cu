@@ -1,0 +1,801 @@
+// qb_api.cu -- implementation of the C-ABI in include/quack_b200.h: devices, the pinned
+// double/triple-buffered batch ring (cudaMemcpyAsync overlapped with compute, one stream per
+// slot), per-mate u64 accumulators, the NCCL reduce of the accumulators, device-resident batches
+// and their CUDA-event timing.  Replaces the loop of read_fastq() (reference quack.c:180-228).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/quack_b200.h"
+#include "qb_host.h"
+#include "qb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// NCCL is bound at first use with dlopen instead of at link time: a host process may already carry
+// its own libnccl.so.2 (PyTorch bundles a newer one than the system's) and must keep exactly one.
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+NcclApi *nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+      api.handle = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (api.handle) break;
+    }
+    if (!api.handle) return;
+#define QB_SYM(field, sym) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, sym))
+    QB_SYM(GetUniqueId, "ncclGetUniqueId");
+    QB_SYM(CommInitRank, "ncclCommInitRank");
+    QB_SYM(CommInitAll, "ncclCommInitAll");
+    QB_SYM(CommDestroy, "ncclCommDestroy");
+    QB_SYM(Reduce, "ncclReduce");
+    QB_SYM(GroupStart, "ncclGroupStart");
+    QB_SYM(GroupEnd, "ncclGroupEnd");
+    QB_SYM(GetErrorString, "ncclGetErrorString");
+#undef QB_SYM
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.CommDestroy && api.Reduce &&
+             api.GroupStart && api.GroupEnd && api.GetErrorString;
+  });
+  return api.ok ? &api : nullptr;
+}
+
+struct Slot {
+  uint8_t *h_seq = nullptr, *h_qual = nullptr;
+  uint32_t *h_off = nullptr, *h_len = nullptr;
+  uint8_t *d_seq = nullptr, *d_qual = nullptr;
+  uint32_t *d_off = nullptr, *d_len = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  bool pending = false;
+};
+
+struct Device {
+  int id = 0;
+  int sm_count = 0;
+  int smem_optin = 0;
+  std::vector<unsigned long long *> acc;  // per mate: [len_cap*97 rows][kNumCounters]
+  unsigned long long *reduce_buf = nullptr;
+  uint32_t *d_bitmap = nullptr, *d_bloom = nullptr;
+  std::vector<Slot> slots;
+  cudaStream_t main_stream = nullptr;
+  ncclComm_t comm = nullptr;  // in-process communicator (n_devices > 1)
+  uint32_t *l2_scratch = nullptr;
+  size_t l2_words = 0;
+};
+
+}  // namespace
+
+struct qb_ctx {
+  qb_config cfg;
+  std::vector<Device> dev;
+  std::mutex mu;
+  uint64_t next_slot = 0;
+  std::string err;
+  uint64_t launches = 0;
+  size_t acc_u64 = 0;  // len_cap*97 + counters
+  qb::AdapterSet ad_host_template{};
+  uint32_t bloom_mul = 0;
+  double bloom_fp = 0;
+  uint32_t qbase = 32;
+  ncclComm_t rank_comm = nullptr;  // multi-process communicator
+  int n_ranks = 1, rank = 0;
+  unsigned long long *h_result = nullptr;  // pinned staging for qb_finish
+};
+
+struct qb_dbatch {
+  int device_index;
+  uint8_t *d_seq, *d_qual;
+  uint32_t *d_off, *d_len;
+  uint32_t n_reads;
+  uint64_t n_bytes;
+  uint32_t max_len;
+};
+
+namespace {
+
+int fail(qb_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx)
+    ctx->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define QB_CUDA(ctx, call)                                                                      \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(ctx, QB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define QB_NCCL(ctx, call)                                                                      \
+  do {                                                                                          \
+    ncclResult_t r__ = (call);                                                                  \
+    if (r__ != ncclSuccess)                                                                     \
+      return fail(ctx, QB_ERR_NCCL, "%s failed: %s (%s:%d)", #call, nccl_api()->GetErrorString(r__), __FILE__, __LINE__); \
+  } while (0)
+
+inline size_t pad_bytes(uint64_t n) { return (size_t)((n + 15) & ~15ull) + 64; }
+inline size_t pad_reads(uint32_t n) { return ((size_t)n + 3 & ~(size_t)3) + 16; }
+
+qb::AdapterSet adapter_set(const qb_ctx *ctx, const Device &d) {
+  qb::AdapterSet a;
+  a.bitmap = d.d_bitmap;
+  a.bloom = d.d_bloom;
+  a.bloom_mul = ctx->bloom_mul;
+  a.enabled = ctx->cfg.adapters_enabled ? 1 : 0;
+  return a;
+}
+
+qb::Accum accum(const qb_ctx *ctx, const Device &d, int mate) {
+  qb::Accum a;
+  a.rows = d.acc[mate];
+  a.counters = d.acc[mate] + (size_t)ctx->cfg.len_cap * qb::kRow;
+  a.len_cap = ctx->cfg.len_cap;
+  return a;
+}
+
+// chooses and launches the statistics kernel for one device-resident batch
+int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaStream_t stream) {
+  if (v.n_reads == 0) return QB_OK;
+  const qb::AdapterSet ad = adapter_set(ctx, d);
+  const qb::Accum ac = accum(ctx, d, mate);
+  int kernel = ctx->cfg.kernel;
+  qb::FusedPlan plan{};
+  if (kernel != QB_KERNEL_SIMPLE) {
+    plan = qb::fused_plan(ctx->cfg.len_cap, v.max_len, ad.enabled, d.sm_count, (uint32_t)d.smem_optin, ctx->qbase);
+    if (!plan.ok) {
+      if (kernel == QB_KERNEL_FUSED)
+        return fail(ctx, QB_ERR_CAPACITY, "len_cap %u does not fit the fused kernel's shared-memory histogram",
+                    ctx->cfg.len_cap);
+      kernel = QB_KERNEL_SIMPLE;
+    } else
+      kernel = QB_KERNEL_FUSED;
+  }
+  cudaError_t e = kernel == QB_KERNEL_FUSED ? qb::launch_fused(v, ac, ad, plan, stream)
+                                            : qb::launch_simple(v, ac, ad, d.sm_count, stream);
+  if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->launches++;
+  }
+  return QB_OK;
+}
+
+int check_mate(qb_ctx *ctx, int mate) {
+  if (!ctx) return QB_ERR_ARG;
+  if (mate < 0 || mate >= ctx->cfg.n_mates) return fail(ctx, QB_ERR_ARG, "mate %d out of range", mate);
+  return QB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return QB_ERR_CUDA;
+  return n;
+}
+
+const char *qb_last_error(const qb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void *qb_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void qb_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int qb_create(const qb_config *cfg_in, qb_ctx **out) {
+  if (!cfg_in || !out) return fail(nullptr, QB_ERR_ARG, "null argument");
+  *out = nullptr;
+  qb_config cfg = *cfg_in;
+  if (cfg.n_devices < 1) return fail(nullptr, QB_ERR_ARG, "n_devices must be >= 1");
+  if (cfg.n_mates < 1 || cfg.n_mates > 2) return fail(nullptr, QB_ERR_ARG, "n_mates must be 1 or 2");
+  if (cfg.len_cap < 11 || cfg.len_cap > (1u << 20)) return fail(nullptr, QB_ERR_ARG, "len_cap must be in [11, 2^20]");
+  if (cfg.batch_bytes == 0) cfg.batch_bytes = 64ull << 20;
+  if (cfg.batch_bytes > 0xFFFFFF00ull - 64) return fail(nullptr, QB_ERR_ARG, "batch_bytes must stay below 4 GiB (u32 offsets)");
+  if (cfg.batch_reads == 0) cfg.batch_reads = (uint32_t)(cfg.batch_bytes / 32 + 1);
+  if (cfg.ring_depth == 0) cfg.ring_depth = 3;
+  if (cfg.ring_depth < 1) return fail(nullptr, QB_ERR_ARG, "ring_depth must be >= 1");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(nullptr, QB_ERR_CUDA, "no usable CUDA device (%s); quack_b200 has no CPU fallback",
+                ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
+
+  qb_ctx *ctx = new qb_ctx();
+  ctx->cfg = cfg;
+  ctx->cfg.device_ids = nullptr;
+  ctx->cfg.adapter_keys = nullptr;
+  ctx->acc_u64 = (size_t)cfg.len_cap * qb::kRow + qb::kNumCounters;
+  if (const char *qb_env = getenv("QB_QBASE")) {
+    const int v = atoi(qb_env);
+    if (v >= 32 && v <= 63) ctx->qbase = (uint32_t)v;
+  }
+
+  std::vector<uint32_t> bitmap, bloom;
+  if (cfg.adapters_enabled) {
+    if (cfg.n_adapter_keys && !cfg.adapter_keys) {
+      delete ctx;
+      return fail(nullptr, QB_ERR_ARG, "adapter_keys is NULL");
+    }
+    qb::build_adapter_images(cfg.adapter_keys, cfg.n_adapter_keys, bitmap, bloom, ctx->bloom_mul, ctx->bloom_fp);
+  }
+
+#define QB_CREATE_CUDA(call)                                                                          \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess) {                                                                         \
+      fail(nullptr, QB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      qb_destroy(ctx);                                                                                \
+      return QB_ERR_CUDA;                                                                             \
+    }                                                                                                 \
+  } while (0)
+
+  ctx->dev.resize(cfg.n_devices);
+  for (int i = 0; i < cfg.n_devices; i++) {
+    Device &d = ctx->dev[i];
+    d.id = cfg_in->device_ids ? cfg_in->device_ids[i] : i;
+    if (d.id < 0 || d.id >= ndev) {
+      fail(nullptr, QB_ERR_ARG, "device id %d not available (%d visible)", d.id, ndev);
+      qb_destroy(ctx);
+      return QB_ERR_ARG;
+    }
+    QB_CREATE_CUDA(cudaSetDevice(d.id));
+    QB_CREATE_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.id));
+    QB_CREATE_CUDA(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.id));
+    QB_CREATE_CUDA(qb::fused_configure());
+    QB_CREATE_CUDA(cudaStreamCreateWithFlags(&d.main_stream, cudaStreamNonBlocking));
+    d.acc.resize(cfg.n_mates);
+    for (int m = 0; m < cfg.n_mates; m++) {
+      QB_CREATE_CUDA(cudaMalloc(&d.acc[m], ctx->acc_u64 * 8));
+      QB_CREATE_CUDA(cudaMemset(d.acc[m], 0, ctx->acc_u64 * 8));
+    }
+    QB_CREATE_CUDA(cudaMalloc(&d.reduce_buf, ctx->acc_u64 * 8));
+    if (cfg.adapters_enabled) {
+      QB_CREATE_CUDA(cudaMalloc(&d.d_bitmap, bitmap.size() * 4));
+      QB_CREATE_CUDA(cudaMemcpy(d.d_bitmap, bitmap.data(), bitmap.size() * 4, cudaMemcpyHostToDevice));
+      QB_CREATE_CUDA(cudaMalloc(&d.d_bloom, bloom.size() * 4));
+      QB_CREATE_CUDA(cudaMemcpy(d.d_bloom, bloom.data(), bloom.size() * 4, cudaMemcpyHostToDevice));
+    }
+    d.slots.resize(cfg.ring_depth);
+    for (Slot &s : d.slots) {
+      QB_CREATE_CUDA(cudaHostAlloc(&s.h_seq, pad_bytes(cfg.batch_bytes), cudaHostAllocDefault));
+      QB_CREATE_CUDA(cudaHostAlloc(&s.h_qual, pad_bytes(cfg.batch_bytes), cudaHostAllocDefault));
+      QB_CREATE_CUDA(cudaHostAlloc(&s.h_off, pad_reads(cfg.batch_reads) * 4, cudaHostAllocDefault));
+      QB_CREATE_CUDA(cudaHostAlloc(&s.h_len, pad_reads(cfg.batch_reads) * 4, cudaHostAllocDefault));
+      QB_CREATE_CUDA(cudaMalloc(&s.d_seq, pad_bytes(cfg.batch_bytes)));
+      QB_CREATE_CUDA(cudaMalloc(&s.d_qual, pad_bytes(cfg.batch_bytes)));
+      QB_CREATE_CUDA(cudaMalloc(&s.d_off, pad_reads(cfg.batch_reads) * 4));
+      QB_CREATE_CUDA(cudaMalloc(&s.d_len, pad_reads(cfg.batch_reads) * 4));
+      QB_CREATE_CUDA(cudaMemset(s.d_seq, 0, pad_bytes(cfg.batch_bytes)));
+      QB_CREATE_CUDA(cudaMemset(s.d_qual, 0, pad_bytes(cfg.batch_bytes)));
+      QB_CREATE_CUDA(cudaMemset(s.d_off, 0, pad_reads(cfg.batch_reads) * 4));
+      QB_CREATE_CUDA(cudaMemset(s.d_len, 0, pad_reads(cfg.batch_reads) * 4));
+      QB_CREATE_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+      QB_CREATE_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    QB_CREATE_CUDA(cudaDeviceSynchronize());
+  }
+  QB_CREATE_CUDA(cudaHostAlloc(&ctx->h_result, ctx->acc_u64 * 8, cudaHostAllocDefault));
+  if (cfg.n_devices > 1) {
+    std::vector<ncclComm_t> comms(cfg.n_devices);
+    std::vector<int> ids(cfg.n_devices);
+    for (int i = 0; i < cfg.n_devices; i++) ids[i] = ctx->dev[i].id;
+    NcclApi *nc = nccl_api();
+    ncclResult_t r = nc ? nc->CommInitAll(comms.data(), cfg.n_devices, ids.data()) : ncclSystemError;
+    if (r != ncclSuccess) {
+      fail(nullptr, QB_ERR_NCCL, "ncclCommInitAll failed: %s", nc ? nc->GetErrorString(r) : "libnccl.so.2 not found");
+      qb_destroy(ctx);
+      return QB_ERR_NCCL;
+    }
+    for (int i = 0; i < cfg.n_devices; i++) ctx->dev[i].comm = comms[i];
+  }
+#undef QB_CREATE_CUDA
+  *out = ctx;
+  return QB_OK;
+}
+
+void qb_destroy(qb_ctx *ctx) {
+  if (!ctx) return;
+  if (ctx->rank_comm) nccl_api()->CommDestroy(ctx->rank_comm);
+  for (Device &d : ctx->dev) {
+    cudaSetDevice(d.id);
+    cudaDeviceSynchronize();
+    if (d.comm) nccl_api()->CommDestroy(d.comm);
+    for (Slot &s : d.slots) {
+      if (s.h_seq) cudaFreeHost(s.h_seq);
+      if (s.h_qual) cudaFreeHost(s.h_qual);
+      if (s.h_off) cudaFreeHost(s.h_off);
+      if (s.h_len) cudaFreeHost(s.h_len);
+      cudaFree(s.d_seq);
+      cudaFree(s.d_qual);
+      cudaFree(s.d_off);
+      cudaFree(s.d_len);
+      if (s.stream) cudaStreamDestroy(s.stream);
+      if (s.done) cudaEventDestroy(s.done);
+    }
+    for (auto p : d.acc) cudaFree(p);
+    cudaFree(d.reduce_buf);
+    cudaFree(d.d_bitmap);
+    cudaFree(d.d_bloom);
+    cudaFree(d.l2_scratch);
+    if (d.main_stream) cudaStreamDestroy(d.main_stream);
+  }
+  if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  delete ctx;
+}
+
+// picks the next slot round-robin over devices x ring and waits until its previous use finished
+static int take_slot(qb_ctx *ctx, int *dev_index, int *slot_index) {
+  const uint64_t total = (uint64_t)ctx->dev.size() * ctx->cfg.ring_depth;
+  uint64_t k;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    k = ctx->next_slot++ % total;
+  }
+  const int di = (int)(k % ctx->dev.size());
+  const int si = (int)(k / ctx->dev.size());
+  Device &d = ctx->dev[di];
+  Slot &s = d.slots[si];
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  if (s.pending) {
+    QB_CUDA(ctx, cudaEventSynchronize(s.done));
+    s.pending = false;
+  }
+  *dev_index = di;
+  *slot_index = si;
+  return QB_OK;
+}
+
+int qb_acquire(qb_ctx *ctx, qb_batch *out) {
+  if (!ctx || !out) return QB_ERR_ARG;
+  int di, si;
+  int rc = take_slot(ctx, &di, &si);
+  if (rc) return rc;
+  Slot &s = ctx->dev[di].slots[si];
+  out->seq = s.h_seq;
+  out->qual = s.h_qual;
+  out->offset = s.h_off;
+  out->length = s.h_len;
+  out->cap_bytes = ctx->cfg.batch_bytes;
+  out->cap_reads = ctx->cfg.batch_reads;
+  out->device_index = di;
+  out->slot = si;
+  return QB_OK;
+}
+
+static int submit_on(qb_ctx *ctx, int di, int si, int mate, const uint8_t *seq, const uint8_t *qual,
+                     const uint32_t *offset, const uint32_t *length, uint32_t n_reads, uint64_t n_bytes,
+                     uint32_t max_len) {
+  if (n_reads > ctx->cfg.batch_reads || n_bytes > ctx->cfg.batch_bytes)
+    return fail(ctx, QB_ERR_CAPACITY, "batch of %u reads / %llu bytes exceeds the slot (%u / %llu)", n_reads,
+                (unsigned long long)n_bytes, ctx->cfg.batch_reads, (unsigned long long)ctx->cfg.batch_bytes);
+  Device &d = ctx->dev[di];
+  Slot &s = d.slots[si];
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  if (n_reads) {
+    if (n_bytes) {
+      QB_CUDA(ctx, cudaMemcpyAsync(s.d_seq, seq, n_bytes, cudaMemcpyHostToDevice, s.stream));
+      QB_CUDA(ctx, cudaMemcpyAsync(s.d_qual, qual, n_bytes, cudaMemcpyHostToDevice, s.stream));
+    }
+    QB_CUDA(ctx, cudaMemcpyAsync(s.d_off, offset, (size_t)n_reads * 4, cudaMemcpyHostToDevice, s.stream));
+    QB_CUDA(ctx, cudaMemcpyAsync(s.d_len, length, (size_t)n_reads * 4, cudaMemcpyHostToDevice, s.stream));
+    qb::BatchView v{s.d_seq, s.d_qual, s.d_off, s.d_len, n_reads, n_bytes, max_len ? max_len : ctx->cfg.len_cap};
+    int rc = launch_batch(ctx, d, v, mate, s.stream);
+    if (rc) return rc;
+  }
+  QB_CUDA(ctx, cudaEventRecord(s.done, s.stream));
+  s.pending = true;
+  return QB_OK;
+}
+
+int qb_submit(qb_ctx *ctx, const qb_batch *b, int mate, uint32_t n_reads, uint64_t n_bytes, uint32_t max_len) {
+  int rc = check_mate(ctx, mate);
+  if (rc) return rc;
+  if (!b || b->device_index < 0 || b->device_index >= (int)ctx->dev.size() || b->slot < 0 ||
+      b->slot >= ctx->cfg.ring_depth)
+    return fail(ctx, QB_ERR_ARG, "bad batch handle");
+  return submit_on(ctx, b->device_index, b->slot, mate, b->seq, b->qual, b->offset, b->length, n_reads, n_bytes,
+                   max_len);
+}
+
+int qb_submit_from(qb_ctx *ctx, int mate, const uint8_t *seq, const uint8_t *qual, const uint32_t *offset,
+                   const uint32_t *length, uint32_t n_reads, uint64_t n_bytes, uint32_t max_len) {
+  int rc = check_mate(ctx, mate);
+  if (rc) return rc;
+  int di, si;
+  rc = take_slot(ctx, &di, &si);
+  if (rc) return rc;
+  return submit_on(ctx, di, si, mate, seq, qual, offset, length, n_reads, n_bytes, max_len);
+}
+
+int qb_accumulate_host(qb_ctx *ctx, int mate, const uint8_t *seq, const uint8_t *qual, const uint32_t *offset,
+                       const uint32_t *length, uint64_t n_reads) {
+  int rc = check_mate(ctx, mate);
+  if (rc) return rc;
+  uint64_t r0 = 0;
+  while (r0 < n_reads) {
+    qb_batch b;
+    rc = qb_acquire(ctx, &b);
+    if (rc) return rc;
+    const uint64_t base = offset[r0];
+    uint64_t r1 = r0, end = base;
+    uint32_t max_len = 0;
+    while (r1 < n_reads && r1 - r0 < b.cap_reads) {
+      const uint64_t o = offset[r1], l = length[r1];
+      if (o < end) return fail(ctx, QB_ERR_LAYOUT, "offsets must be ascending and reads must not overlap (read %llu)",
+                               (unsigned long long)r1);
+      if (l > ctx->cfg.len_cap)
+        return fail(ctx, QB_ERR_CAPACITY, "read %llu has length %llu > len_cap %u", (unsigned long long)r1,
+                    (unsigned long long)l, ctx->cfg.len_cap);
+      if (o + l - base > b.cap_bytes) break;
+      b.offset[r1 - r0] = (uint32_t)(o - base);
+      b.length[r1 - r0] = (uint32_t)l;
+      if (l > max_len) max_len = (uint32_t)l;
+      end = o + l;
+      r1++;
+    }
+    if (r1 == r0) return fail(ctx, QB_ERR_CAPACITY, "read %llu does not fit an empty slot", (unsigned long long)r0);
+    memcpy(b.seq, seq + base, end - base);
+    memcpy(b.qual, qual + base, end - base);
+    rc = qb_submit(ctx, &b, mate, (uint32_t)(r1 - r0), end - base, max_len);
+    if (rc) return rc;
+    r0 = r1;
+  }
+  return QB_OK;
+}
+
+int qb_sync(qb_ctx *ctx) {
+  if (!ctx) return QB_ERR_ARG;
+  for (Device &d : ctx->dev) {
+    QB_CUDA(ctx, cudaSetDevice(d.id));
+    for (Slot &s : d.slots) {
+      QB_CUDA(ctx, cudaStreamSynchronize(s.stream));
+      s.pending = false;
+    }
+    QB_CUDA(ctx, cudaStreamSynchronize(d.main_stream));
+  }
+  return QB_OK;
+}
+
+int qb_reset(qb_ctx *ctx, int mate) {
+  int rc = check_mate(ctx, mate);
+  if (rc) return rc;
+  rc = qb_sync(ctx);
+  if (rc) return rc;
+  for (Device &d : ctx->dev) {
+    QB_CUDA(ctx, cudaSetDevice(d.id));
+    QB_CUDA(ctx, cudaMemset(d.acc[mate], 0, ctx->acc_u64 * 8));
+  }
+  return QB_OK;
+}
+
+int qb_nccl_unique_id(uint8_t id_out[QB_NCCL_ID_BYTES]) {
+  static_assert(sizeof(ncclUniqueId) == QB_NCCL_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  NcclApi *nc = nccl_api();
+  if (!nc || nc->GetUniqueId(&id) != ncclSuccess) return QB_ERR_NCCL;
+  memcpy(id_out, &id, sizeof id);
+  return QB_OK;
+}
+
+int qb_comm_init_rank(qb_ctx *ctx, int n_ranks, int rank, const uint8_t id_in[QB_NCCL_ID_BYTES]) {
+  if (!ctx || !id_in || n_ranks < 1 || rank < 0 || rank >= n_ranks) return QB_ERR_ARG;
+  if (ctx->dev.size() != 1) return fail(ctx, QB_ERR_ARG, "qb_comm_init_rank needs a one-device context per rank");
+  ncclUniqueId id;
+  memcpy(&id, id_in, sizeof id);
+  NcclApi *nc = nccl_api();
+  if (!nc) return fail(ctx, QB_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  QB_CUDA(ctx, cudaSetDevice(ctx->dev[0].id));
+  QB_NCCL(ctx, nc->CommInitRank(&ctx->rank_comm, n_ranks, id, rank));
+  ctx->n_ranks = n_ranks;
+  ctx->rank = rank;
+  return QB_OK;
+}
+
+int qb_finish(qb_ctx *ctx, int mate, uint64_t *rows_out, uint64_t rows_cap, uint64_t *max_length,
+              uint64_t *n_reads) {
+  int rc = check_mate(ctx, mate);
+  if (rc) return rc;
+  rc = qb_sync(ctx);
+  if (rc) return rc;
+  Device &root = ctx->dev[0];
+  const unsigned long long *src = root.acc[mate];
+  if (ctx->dev.size() > 1) {
+    // one grouped ncclReduce of [rows | counters] from every device of this process to device 0
+    NcclApi *nc = nccl_api();
+    QB_NCCL(ctx, nc->GroupStart());
+    for (Device &d : ctx->dev)
+      QB_NCCL(ctx, nc->Reduce(d.acc[mate], d.reduce_buf, ctx->acc_u64, ncclUint64, ncclSum, 0, d.comm, d.main_stream));
+    QB_NCCL(ctx, nc->GroupEnd());
+    for (Device &d : ctx->dev) {
+      QB_CUDA(ctx, cudaSetDevice(d.id));
+      QB_CUDA(ctx, cudaStreamSynchronize(d.main_stream));
+    }
+    src = root.reduce_buf;
+  }
+  QB_CUDA(ctx, cudaSetDevice(root.id));
+  if (ctx->rank_comm && ctx->n_ranks > 1) {
+    // one ncclReduce across the ranks (one process per GPU) to rank 0, over NVLink/NVSwitch
+    QB_NCCL(ctx, nccl_api()->Reduce(src, root.reduce_buf, ctx->acc_u64, ncclUint64, ncclSum, 0, ctx->rank_comm,
+                                    root.main_stream));
+    QB_CUDA(ctx, cudaStreamSynchronize(root.main_stream));
+    if (ctx->rank == 0) src = root.reduce_buf;
+  }
+  QB_CUDA(ctx, cudaMemcpyAsync(ctx->h_result, src, ctx->acc_u64 * 8, cudaMemcpyDeviceToHost, root.main_stream));
+  QB_CUDA(ctx, cudaStreamSynchronize(root.main_stream));
+
+  const uint32_t cap = ctx->cfg.len_cap;
+  unsigned long long *rows = ctx->h_result;
+  const unsigned long long *cnt = rows + (size_t)cap * qb::kRow;
+  if (cnt[qb::kCntError])
+    return fail(ctx, QB_ERR_CAPACITY, "%llu tile(s)/read(s) exceeded len_cap or the batch layout rules; result invalid",
+                cnt[qb::kCntError]);
+  uint64_t ml = 0;
+  for (uint32_t i = 0; i < cap; i++)
+    if (rows[(size_t)i * qb::kRow + qb::kColLength]) ml = i + 1;  // quack.c:194-198, derived
+  if (!ctx->cfg.adapters_enabled && ml > 10) {
+    // no -a: the reference counts kmer_count[10] once per read longer than 10 (quack.c:210-217)
+    unsigned long long k = 0;
+    for (uint64_t i = 10; i < ml; i++) k += rows[(size_t)i * qb::kRow + qb::kColLength];
+    rows[(size_t)10 * qb::kRow + qb::kColKmer] = k;
+  }
+  if (max_length) *max_length = ml;
+  if (n_reads) *n_reads = cnt[qb::kCntReads];
+  if (rows_out) {
+    if (ml > rows_cap) return fail(ctx, QB_ERR_CAPACITY, "rows_out holds %llu rows, need %llu",
+                                   (unsigned long long)rows_cap, (unsigned long long)ml);
+    memcpy(rows_out, rows, (size_t)ml * qb::kRow * 8);
+  }
+  return QB_OK;
+}
+
+int qb_invalid_quality_count(qb_ctx *ctx, int mate, uint64_t *out) {
+  int rc = check_mate(ctx, mate);
+  if (rc) return rc;
+  rc = qb_sync(ctx);
+  if (rc) return rc;
+  unsigned long long total = 0;
+  for (Device &d : ctx->dev) {
+    unsigned long long v = 0;
+    QB_CUDA(ctx, cudaSetDevice(d.id));
+    QB_CUDA(ctx, cudaMemcpy(&v, d.acc[mate] + (size_t)ctx->cfg.len_cap * qb::kRow + qb::kCntInvalidQual, 8,
+                            cudaMemcpyDeviceToHost));
+    total += v;
+  }
+  *out = total;
+  return QB_OK;
+}
+
+uint64_t qb_launch_count(const qb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------- device-resident batches
+
+static int dbatch_alloc(qb_ctx *ctx, int di, uint32_t n_reads, uint64_t n_bytes, qb_dbatch **out) {
+  if (di < 0 || di >= (int)ctx->dev.size()) return fail(ctx, QB_ERR_ARG, "device_index %d out of range", di);
+  if (n_bytes > 0xFFFFFF00ull - 64) return fail(ctx, QB_ERR_CAPACITY, "a batch must stay below 4 GiB (u32 offsets)");
+  Device &d = ctx->dev[di];
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  qb_dbatch *b = new qb_dbatch();
+  memset(b, 0, sizeof *b);
+  b->device_index = di;
+  b->n_reads = n_reads;
+  b->n_bytes = n_bytes;
+  cudaError_t e;
+  if ((e = cudaMalloc(&b->d_seq, pad_bytes(n_bytes))) != cudaSuccess ||
+      (e = cudaMalloc(&b->d_qual, pad_bytes(n_bytes))) != cudaSuccess ||
+      (e = cudaMalloc(&b->d_off, pad_reads(n_reads) * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&b->d_len, pad_reads(n_reads) * 4)) != cudaSuccess) {
+    qb_dbatch_free(ctx, b);
+    return fail(ctx, QB_ERR_NOMEM, "cudaMalloc for a device batch failed: %s", cudaGetErrorString(e));
+  }
+  QB_CUDA(ctx, cudaMemset(b->d_seq + (n_bytes & ~15ull), 0, pad_bytes(n_bytes) - (n_bytes & ~15ull)));
+  QB_CUDA(ctx, cudaMemset(b->d_qual + (n_bytes & ~15ull), 0, pad_bytes(n_bytes) - (n_bytes & ~15ull)));
+  QB_CUDA(ctx, cudaMemset(b->d_off, 0, pad_reads(n_reads) * 4));
+  QB_CUDA(ctx, cudaMemset(b->d_len, 0, pad_reads(n_reads) * 4));
+  *out = b;
+  return QB_OK;
+}
+
+int qb_dbatch_upload(qb_ctx *ctx, int device_index, const uint8_t *seq, const uint8_t *qual, const uint32_t *offset,
+                     const uint32_t *length, uint32_t n_reads, uint64_t n_bytes, uint32_t max_len, qb_dbatch **out) {
+  if (!ctx || !out) return QB_ERR_ARG;
+  qb_dbatch *b = nullptr;
+  int rc = dbatch_alloc(ctx, device_index, n_reads, n_bytes, &b);
+  if (rc) return rc;
+  b->max_len = max_len ? max_len : ctx->cfg.len_cap;
+  if (n_bytes) {
+    QB_CUDA(ctx, cudaMemcpy(b->d_seq, seq, n_bytes, cudaMemcpyHostToDevice));
+    QB_CUDA(ctx, cudaMemcpy(b->d_qual, qual, n_bytes, cudaMemcpyHostToDevice));
+  }
+  if (n_reads) {
+    QB_CUDA(ctx, cudaMemcpy(b->d_off, offset, (size_t)n_reads * 4, cudaMemcpyHostToDevice));
+    QB_CUDA(ctx, cudaMemcpy(b->d_len, length, (size_t)n_reads * 4, cudaMemcpyHostToDevice));
+  }
+  *out = b;
+  return QB_OK;
+}
+
+int qb_dbatch_generate(qb_ctx *ctx, int device_index, uint64_t seed, int mate, uint64_t first_read, uint32_t n_reads,
+                       uint32_t len_min, uint32_t len_max, double adapter_rate, qb_dbatch **out) {
+  if (!ctx || !out || len_min == 0 || len_max < len_min) return QB_ERR_ARG;
+  // lengths first (they fix the byte count), then generate in host chunks and upload
+  uint64_t total = 0;
+  for (uint32_t r = 0; r < n_reads; r++) total += qb::gen_length(seed, first_read + r, len_min, len_max);
+  qb_dbatch *b = nullptr;
+  int rc = dbatch_alloc(ctx, device_index, n_reads, total, &b);
+  if (rc) return rc;
+  b->max_len = len_max;
+  const uint32_t chunk = 1u << 20;
+  uint8_t *hs = (uint8_t *)qb_host_alloc((size_t)chunk * len_max), *hq = (uint8_t *)qb_host_alloc((size_t)chunk * len_max);
+  uint32_t *ho = (uint32_t *)qb_host_alloc((size_t)chunk * 4), *hl = (uint32_t *)qb_host_alloc((size_t)chunk * 4);
+  if (!hs || !hq || !ho || !hl) {
+    qb_host_free(hs), qb_host_free(hq), qb_host_free(ho), qb_host_free(hl);
+    qb_dbatch_free(ctx, b);
+    return fail(ctx, QB_ERR_NOMEM, "pinned staging allocation failed");
+  }
+  uint64_t base = 0;
+  for (uint32_t r0 = 0; r0 < n_reads && rc == QB_OK; r0 += chunk) {
+    const uint32_t n = n_reads - r0 < chunk ? n_reads - r0 : chunk;
+    uint64_t nb = 0;
+    rc = qb_gen_reads(seed, mate, first_read + r0, n, len_min, len_max, adapter_rate, hs, hq, ho, hl, &nb);
+    if (rc) break;
+    for (uint32_t i = 0; i < n; i++) ho[i] += (uint32_t)base;
+    if (cudaMemcpy(b->d_seq + base, hs, nb, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(b->d_qual + base, hq, nb, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(b->d_off + r0, ho, (size_t)n * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(b->d_len + r0, hl, (size_t)n * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+      rc = fail(ctx, QB_ERR_CUDA, "upload of generated reads failed: %s", cudaGetErrorString(cudaGetLastError()));
+    base += nb;
+  }
+  qb_host_free(hs), qb_host_free(hq), qb_host_free(ho), qb_host_free(hl);
+  if (rc) {
+    qb_dbatch_free(ctx, b);
+    return rc;
+  }
+  *out = b;
+  return QB_OK;
+}
+
+int qb_dbatch_info(const qb_dbatch *b, uint32_t *n_reads, uint64_t *n_bytes) {
+  if (!b) return QB_ERR_ARG;
+  if (n_reads) *n_reads = b->n_reads;
+  if (n_bytes) *n_bytes = b->n_bytes;
+  return QB_OK;
+}
+
+void qb_dbatch_free(qb_ctx *ctx, qb_dbatch *b) {
+  if (!b) return;
+  if (ctx && b->device_index >= 0 && b->device_index < (int)ctx->dev.size()) cudaSetDevice(ctx->dev[b->device_index].id);
+  cudaFree(b->d_seq);
+  cudaFree(b->d_qual);
+  cudaFree(b->d_off);
+  cudaFree(b->d_len);
+  delete b;
+}
+
+int qb_dbatch_run(qb_ctx *ctx, qb_dbatch *b, int mate) {
+  int rc = check_mate(ctx, mate);
+  if (rc) return rc;
+  if (!b) return QB_ERR_ARG;
+  Device &d = ctx->dev[b->device_index];
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  qb::BatchView v{b->d_seq, b->d_qual, b->d_off, b->d_len, b->n_reads, b->n_bytes, b->max_len};
+  return launch_batch(ctx, d, v, mate, d.main_stream);
+}
+
+int qb_dbatch_time(qb_ctx *ctx, qb_dbatch *b, int mate, int warmup, int iters, int flush_l2, float *ms_avg,
+                   float *ms_min) {
+  int rc = check_mate(ctx, mate);
+  if (rc) return rc;
+  if (!b || iters < 1) return QB_ERR_ARG;
+  Device &d = ctx->dev[b->device_index];
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  if (flush_l2 && !d.l2_scratch) {
+    d.l2_words = (256ull << 20) / 4;  // 256 MiB > 126 MB of L2
+    QB_CUDA(ctx, cudaMalloc(&d.l2_scratch, d.l2_words * 4));
+  }
+  cudaEvent_t e0, e1;
+  QB_CUDA(ctx, cudaEventCreate(&e0));
+  QB_CUDA(ctx, cudaEventCreate(&e1));
+  for (int i = 0; i < warmup; i++)
+    if ((rc = qb_dbatch_run(ctx, b, mate))) return rc;
+  QB_CUDA(ctx, cudaStreamSynchronize(d.main_stream));
+  double sum = 0;
+  float best = 1e30f;
+  for (int i = 0; i < iters; i++) {
+    if (flush_l2) QB_CUDA(ctx, qb::launch_l2_flush(d.l2_scratch, d.l2_words, d.main_stream));
+    QB_CUDA(ctx, cudaEventRecord(e0, d.main_stream));
+    if ((rc = qb_dbatch_run(ctx, b, mate))) return rc;
+    QB_CUDA(ctx, cudaEventRecord(e1, d.main_stream));
+    QB_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0;
+    QB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    sum += ms;
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_avg) *ms_avg = (float)(sum / iters);
+  if (ms_min) *ms_min = best;
+  return QB_OK;
+}
+
+int qb_measure_h2d(qb_ctx *ctx, int device_index, uint64_t bytes, int iters, double *gbs) {
+  if (!ctx || !gbs || device_index < 0 || device_index >= (int)ctx->dev.size() || bytes == 0) return QB_ERR_ARG;
+  Device &d = ctx->dev[device_index];
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  void *h = nullptr, *dv = nullptr;
+  QB_CUDA(ctx, cudaHostAlloc(&h, bytes, cudaHostAllocDefault));
+  memset(h, 1, bytes);
+  QB_CUDA(ctx, cudaMalloc(&dv, bytes));
+  cudaEvent_t e0, e1;
+  QB_CUDA(ctx, cudaEventCreate(&e0));
+  QB_CUDA(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int i = 0; i < iters + 1; i++) {
+    QB_CUDA(ctx, cudaEventRecord(e0, d.main_stream));
+    QB_CUDA(ctx, cudaMemcpyAsync(dv, h, bytes, cudaMemcpyHostToDevice, d.main_stream));
+    QB_CUDA(ctx, cudaEventRecord(e1, d.main_stream));
+    QB_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms;
+    QB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (i > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dv);
+  cudaFreeHost(h);
+  *gbs = (double)bytes / (best * 1e-3) / 1e9;
+  return QB_OK;
+}
+
+// tools: shared-memory pipe microbenchmarks (not part of the documented boundary)
+int qb_microbench(char *report, size_t cap) {
+  int sm = 0;
+  if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0) != cudaSuccess) return QB_ERR_CUDA;
+  return qb::run_microbench(sm, report, cap) == cudaSuccess ? QB_OK : QB_ERR_CUDA;
+}
+
+// tools: the filter parameters chosen for the adapter set (false-positive rate over all 2^20 keys)
+int qb_adapter_filter_info(const qb_ctx *ctx, uint32_t *mul, double *fp_rate) {
+  if (!ctx) return QB_ERR_ARG;
+  if (mul) *mul = ctx->bloom_mul;
+  if (fp_rate) *fp_rate = ctx->bloom_fp;
+  return QB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,194 @@
+// qb_host.cpp -- host-side helpers behind the C-ABI that need no CUDA: the base code table,
+// adapter key extraction (read_adapters(), reference quack.c:154-178), the Bloom/bitmap images the
+// kernels consume, and the deterministic synthetic read generator.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/quack_b200.h"
+#include "qb_host.h"
+
+extern "C" int qb_base_code(int c) {
+  const unsigned b = (unsigned)c & 0xFFu;
+  // lookup[(c-65)&~32], quack.c:150: C->2, G->3, T->1, every other letter A..T (incl. N) -> 0;
+  // the same bit tests define the bytes the reference leaves undefined.
+  const int cg = (b & 0x5Bu) == 0x43u;
+  const int lo = (b & 0x1Fu) == 0x07u || (b & 0x1Fu) == 0x14u;
+  return 2 * cg + lo;
+}
+
+extern "C" int qb_adapter_record_keys(const char *seq, size_t l, uint32_t *keys, size_t cap) {
+  // quack.c:165-172: pack bases 0..9 (not inserted), then roll in base i = 10..l-1 and insert
+  if (l <= QB_KMER_SIZE) return 0;
+  if (l - QB_KMER_SIZE > cap) return QB_ERR_CAPACITY;
+  uint32_t index = 0;
+  size_t i, n = 0;
+  for (i = 0; i < QB_KMER_SIZE; i++)
+    index = ((index << 2) + (uint32_t)qb_base_code((unsigned char)seq[i])) & (QB_KEY_SPACE - 1);
+  for (; i < l; i++) {
+    index = ((index << 2) + (uint32_t)qb_base_code((unsigned char)seq[i])) & (QB_KEY_SPACE - 1);
+    keys[n++] = index;
+  }
+  return (int)n;
+}
+
+namespace qb {
+
+uint32_t key_to_internal(uint32_t ref_key) {
+  // reference order: first base in bits 19:18; kernel order: first base in bits 1:0
+  uint32_t k = 0;
+  for (int i = 0; i < QB_KMER_SIZE; i++) k |= ((ref_key >> (2 * (QB_KMER_SIZE - 1 - i))) & 3u) << (2 * i);
+  return k;
+}
+
+static inline uint32_t bw_index(uint32_t p) { return (p >> 7) & 255u; }
+
+void build_adapter_images(const uint32_t *ref_keys, uint32_t n, std::vector<uint32_t> &bitmap,
+                          std::vector<uint32_t> &bloom, uint32_t &mul, double &fp_rate) {
+  bitmap.assign(QB_KEY_SPACE / 32, 0);
+  std::vector<uint32_t> keys;
+  keys.reserve(n);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t k = key_to_internal(ref_keys[i] & (QB_KEY_SPACE - 1));
+    if (!((bitmap[k >> 5] >> (k & 31)) & 1u)) {
+      bitmap[k >> 5] |= 1u << (k & 31);
+      keys.push_back(k);
+    }
+  }
+  // pick the multiplier with the fewest false positives over the whole key space (2^20 probes each)
+  static const uint32_t cand[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u,
+                                  0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
+  uint32_t best_mul = cand[0];
+  uint64_t best_fp = ~0ull;
+  std::vector<uint32_t> words(256), best_words(256);
+  for (uint32_t m : cand) {
+    std::fill(words.begin(), words.end(), 0u);
+    for (uint32_t k : keys) {
+      const uint32_t p = k * m;
+      words[bw_index(p)] |= (1u << (k & 31u)) | (1u << ((p >> 15) & 31u));
+    }
+    uint64_t fp = 0;
+    for (uint32_t k = 0; k < QB_KEY_SPACE; k++) {
+      const uint32_t p = k * m;
+      const uint32_t w = words[bw_index(p)];
+      if (((w >> (k & 31u)) & (w >> ((p >> 15) & 31u)) & 1u) && !((bitmap[k >> 5] >> (k & 31)) & 1u)) fp++;
+    }
+    if (fp < best_fp) {
+      best_fp = fp;
+      best_mul = m;
+      best_words = words;
+    }
+  }
+  mul = best_mul;
+  fp_rate = (double)best_fp / (double)QB_KEY_SPACE;
+  bloom.resize(256 * 32);
+  for (uint32_t w = 0; w < 256; w++)
+    for (uint32_t b = 0; b < 32; b++) bloom[w * 32 + b] = best_words[w];  // one copy per bank
+}
+
+// ------------------------------------------------------------------ synthetic reads
+
+static inline uint64_t splitmix64(uint64_t &x) {
+  uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+struct Xoshiro {
+  uint64_t s[4];
+  static inline uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+  inline uint64_t next() {  // xoshiro256**
+    const uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+    s[2] ^= s[0];
+    s[3] ^= s[1];
+    s[1] ^= s[2];
+    s[0] ^= s[3];
+    s[2] ^= t;
+    s[3] = rotl(s[3], 45);
+    return r;
+  }
+};
+
+static inline Xoshiro seed_read(uint64_t seed, uint64_t stream, uint64_t i) {
+  uint64_t x = seed * 0xD1342543DE82EF95ull + stream * 0xA24BAED4963EE407ull + i * 0x9FB21C651E98DF25ull + 1;
+  Xoshiro g;
+  for (int k = 0; k < 4; k++) g.s[k] = splitmix64(x);
+  return g;
+}
+
+static const char kAdapterR1[] = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT";  // TruSeq2_PE_f
+static const char kAdapterR2[] = "AGATCGGAAGAGCGGTTCAGCAGGAATGCCGAG";  // TruSeq2_PE_r
+
+uint32_t gen_length(uint64_t seed, uint64_t i, uint32_t len_min, uint32_t len_max) {
+  if (len_max <= len_min) return len_min;
+  Xoshiro g = seed_read(seed, 7, i);  // shared by both mates
+  return len_min + (uint32_t)(g.next() % (uint64_t)(len_max - len_min + 1));
+}
+
+void gen_one(uint64_t seed, int mate, uint64_t i, uint32_t len, uint32_t len_max, double adapter_rate,
+             uint8_t *seq, uint8_t *qual) {
+  Xoshiro g = seed_read(seed, 100 + (uint64_t)mate, i);
+  // bases: uniform ACGT, 1/1024 N
+  for (uint32_t p = 0; p < len; p += 4) {
+    uint64_t r = g.next();
+    for (uint32_t k = 0; k < 4 && p + k < len; k++, r >>= 16)
+      seq[p + k] = ((r >> 2) & 1023u) == 0 ? 'N' : "ACGT"[r & 3u];
+  }
+  // read-through: the pair decision and insert size come from the pair stream (same for both mates)
+  if (adapter_rate > 0 && len > 21) {
+    Xoshiro pg = seed_read(seed, 9, i);
+    const double u = (double)(pg.next() >> 11) * (1.0 / 9007199254740992.0);
+    if (u < adapter_rate) {
+      const uint32_t s = 20 + (uint32_t)(pg.next() % (uint64_t)(len - 20));
+      const char *ad = mate == 2 ? kAdapterR2 : kAdapterR1;
+      const uint32_t al = (uint32_t)strlen(ad);
+      for (uint32_t p = s; p < len; p++) seq[p] = (p - s < al) ? (uint8_t)ad[p - s] : 'A';
+    }
+  }
+  // quality: mean 38 - 10 (p/L)^2 (2 lower for mate 2), sigma 4 (Irwin-Hall of 4 uniforms), Phred [2,41]
+  const double L = (double)len_max, m0 = mate == 2 ? 36.0 : 38.0;
+  for (uint32_t p = 0; p < len; p++) {
+    const uint64_t r = g.next();
+    const double z = ((double)(r & 0xFFFF) + (double)((r >> 16) & 0xFFFF) + (double)((r >> 32) & 0xFFFF) +
+                      (double)(r >> 48) - 131070.0) * (1.0 / 37837.23);  // sd of the sum = 65536/sqrt(3)
+    const double x = (double)p / L;
+    double q = std::floor(m0 - 10.0 * x * x + 4.0 * z + 0.5);
+    if (q < 2.0) q = 2.0;
+    if (q > 41.0) q = 41.0;
+    qual[p] = (uint8_t)(33 + (int)q);
+  }
+}
+
+}  // namespace qb
+
+extern "C" int qb_gen_reads(uint64_t seed, int mate, uint64_t first_read, uint32_t n_reads, uint32_t len_min,
+                            uint32_t len_max, double adapter_rate, uint8_t *seq, uint8_t *qual, uint32_t *offset,
+                            uint32_t *length, uint64_t *n_bytes) {
+  if (!seq || !qual || !offset || !length || len_min == 0 || len_max < len_min) return QB_ERR_ARG;
+  uint64_t o = 0;
+  for (uint32_t r = 0; r < n_reads; r++) {
+    const uint32_t l = qb::gen_length(seed, first_read + r, len_min, len_max);
+    if (o + l > 0xFFFFFF00ull) return QB_ERR_CAPACITY;
+    offset[r] = (uint32_t)o;
+    length[r] = l;
+    o += l;
+  }
+  if (n_bytes) *n_bytes = o;
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 4;
+  if (nt > 64) nt = 64;
+  if (n_reads < 4096) nt = 1;
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++) {
+    const uint32_t a = (uint32_t)((uint64_t)n_reads * t / nt), b = (uint32_t)((uint64_t)n_reads * (t + 1) / nt);
+    th.emplace_back([=]() {
+      for (uint32_t r = a; r < b; r++)
+        qb::gen_one(seed, mate, first_read + r, length[r], len_max, adapter_rate, seq + offset[r], qual + offset[r]);
+    });
+  }
+  for (auto &t : th) t.join();
+  return QB_OK;
+}

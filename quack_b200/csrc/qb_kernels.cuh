@@ -1,0 +1,87 @@
+// qb_kernels.cuh -- internal interface between the C-ABI layer (qb_api.cu) and the sm_100a
+// kernels (qb_kernels.cu).  Not installed; the public boundary is include/quack_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qb {
+
+constexpr int kRow = 97;             // base_information as u64[97], quack.c:134-139
+constexpr int kColContent = 91;
+constexpr int kColLength = 95;
+constexpr int kColKmer = 96;
+constexpr uint32_t kNoHit = 0xFFFFFFFFu;
+
+// counters[] slots (u64, per mate)
+constexpr int kCntReads = 0;         // number_of_sequences, quack.c:220
+constexpr int kCntInvalidQual = 1;   // quality bytes outside [33,123] (UB in the reference)
+constexpr int kCntError = 2;         // != 0: a tile/read exceeded capacity (results invalid)
+constexpr int kNumCounters = 4;
+
+// ---- adapter set as the kernels see it -------------------------------------------------
+// Internal key order: first base of the window LEAST significant (2 bits per base, codes
+// A0 T1 C2 G3).  The public API takes the reference order (first base most significant);
+// qb_api.cu converts.
+constexpr uint32_t kBloomWords = 256;          // words per bank copy (power of two)
+constexpr uint32_t kBloomBytes = kBloomWords * 32 * 4;  // 32 KiB, one copy per shared-memory bank
+
+struct AdapterSet {
+  const uint32_t *bitmap;  // exact membership, 2^20 bits, device global (stays in L2)
+  const uint32_t *bloom;   // [kBloomWords][32] blocked Bloom filter, bank-replicated, device global
+  uint32_t bloom_mul;      // odd multiplier M: p = key * M
+  int enabled;             // 0: no -a (kmer_count handled at finish)
+};
+
+__host__ __device__ inline uint32_t bloom_word_index(uint32_t p) { return (p >> 7) & (kBloomWords - 1); }
+__host__ __device__ inline uint32_t bloom_bit1(uint32_t key) { return key & 31u; }
+__host__ __device__ inline uint32_t bloom_bit2(uint32_t p) { return (p >> 15) & 31u; }
+
+// ---- one batch in device memory ---------------------------------------------------------
+struct BatchView {
+  const uint8_t *seq;      // padded: readable up to round_up(n_bytes,16)+16
+  const uint8_t *qual;
+  const uint32_t *offset;  // padded to a multiple of 4 entries (+4)
+  const uint32_t *length;
+  uint32_t n_reads;
+  uint64_t n_bytes;
+  uint32_t max_len;        // longest read in the batch (upper bound)
+};
+
+struct Accum {
+  unsigned long long *rows;      // [len_cap][97]
+  unsigned long long *counters;  // [kNumCounters]
+  uint32_t len_cap;
+};
+
+// ---- fused kernel geometry (computed on the host, see fused_plan) ------------------------
+struct FusedPlan {
+  uint32_t half_len;        // Lh: positions [0,Lh) count in the low u16, [Lh,2Lh) in the high u16
+  uint32_t tile_bytes;      // capacity of one stage buffer (seq or qual), multiple of 16
+  uint32_t reads_per_tile;  // multiple of 4, <= kMaxTileReads
+  uint32_t stages;
+  uint32_t qbase;           // score field s' = q - qbase, s' in [1,63] counted in shared memory
+  uint32_t smem_bytes;
+  uint32_t grid;
+  int ok;                   // 0: len_cap does not fit -> use the simple kernel
+};
+
+constexpr uint32_t kMaxTileReads = 256;
+constexpr int kFusedConsumerWarps = 31;  // + 1 producer warp = 1024 threads, 1 CTA per SM
+
+FusedPlan fused_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int sm_count,
+                     uint32_t smem_optin, uint32_t qbase);
+
+cudaError_t launch_simple(const BatchView &b, const Accum &a, const AdapterSet &ad, int sm_count,
+                          cudaStream_t stream);
+cudaError_t launch_fused(const BatchView &b, const Accum &a, const AdapterSet &ad, const FusedPlan &plan,
+                         cudaStream_t stream);
+cudaError_t fused_configure();  // opt in to the large dynamic shared memory once per device
+
+// L2 flush helper for timing (writes `bytes` of scratch)
+cudaError_t launch_l2_flush(uint32_t *scratch, size_t words, cudaStream_t stream);
+
+// Microbenchmarks of the shared-memory pipes the fused kernel leans on (tools/microbench).
+cudaError_t run_microbench(int sm_count, char *report, size_t report_cap);
+
+}  // namespace qb

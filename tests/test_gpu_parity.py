@@ -1,0 +1,205 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle: bit-exact count arrays.
+
+Every test here needs a B200; run with `pytest -m gpu`.  The oracle is the checker only.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from quack_b200 import capi
+import qb_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [capi.KERNEL_SIMPLE, capi.KERNEL_FUSED]
+KNAME = {capi.KERNEL_SIMPLE: "simple", capi.KERNEL_FUSED: "fused"}
+
+
+@pytest.fixture(scope="module")
+def table():
+    return util.oracle_table()
+
+
+@pytest.fixture(scope="module")
+def keys(table):
+    return table.keys()
+
+
+def run_gpu(batch, len_cap, keys, kernel, resident=False, **kw):
+    seq, qual, off, lens = batch
+    with capi.Context(len_cap, adapter_keys=keys, kernel=kernel, **kw) as ctx:
+        if resident:
+            b = ctx.upload(seq, qual, off, lens, max_len=int(lens.max()) if len(lens) else 0)
+            b.run(0)
+            res = ctx.finish(0)
+            b.free()
+        else:
+            ctx.accumulate_host(0, seq, qual, off, lens)
+            res = ctx.finish(0)
+        res.invalid = ctx.invalid_quality_count(0)
+    return res
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
+@pytest.mark.parametrize("name", ["kat_t", "kat_k", "framing", "rand_small"])
+@pytest.mark.parametrize("ad", [False, True], ids=["noad", "ad"])
+def test_golden_fixtures(name, ad, kernel, golden_dir, keys):
+    """Reference-generated raw arrays (tests/golden/golden_raw.npz) reproduced by the kernels."""
+    files = {"kat_t": "kat_t.fq", "kat_k": "kat_k.fq", "framing": "framing.fq", "rand_small": "rand_small.fq.gz"}
+    recs, _ = po.parse_records(os.path.join(golden_dir, files[name]))
+    batch = util.pack(recs)
+    got = run_gpu(batch, 304, keys if ad else None, kernel)
+    gold = np.load(os.path.join(golden_dir, "golden_raw.npz"))
+    ml, n = gold[f"{name}.{'ad' if ad else 'noad'}.meta"]
+    assert (got.max_length, got.n_reads) == (int(ml), int(n))
+    assert np.array_equal(got.rows, gold[f"{name}.{'ad' if ad else 'noad'}.rows"])
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
+@pytest.mark.parametrize("ad", [False, True], ids=["noad", "ad"])
+@pytest.mark.parametrize("resident", [False, True], ids=["stream", "resident"])
+def test_fixed_150(kernel, ad, resident, table, keys):
+    batch = util.random_batch(11, 20000, 150, 150, plant=0.2)
+    got = run_gpu(batch, 150, keys if ad else None, kernel, resident=resident)
+    util.assert_same(got, po.accumulate_batch(*batch, table if ad else None), "fixed150")
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
+@pytest.mark.parametrize("lmin,lmax,cap", [(1, 40, 40), (35, 300, 304), (0, 25, 64), (9, 12, 150), (300, 300, 300)])
+def test_ragged(kernel, lmin, lmax, cap, table, keys):
+    batch = util.random_batch(lmin * 1000 + lmax, 30000, lmin, lmax, plant=0.3)
+    got = run_gpu(batch, cap, keys, kernel)
+    util.assert_same(got, po.accumulate_batch(*batch, table), f"ragged {lmin}-{lmax}")
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
+def test_all_byte_values(kernel, table, keys):
+    """Every byte value in both streams: both sides define the bytes the reference leaves undefined
+    the same way, and count out-of-range quality bytes instead of corrupting neighbours."""
+    rng = np.random.default_rng(5)
+    n, l = 4000, 97
+    seq = rng.integers(0, 256, size=n * l).astype(np.uint8)
+    qual = rng.integers(0, 256, size=n * l).astype(np.uint8)
+    off = (np.arange(n) * l).astype(np.uint32)
+    lens = np.full(n, l, dtype=np.uint32)
+    want = po.accumulate_batch(seq, qual, off, lens, table)
+    got = run_gpu((seq, qual, off, lens), 128, keys, kernel)
+    util.assert_same(got, want, "all bytes")
+    assert got.invalid == want.n_invalid_qual > 0
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
+@pytest.mark.parametrize("qlo,qhi", [(0, 90), (31, 71), (60, 62)], ids=["full", "phred64", "edge"])
+def test_score_ranges(kernel, qlo, qhi, table, keys):
+    """Scores beyond the shared-memory window (Phred > 62, e.g. phred64 files) take the exact slow path."""
+    batch = util.random_batch(77, 8000, 100, 151, qlo=qlo, qhi=qhi)
+    got = run_gpu(batch, 151, keys, kernel)
+    util.assert_same(got, po.accumulate_batch(*batch, table), f"scores {qlo}-{qhi}")
+
+
+def test_adapter_first_hit_every_position(table, keys):
+    """First-hit semantics with the hit planted at every position, two adapters per read
+    (only the first may count), hits ending on the last base (no count) and windows spanning reads."""
+    ad = b"AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT"
+    reads = []
+    for l in (30, 61, 150):
+        for at in range(0, l):
+            s = bytearray(b"C" * l)
+            m = min(len(ad), l - at)
+            s[at: at + m] = ad[:m]
+            if at + 40 < l:
+                s[at + 40: at + 40 + 11] = ad[:11]
+            reads.append((bytes(s), b"I" * l))
+    reads.append((b"CCCCCCCCCCCCGATCGGAAGA", b"I" * 22))       # hit ends on the last base
+    reads.append((b"GATCG", b"IIIII"))                        # window would span into the next read
+    reads.append((b"GAAGACCCCCCCCCCC", b"I" * 16))
+    batch = util.pack(reads)
+    want = po.accumulate_batch(*batch, table)
+    for kernel in KERNELS:
+        util.assert_same(run_gpu(batch, 150, keys, kernel), want, KNAME[kernel])
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
+def test_two_mates_many_small_batches(kernel, table, keys):
+    """Ring of tiny slots: many submits, slot reuse, two independent accumulators."""
+    b1 = util.random_batch(21, 12000, 20, 150, plant=0.1)
+    b2 = util.random_batch(22, 9000, 150, 150, plant=0.1)
+    with capi.Context(150, n_mates=2, adapter_keys=keys, kernel=kernel, batch_bytes=64 << 10, batch_reads=700,
+                      ring_depth=2) as ctx:
+        ctx.accumulate_host(0, *b1)
+        ctx.accumulate_host(1, *b2)
+        ctx.accumulate_host(0, *b2)
+        r0, r1 = ctx.finish(0), ctx.finish(1)
+        assert ctx.launch_count > 30
+    w1, w2 = po.accumulate_batch(*b1, table), po.accumulate_batch(*b2, table)
+    util.assert_same(r1, w2, "mate 1")
+    assert r0.n_reads == w1.n_reads + w2.n_reads and r0.max_length == 150
+    rows = w2.rows.copy()
+    rows[: w1.max_length] += w1.rows
+    assert np.array_equal(r0.rows, rows)
+
+
+def test_u16_flush_path(table, keys, monkeypatch):
+    """More than 65535 reads through one CTA forces the mid-launch flush of the packed u16 counters."""
+    monkeypatch.setenv("QB_FUSED_GRID", "2")
+    batch = util.random_batch(31, 300000, 30, 50, plant=0.05)
+    got = run_gpu(batch, 64, keys, capi.KERNEL_FUSED, resident=True)
+    util.assert_same(got, po.accumulate_batch(*batch, table), "flush")
+
+
+def test_linearity_and_generator_full_size(keys, table):
+    """Config-2 shape at a size the oracle cannot chew quickly: 2 M generated 150-bp reads.  Checked by
+    properties (running the batch twice doubles every count; per-position content and score sums equal
+    the number of reads that long) and against the oracle on the first 100 k reads."""
+    n = 2_000_000
+    with capi.Context(150, adapter_keys=keys, kernel=capi.KERNEL_FUSED) as ctx:
+        b = ctx.generate(2, 1, 0, n, 150, 150, 0.1)
+        b.run(0)
+        r1 = ctx.finish(0)
+        b.run(0)
+        r2 = ctx.finish(0)
+        b.free()
+        assert r1.n_reads == n and r2.n_reads == 2 * n and r1.max_length == 150
+        assert np.array_equal(r2.rows, 2 * r1.rows)
+        assert np.all(r1.rows[:, 91:95].sum(axis=1) == n) and np.all(r1.rows[:, :91].sum(axis=1) == n)
+        assert r1.rows[149, 95] == n
+        # ~10 % planted read-through + ~3.4 % chance hits on random sequence
+        assert 0.10 * n < r1.rows[:, 96].sum() < 0.16 * n
+    seq, qual, off, lens = capi.gen_reads(2, 1, 0, 100_000, 150, 150, 0.1)
+    want = po.accumulate_batch(seq, qual, off, lens, table)
+    for kernel in KERNELS:
+        util.assert_same(run_gpu((seq, qual, off, lens), 150, keys, kernel, resident=True), want, "gen 100k")
+
+
+def test_capacity_errors(keys):
+    batch = util.random_batch(3, 100, 60, 60)
+    with capi.Context(40, adapter_keys=keys) as ctx:
+        with pytest.raises(capi.QbError) as e:
+            ctx.accumulate_host(0, *batch)
+        assert e.value.code == -4
+    with capi.Context(150, adapter_keys=keys) as ctx:     # resident batch bypasses the host check: kernel flags it
+        b = ctx.upload(*batch, max_len=60)
+        ctx2 = capi.Context(40, adapter_keys=keys)
+        b2 = ctx2.upload(*batch, max_len=40)
+        b2.run(0)
+        with pytest.raises(capi.QbError):
+            ctx2.finish(0)
+        b2.free()
+        ctx2.close()
+        b.run(0)
+        assert ctx.finish(0).n_reads == 100
+        b.free()
+
+
+def test_empty_and_reset(keys):
+    with capi.Context(150, adapter_keys=keys) as ctx:
+        r = ctx.finish(0)
+        assert (r.max_length, r.n_reads, r.rows.shape) == (0, 0, (0, 97))
+        batch = util.random_batch(4, 500, 150, 150)
+        ctx.accumulate_host(0, *batch)
+        assert ctx.finish(0).n_reads == 500
+        ctx.reset(0)
+        assert ctx.finish(0).n_reads == 0

@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Development probe (not the judged bench): kernel-only throughput of the simple and fused kernels on
+generated 150-bp reads, with and without the adapter set, plus pinned H2D bandwidth."""
+import json
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from quack_b200 import capi
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import qb_testutil as util
+
+HBM = 6550.1
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
+    keys = np.concatenate([capi.adapter_record_keys(r) for r in util.adapter_records()])
+    out = []
+    for lmin, lmax, cap in ((150, 150, 150), (35, 300, 304)):
+        for ad in (None, keys):
+            for kernel in (capi.KERNEL_FUSED, capi.KERNEL_SIMPLE):
+                nn = n if kernel == capi.KERNEL_FUSED else n // 8
+                with capi.Context(cap, adapter_keys=ad, kernel=kernel) as ctx:
+                    b = ctx.generate(2, 1, 0, nn, lmin, lmax, 0.1)
+                    nr, nb = b.info
+                    avg, mn = b.time(0, warmup=2, iters=5, flush_l2=False)
+                    alg = 2 * nb + 8 * nr
+                    rec = {"len": [lmin, lmax], "adapters": ad is not None,
+                           "kernel": "fused" if kernel == capi.KERNEL_FUSED else "simple", "reads": nr,
+                           "ms_avg": round(avg, 4), "ms_min": round(mn, 4), "Greads_s": round(nr / avg / 1e6, 3),
+                           "Gbases_s": round(nb / avg / 1e6, 2), "GBps": round(alg / avg / 1e6, 1),
+                           "frac_hbm": round(alg / avg / 1e6 / HBM, 4)}
+                    if ad is not None:
+                        rec["bloom"] = ctx.adapter_filter_info()
+                    print(json.dumps(rec), flush=True)
+                    out.append(rec)
+                    b.free()
+    with capi.Context(150) as ctx:
+        print(json.dumps({"h2d_GBps": round(ctx.measure_h2d(256 << 20, 5), 2)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
