@@ -78,7 +78,7 @@ struct Device {
   int smem_optin = 0;
   std::vector<unsigned long long *> acc;  // per mate: [len_cap*97 rows][kNumCounters]
   unsigned long long *reduce_buf = nullptr;
-  uint32_t *d_bitmap = nullptr, *d_bloom = nullptr;
+  uint32_t *d_bitmap = nullptr, *d_bloom = nullptr, *d_exact = nullptr;
   std::vector<Slot> slots;
   cudaStream_t main_stream = nullptr;
   ncclComm_t comm = nullptr;  // in-process communicator (n_devices > 1)
@@ -99,7 +99,7 @@ struct qb_ctx {
   qb::AdapterSet ad_host_template{};
   uint32_t bloom_mul = 0;
   double bloom_fp = 0;
-  uint32_t qbase = 32;
+  uint32_t qbase = 33;  // score bin s = q - qbase, s in [0,62] counted in shared memory
   ncclComm_t rank_comm = nullptr;  // multi-process communicator
   int n_ranks = 1, rank = 0;
   unsigned long long *h_result = nullptr;  // pinned staging for qb_finish
@@ -150,6 +150,7 @@ qb::AdapterSet adapter_set(const qb_ctx *ctx, const Device &d) {
   qb::AdapterSet a;
   a.bitmap = d.d_bitmap;
   a.bloom = d.d_bloom;
+  a.exact = d.d_exact;
   a.bloom_mul = ctx->bloom_mul;
   a.enabled = ctx->cfg.adapters_enabled ? 1 : 0;
   return a;
@@ -242,16 +243,16 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
   ctx->acc_u64 = (size_t)cfg.len_cap * qb::kRow + qb::kNumCounters;
   if (const char *qb_env = getenv("QB_QBASE")) {
     const int v = atoi(qb_env);
-    if (v >= 32 && v <= 63) ctx->qbase = (uint32_t)v;
+    if (v >= 33 && v <= 64) ctx->qbase = (uint32_t)v;
   }
 
-  std::vector<uint32_t> bitmap, bloom;
+  std::vector<uint32_t> bitmap, bloom, exact;
   if (cfg.adapters_enabled) {
     if (cfg.n_adapter_keys && !cfg.adapter_keys) {
       delete ctx;
       return fail(nullptr, QB_ERR_ARG, "adapter_keys is NULL");
     }
-    qb::build_adapter_images(cfg.adapter_keys, cfg.n_adapter_keys, bitmap, bloom, ctx->bloom_mul, ctx->bloom_fp);
+    qb::build_adapter_images(cfg.adapter_keys, cfg.n_adapter_keys, bitmap, bloom, exact, ctx->bloom_mul, ctx->bloom_fp);
   }
 
 #define QB_CREATE_CUDA(call)                                                                          \
@@ -289,6 +290,10 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
       QB_CREATE_CUDA(cudaMemcpy(d.d_bitmap, bitmap.data(), bitmap.size() * 4, cudaMemcpyHostToDevice));
       QB_CREATE_CUDA(cudaMalloc(&d.d_bloom, bloom.size() * 4));
       QB_CREATE_CUDA(cudaMemcpy(d.d_bloom, bloom.data(), bloom.size() * 4, cudaMemcpyHostToDevice));
+      if (!exact.empty()) {
+        QB_CREATE_CUDA(cudaMalloc(&d.d_exact, exact.size() * 4));
+        QB_CREATE_CUDA(cudaMemcpy(d.d_exact, exact.data(), exact.size() * 4, cudaMemcpyHostToDevice));
+      }
     }
     d.slots.resize(cfg.ring_depth);
     for (Slot &s : d.slots) {
@@ -351,6 +356,7 @@ void qb_destroy(qb_ctx *ctx) {
     cudaFree(d.reduce_buf);
     cudaFree(d.d_bitmap);
     cudaFree(d.d_bloom);
+    cudaFree(d.d_exact);
     cudaFree(d.l2_scratch);
     if (d.main_stream) cudaStreamDestroy(d.main_stream);
   }

@@ -9,6 +9,7 @@
 
 #include "../../include/quack_b200.h"
 #include "qb_host.h"
+#include "qb_kernels.cuh"
 
 extern "C" int qb_base_code(int c) {
   const unsigned b = (unsigned)c & 0xFFu;
@@ -46,7 +47,8 @@ uint32_t key_to_internal(uint32_t ref_key) {
 static inline uint32_t bw_index(uint32_t p) { return (p >> 7) & 255u; }
 
 void build_adapter_images(const uint32_t *ref_keys, uint32_t n, std::vector<uint32_t> &bitmap,
-                          std::vector<uint32_t> &bloom, uint32_t &mul, double &fp_rate) {
+                          std::vector<uint32_t> &bloom, std::vector<uint32_t> &exact, uint32_t &mul,
+                          double &fp_rate) {
   bitmap.assign(QB_KEY_SPACE / 32, 0);
   std::vector<uint32_t> keys;
   keys.reserve(n);
@@ -86,6 +88,15 @@ void build_adapter_images(const uint32_t *ref_keys, uint32_t n, std::vector<uint
   bloom.resize(256 * 32);
   for (uint32_t w = 0; w < 256; w++)
     for (uint32_t b = 0; b < 32; b++) bloom[w * 32 + b] = best_words[w];  // one copy per bank
+  exact.clear();
+  if (keys.size() * 3 <= kExactSlots) {
+    exact.assign(kExactSlots, kExactEmpty);
+    for (uint32_t k : keys) {
+      uint32_t i = exact_slot(k);
+      while (exact[i] != kExactEmpty) i = (i + 1u) & (kExactSlots - 1u);
+      exact[i] = k;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ synthetic reads

@@ -153,6 +153,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void consumer_bar() {
   asm volatile("bar.sync 1, %0;" ::"n"(kCThreads) : "memory");
 }
@@ -165,10 +173,19 @@ struct FusedArgs {
   uint32_t n_tiles;
 };
 
+constexpr uint32_t kPadBefore = 16;   // readable bytes in front of a staged buffer (halo lanes, windows)
+constexpr uint32_t kPadAfter = 256;   // readable bytes behind it (last partial warp step)
+constexpr uint32_t kCandCap = 512;    // Bloom-positive candidates queued per tile
+
+struct Candidate {
+  int32_t unit;      // 8-byte unit index in the staged tile
+  uint32_t lo, hi;   // 2-bit codes of the 24 bases ending with this unit's 8 bases (see phase A)
+};
+
 // shared-memory carve-up, all offsets multiples of 16 bytes
 struct SmemLayout {
-  uint32_t hist, bloom, lenhist, kmerhist, kbuf, stage0, stage_stride, seq_off, qual_off, soff_off,
-      slen_off, fhit_off, meta, bars, total;
+  uint32_t hist, bloom, exact, lenhist, kmerhist, cand, stage0, stage_stride, seq_off, qual_off, soff_off, slen_off,
+      fhit_off, meta, bars, total;
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -176,63 +193,164 @@ __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15
 __host__ __device__ inline SmemLayout smem_layout(uint32_t half_len, uint32_t len_cap, uint32_t tile_bytes,
                                                   uint32_t stages, int adapters) {
   SmemLayout L;
+  const uint32_t buf = kPadBefore + tile_bytes + kPadAfter;
   uint32_t o = 0;
   L.hist = o;
   o += 256u * half_len * 4u;
   L.bloom = o;
   o += adapters ? kBloomBytes : 0u;
+  L.exact = o;
+  o += adapters ? kExactSlots * 4u : 0u;
   L.lenhist = o;
   o += align16(len_cap * 4u);
   L.kmerhist = o;
   o += align16(len_cap * 4u);
-  L.kbuf = o;
-  o += tile_bytes + 16u;
+  L.cand = o;
+  o += adapters ? align16(kCandCap * (uint32_t)sizeof(Candidate)) : 0u;
   L.stage0 = o;
-  L.seq_off = 0;
-  L.qual_off = tile_bytes + 16u;
-  L.soff_off = 2u * (tile_bytes + 16u);
+  L.seq_off = kPadBefore;
+  L.qual_off = buf + kPadBefore;
+  L.soff_off = 2u * buf;
   L.slen_off = L.soff_off + kMaxTileReads * 4u;
   L.fhit_off = L.slen_off + kMaxTileReads * 4u;
   L.stage_stride = L.fhit_off + kMaxTileReads * 4u;
   o += stages * L.stage_stride;
   L.meta = o;
-  o += 16u * kMaxStages;  // lo_al, n_reads, span, pad per stage
+  o += 16u * kMaxStages + 16u;  // per stage: lo_al, n_reads, span, pad; then 2 candidate counters
   L.bars = o;
   o += 16u * kMaxStages;  // full, empty per stage
   L.total = o;
   return L;
 }
 
-// phase A arithmetic for one aligned word: returns the 4 key bytes K (code<<6 | s') and, through
-// cc, the 2-bit codes alone in bits 7:6 of each byte.
-//   s' = q - qbase in [1,63] is counted in shared memory; any other quality byte in the word sends
-//   the whole word to the exact slow path of phase H (K = code<<6 | 0, the dummy rows).
-__device__ __forceinline__ uint32_t key_bytes(uint32_t sw, uint32_t qw, uint32_t qsub, uint32_t &cc) {
-  // per byte: bit7 of n_cg is 0 iff (b & 0x5B) == 0x43; bit6 of n_g / n_t is 0 iff (b & 0x1F) == 7 / 0x14
-  const uint32_t n_cg = ((sw & 0x5B5B5B5Bu) ^ 0x43434343u) + 0x7F7F7F7Fu;
-  const uint32_t n_g = ((sw & 0x1F1F1F1Fu) ^ 0x07070707u) + 0x3F3F3F3Fu;
-  const uint32_t n_t = ((sw & 0x1F1F1F1Fu) ^ 0x14141414u) + 0x3F3F3F3Fu;
-  const uint32_t nc = (n_cg & 0x80808080u) | (n_g & n_t & 0x40404040u);
-  cc = nc ^ 0xC0C0C0C0u;
-  const uint32_t qs = qw - qsub;  // a borrow can only start at a byte that is itself out of range
-  return (qs & 0xC0C0C0C0u) ? cc : (qs | cc);
+// three-input logic op with an explicit truth table (a = 0xF0, b = 0xCC, c = 0xAA); constants passed
+// as operands stay in registers, so e.g. (x & A) ^ B is ONE LOP3 instead of two
+template <int kLut>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(kLut));
+  return d;
 }
 
-template <bool kAdapters>
+// loop-invariant SWAR constants, kept in registers
+struct KeyConsts {
+  uint32_t m5b, x43, m1f, x07, x14, a7f, a3f, m80, mc0, one, qsub;
+  __device__ __forceinline__ explicit KeyConsts(uint32_t qbase)
+      : m5b(0x5B5B5B5Bu), x43(0x43434343u), m1f(0x1F1F1F1Fu), x07(0x07070707u), x14(0x14141414u),
+        a7f(0x7F7F7F7Fu), a3f(0x3F3F3F3Fu), m80(0x80808080u), mc0(0xC0C0C0C0u), one(0x01010101u),
+        qsub(qbase * 0x01010101u) {}
+};
+
+// Phase A arithmetic for one aligned word of 4 bases + 4 quality bytes.  Returns the 4 key bytes
+//   K = code << 6 | s,   code = A0 T1 C2 G3 (quack.c:150),   s = q - qbase in [0,62]
+// `nc` gets the inverted codes in bits 7:6 of each byte (other bits undefined); `bad` accumulates
+// qs | (qs + 1), whose bits 7:6 are non-zero iff some quality byte is outside the window: then the
+// caller re-keys the word to s = 63 (rows nobody reads) and counts its 4 bases exactly.
+__device__ __forceinline__ uint32_t key_bytes(uint32_t sw, uint32_t qw, const KeyConsts &c, uint32_t &nc,
+                                              uint32_t &bad) {
+  // per byte: bit7 of n_cg is 0 iff (b & 0x5B) == 0x43; bit6 of n_g / n_t is 0 iff (b & 0x1F) == 7 / 0x14
+  const uint32_t n_cg = lop3<0x6A>(sw, c.m5b, c.x43) + c.a7f;
+  const uint32_t n_g = lop3<0x6A>(sw, c.m1f, c.x07) + c.a3f;
+  const uint32_t n_t = lop3<0x6A>(sw, c.m1f, c.x14) + c.a3f;
+  nc = lop3<0xE4>(n_cg, n_g & n_t, c.m80);  // bit 7 from n_cg, the rest from n_g & n_t
+  // a borrow can only start at a byte that is itself out of range, and that byte ends >= 0xC0
+  const uint32_t qs = qw - c.qsub;
+  bad = lop3<0xFE>(bad, qs, qs + c.one);
+  return lop3<0xF2>(qs, nc, c.mc0);  // qs | (~nc & 0xC0C0C0C0)
+}
+// key bytes of a word that has an out-of-window quality byte: code << 6 | 63
+__device__ __forceinline__ uint32_t key_bytes_bad(uint32_t nc) { return (~nc & 0xC0C0C0C0u) | 0x3F3F3F3Fu; }
+
+__device__ __forceinline__ bool word_bad(uint32_t qw, uint32_t qsub) {
+  const uint32_t qs = qw - qsub;
+  return ((qs | (qs + 0x01010101u)) & 0xC0C0C0C0u) != 0u;
+}
+
+// largest r with soff[r] <= abs (reads of a tile are in ascending offset order), -1 if none
+__device__ __forceinline__ int find_read(const uint32_t *soff, uint32_t nr, uint32_t abs) {
+  int a = 0, b = (int)nr - 1, r = -1;
+  while (a <= b) {
+    const int m = (a + b) >> 1;
+    if (soff[m] <= abs) {
+      r = m;
+      a = m + 1;
+    } else
+      b = m - 1;
+  }
+  return r;
+}
+
+// rare path: the 4 bases of a word with an out-of-window quality byte, counted one by one
+__device__ __noinline__ uint32_t exact_word(uint32_t sw, uint32_t qw, uint32_t abs0, const uint32_t *soff,
+                                            const uint32_t *slen, uint32_t nr, const Accum a) {
+  uint32_t n_invalid = 0;
+  for (uint32_t j = 0; j < 4; j++) {
+    const uint32_t abs = abs0 + j;
+    const int r = find_read(soff, nr, abs);
+    if (r < 0) continue;
+    const uint32_t p = abs - soff[r], len = slen[r];
+    if (p >= len || len > a.len_cap) continue;  // alignment slack, or a read the launch rejects anyway
+    unsigned long long *row = a.rows + (size_t)p * kRow;
+    atomicAdd(&row[kColContent + base_code((sw >> (8 * j)) & 0xFFu)], 1ull);
+    const int sc = (int)((qw >> (8 * j)) & 0xFFu) - 33;
+    if (sc >= 0 && sc < 91)
+      atomicAdd(&row[sc], 1ull);
+    else
+      n_invalid++;
+  }
+  return n_invalid;
+}
+
+// rare path: window t (0..7) of a Bloom-positive unit.  Re-test it against the filter, then against the
+// exact key set (shared-memory hash table; the 2^20-bit map in L2 if the set was too big for it).
+__device__ __forceinline__ void confirm_window(const Candidate c, int t, const AdapterSet ad,
+                                               const uint8_t *bloom_lane, const uint32_t *exact_s, uint32_t lo_al,
+                                               const uint32_t *soff, const uint32_t *slen, uint32_t nr,
+                                               uint32_t *fhit) {
+  const uint32_t key = __funnelshift_r(c.lo, c.hi, 14 + 2 * t) & 0xFFFFFu;
+  const uint32_t p = key * ad.bloom_mul;
+  const uint32_t word = *reinterpret_cast<const uint32_t *>(bloom_lane + (p & 0x7F80u));
+  if (!((word >> (key & 31u)) & (word >> ((p >> 15) & 31u)) & 1u)) return;
+  bool member = false;
+  if (ad.exact) {
+    for (uint32_t i = exact_slot(key);; i = (i + 1u) & (kExactSlots - 1u)) {
+      const uint32_t v = exact_s[i];
+      if (v == key) member = true;
+      if (v == key || v == kExactEmpty) break;
+    }
+  } else {
+    member = (ad.bitmap[key >> 5] >> (key & 31u)) & 1u;
+  }
+  if (!member) return;
+  const uint32_t abs = lo_al + (uint32_t)(c.unit * 8 + t);  // byte on which the window ends
+  const int r = find_read(soff, nr, abs);
+  if (r < 0) return;
+  const uint32_t pos = abs - soff[r];
+  if (pos >= 9u && pos < slen[r]) atomicMin(&fhit[r], pos);  // whole window inside the read
+}
+
+__device__ __noinline__ void confirm_candidate(const Candidate c, const AdapterSet ad, const uint8_t *bloom_lane,
+                                               const uint32_t *exact_s, uint32_t lo_al, const uint32_t *soff,
+                                               const uint32_t *slen, uint32_t nr, uint32_t *fhit) {
+  for (int t = 0; t < 8; t++) confirm_window(c, t, ad, bloom_lane, exact_s, lo_al, soff, slen, nr, fhit);
+}
+
+template <bool kAdapters, uint32_t kLh>
 __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args) {
   extern __shared__ __align__(128) uint8_t smem[];
   const FusedPlan &plan = args.plan;
-  const uint32_t Lh = plan.half_len;
+  constexpr uint32_t Lh = kLh;  // == plan.half_len
   const uint32_t len_cap = args.a.len_cap;
   const uint32_t S = plan.stages;
   const SmemLayout L = smem_layout(Lh, len_cap, plan.tile_bytes, S, kAdapters);
 
   uint32_t *hist = reinterpret_cast<uint32_t *>(smem + L.hist);
-  const uint32_t *bloom_s = reinterpret_cast<const uint32_t *>(smem + L.bloom);
   uint32_t *lenhist = reinterpret_cast<uint32_t *>(smem + L.lenhist);
   uint32_t *kmerhist = reinterpret_cast<uint32_t *>(smem + L.kmerhist);
-  uint8_t *kbuf = smem + L.kbuf;
+  Candidate *cand = reinterpret_cast<Candidate *>(smem + L.cand);
+  const uint32_t *exact_s = reinterpret_cast<const uint32_t *>(smem + L.exact);
   uint32_t *meta = reinterpret_cast<uint32_t *>(smem + L.meta);
+  uint32_t *cand_count = meta + 4 * kMaxStages;  // [2], alternating per tile
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);  // [2*s] full, [2*s+1] empty
 
   const uint32_t tid = threadIdx.x;
@@ -248,12 +366,22 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
   if (kAdapters) {
     uint32_t *bw = reinterpret_cast<uint32_t *>(smem + L.bloom);
     for (uint32_t i = tid; i < kBloomWords * 32u; i += kThreads) bw[i] = args.ad.bloom[i];
+    uint32_t *ex = reinterpret_cast<uint32_t *>(smem + L.exact);
+    if (args.ad.exact)
+      for (uint32_t i = tid; i < kExactSlots; i += kThreads) ex[i] = args.ad.exact[i];
   }
   for (uint32_t s = 0; s < S; s++) {
-    uint32_t *fh = reinterpret_cast<uint32_t *>(smem + L.stage0 + s * L.stage_stride + L.fhit_off);
+    uint8_t *st = smem + L.stage0 + s * L.stage_stride;
+    uint32_t *fh = reinterpret_cast<uint32_t *>(st + L.fhit_off);
     for (uint32_t i = tid; i < kMaxTileReads; i += kThreads) fh[i] = kNoHit;
+    // pads are read (never consumed) by halo lanes: keep them defined
+    for (uint32_t i = tid; i < kPadBefore / 4; i += kThreads) {
+      reinterpret_cast<uint32_t *>(st)[i] = 0;
+      reinterpret_cast<uint32_t *>(st + L.qual_off - kPadBefore)[i] = 0;
+    }
   }
   if (tid == 0) {
+    cand_count[0] = cand_count[1] = 0;
     for (uint32_t s = 0; s < S; s++) {
       mbar_init(&bars[2 * s], 1);
       mbar_init(&bars[2 * s + 1], kCW);
@@ -307,21 +435,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
   }
 
   // ================================= consumer warps =================================
-  const uint32_t ctid = tid;  // 0 .. kCThreads-1
-  const uint32_t qsub = plan.qbase * 0x01010101u;
+  const KeyConsts kc(plan.qbase);
+  const uint32_t qsub = kc.qsub;
+  constexpr uint32_t Lh4 = Lh * 4u;
+  uint8_t *const hist_lane = smem + L.hist + lane * 4u;  // byte address of this lane's bank column
   unsigned long long n_invalid = 0;
   uint32_t reads_since_flush = 0;
 
   auto flush = [&]() {
     // all consumer warps have passed the barrier that ends phase H
     const uint32_t npos = min(2u * Lh, len_cap);
-    for (uint32_t pos = ctid; pos < npos; pos += kCThreads) {
+    for (uint32_t pos = tid; pos < npos; pos += kCThreads) {
       const bool hi = pos >= Lh;
       const uint32_t col = hi ? pos - Lh : pos;
       const uint32_t sh = hi ? 16u : 0u;
       unsigned long long *row = args.a.rows + (size_t)pos * kRow;
       uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-      for (uint32_t sp = 1; sp < 64; sp++) {
+      for (uint32_t sp = 0; sp < 63; sp++) {  // s = 63 rows are the dummies
         const uint32_t v0 = (hist[(sp)*Lh + col] >> sh) & 0xFFFFu;
         const uint32_t v1 = (hist[(64u + sp) * Lh + col] >> sh) & 0xFFFFu;
         const uint32_t v2 = (hist[(128u + sp) * Lh + col] >> sh) & 0xFFFFu;
@@ -340,17 +470,15 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
       if (c1) atomicAdd(&row[kColContent + 1], (unsigned long long)c1);
       if (c2) atomicAdd(&row[kColContent + 2], (unsigned long long)c2);
       if (c3) atomicAdd(&row[kColContent + 3], (unsigned long long)c3);
-      if (pos < len_cap) {
-        const uint32_t lc = lenhist[pos], kc = kmerhist[pos];
-        if (lc) atomicAdd(&row[kColLength], (unsigned long long)lc);
-        if (kc) atomicAdd(&row[kColKmer], (unsigned long long)kc);
-        lenhist[pos] = 0;
-        kmerhist[pos] = 0;
-      }
+      const uint32_t lc = lenhist[pos], kcnt = kmerhist[pos];
+      if (lc) atomicAdd(&row[kColLength], (unsigned long long)lc);
+      if (kcnt) atomicAdd(&row[kColKmer], (unsigned long long)kcnt);
+      lenhist[pos] = 0;
+      kmerhist[pos] = 0;
     }
     consumer_bar();
     uint4 *h4 = reinterpret_cast<uint4 *>(hist);
-    for (uint32_t i = ctid; i < 64u * Lh; i += kCThreads) h4[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < 64u * Lh; i += kCThreads) h4[i] = make_uint4(0, 0, 0, 0);
     consumer_bar();
   };
 
@@ -360,129 +488,160 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
     mbar_wait(&bars[2 * s], use & 1u);
     const uint32_t lo_al = meta[4 * s + 0];
     const uint32_t nr = meta[4 * s + 1];
-    const uint32_t nwords = meta[4 * s + 2] >> 2;
+    const uint32_t span = meta[4 * s + 2];
     uint8_t *st = smem + L.stage0 + s * L.stage_stride;
-    const uint32_t *seqw = reinterpret_cast<const uint32_t *>(st + L.seq_off);
-    const uint32_t *qualw = reinterpret_cast<const uint32_t *>(st + L.qual_off);
-    const uint8_t *qualb = st + L.qual_off;
     const uint32_t *soff = reinterpret_cast<const uint32_t *>(st + L.soff_off);
     const uint32_t *slen = reinterpret_cast<const uint32_t *>(st + L.slen_off);
     uint32_t *fhit = reinterpret_cast<uint32_t *>(st + L.fhit_off);
-    uint32_t *kw = reinterpret_cast<uint32_t *>(kbuf);
+    uint8_t *kbuf = st + L.qual_off;  // phase A overwrites the quality bytes with the key bytes K
+    uint32_t *ccount = &cand_count[it & 1u];
 
-    // ------------------------------ phase A: flat over the tile's words ------------------------------
+    // ---------------- phase A: flat over the tile, K written in place of the quality bytes ----------------
     if (!kAdapters) {
-      for (uint32_t w = warp * 32u + lane; w < nwords; w += kCThreads) {
-        uint32_t cc;
-        kw[w] = key_bytes(seqw[w], qualw[w], qsub, cc);
+      const uint4 *s4 = reinterpret_cast<const uint4 *>(st + L.seq_off);
+      uint4 *q4 = reinterpret_cast<uint4 *>(st + L.qual_off);
+      const uint32_t nvec = span >> 4;
+      for (uint32_t v = tid; v < nvec; v += kCThreads) {
+        const uint4 sv = s4[v], qv = q4[v];
+        uint32_t n0, n1, n2, n3, bad = 0;
+        uint4 K;
+        K.x = key_bytes(sv.x, qv.x, kc, n0, bad);
+        K.y = key_bytes(sv.y, qv.y, kc, n1, bad);
+        K.z = key_bytes(sv.z, qv.z, kc, n2, bad);
+        K.w = key_bytes(sv.w, qv.w, kc, n3, bad);
+        if (bad & 0xC0C0C0C0u) {  // rare: re-key the offending words to the dummy rows, count them exactly
+          const uint32_t abs0 = lo_al + v * 16u;
+          if (word_bad(qv.x, qsub)) K.x = key_bytes_bad(n0), n_invalid += exact_word(sv.x, qv.x, abs0, soff, slen, nr, args.a);
+          if (word_bad(qv.y, qsub)) K.y = key_bytes_bad(n1), n_invalid += exact_word(sv.y, qv.y, abs0 + 4u, soff, slen, nr, args.a);
+          if (word_bad(qv.z, qsub)) K.z = key_bytes_bad(n2), n_invalid += exact_word(sv.z, qv.z, abs0 + 8u, soff, slen, nr, args.a);
+          if (word_bad(qv.w, qsub)) K.w = key_bytes_bad(n3), n_invalid += exact_word(sv.w, qv.w, abs0 + 12u, soff, slen, nr, args.a);
+        }
+        q4[v] = K;
       }
     } else {
-      // each warp step covers 29 new words; lanes 0..2 re-read the 3 words before them so that
-      // every 10-mer window ending in lanes 3..31 finds its 9 earlier bases inside the warp
-      const uint32_t nsteps = (nwords + 28u) / 29u;
-      const uint32_t M = args.ad.bloom_mul;
+      // One 8-byte unit (8 bases) per lane.  A warp step covers 30 new units; lanes 0 and 1 re-read the
+      // two units in front so that every 10-mer window ending in lanes 2..31 finds its 9 earlier bases
+      // inside the warp (two shuffles).  Halo lanes compute but never store or report.
+      const uint2 *s8 = reinterpret_cast<const uint2 *>(st + L.seq_off);
+      uint2 *q8 = reinterpret_cast<uint2 *>(st + L.qual_off);
+      const uint8_t *bloom_b = smem + L.bloom;
       const uint32_t lane4 = lane * 4u;
+      const int n8 = (int)(span >> 3);
+      const uint32_t nsteps = ((uint32_t)n8 + 29u) / 30u;
+      const uint32_t M = args.ad.bloom_mul;
       for (uint32_t step = warp; step < nsteps; step += kCW) {
-        const int w = (int)(step * 29u + lane) - 3;
-        const bool inr = (w >= 0) && ((uint32_t)w < nwords);
-        const uint32_t sw = inr ? seqw[w] : 0u;
-        const uint32_t qw = inr ? qualw[w] : 0u;
-        uint32_t cc;
-        const uint32_t K = key_bytes(sw, qw, qsub, cc);
-        const bool own = inr && lane >= 3u;
-        if (own) kw[w] = K;
-        // 4 bases -> 8 bits, first base least significant
-        const uint32_t p8 = (cc * 0x41041u) >> 24;
-        const uint32_t a16 = __shfl_up_sync(0xffffffffu, p8, 1) | (p8 << 8);
-        const uint32_t R = __shfl_up_sync(0xffffffffu, a16, 2) | (a16 << 16);  // 16 bases, mine on top
+        const int u = (int)(step * 30u + lane) - 2;  // -2, -1 land in the pad in front; > n8 in the pad behind
+        const uint2 sv = s8[u], qv = q8[u];
+        uint32_t n0, n1, bad = 0;
+        uint2 K;
+        K.x = key_bytes(sv.x, qv.x, kc, n0, bad);
+        K.y = key_bytes(sv.y, qv.y, kc, n1, bad);
+        const bool own = lane >= 2u && u < n8;
+        if (own) {
+          if (bad & 0xC0C0C0C0u) {
+            const uint32_t abs0 = lo_al + (uint32_t)u * 8u;
+            if (word_bad(qv.x, qsub)) K.x = key_bytes_bad(n0), n_invalid += exact_word(sv.x, qv.x, abs0, soff, slen, nr, args.a);
+            if (word_bad(qv.y, qsub)) K.y = key_bytes_bad(n1), n_invalid += exact_word(sv.y, qv.y, abs0 + 4u, soff, slen, nr, args.a);
+          }
+          q8[u] = K;
+        }
+        // 8 bases -> 16 bits, first base least significant (codes are the inverted bits 7:6 of n0/n1)
+        const uint32_t c0 = ~n0 & 0xC0C0C0C0u, c1 = ~n1 & 0xC0C0C0C0u;
+        const uint32_t p16 = ((c0 * 0x41041u) >> 24) | (((c1 * 0x41041u) >> 16) & 0xFF00u);
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, p16, 1);
+        const uint32_t pp = __shfl_up_sync(0xffffffffu, p16, 2);
+        const uint32_t lo = (pp & 0xFFFFu) | (prev << 16);  // 16 earlier bases
+        const uint32_t hi = p16;                             // my 8 bases
         uint32_t acc = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint32_t wj = R >> (6 + 2 * j);  // low 20 bits: window ending at my byte j
-          const uint32_t p = wj * M;             // low 20 bits depend on the window only
-          const uint32_t word =
-              *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(bloom_s) + ((p & 0x7F80u) | lane4));
+        for (int t = 0; t < 8; t++) {
+          const uint32_t wj = __funnelshift_r(lo, hi, 14 + 2 * t);  // low 20 bits: window ending at my base t
+          const uint32_t p = wj * M;                                // low 20 bits depend on the window only
+          const uint32_t word = *reinterpret_cast<const uint32_t *>(bloom_b + ((p & 0x7F80u) | lane4));
           acc |= __funnelshift_r(word, 0u, wj) & __funnelshift_r(word, 0u, p >> 15);
         }
-        const bool maybe = own && (acc & 1u);
-        if (__any_sync(0xffffffffu, maybe)) {
-          if (maybe) {
-#pragma unroll 1
-            for (int j = 0; j < 4; j++) {
-              const uint32_t key = (R >> (6 + 2 * j)) & 0xFFFFFu;
-              if ((args.ad.bitmap[key >> 5] >> (key & 31u)) & 1u) {
-                const uint32_t end_abs = lo_al + 4u * (uint32_t)w + (uint32_t)j;  // byte where the window ends
-                // read containing that byte: largest r with soff[r] <= end_abs
-                int a = 0, b = (int)nr - 1, r = -1;
-                while (a <= b) {
-                  const int m = (a + b) >> 1;
-                  if (soff[m] <= end_abs) {
-                    r = m;
-                    a = m + 1;
-                  } else
-                    b = m - 1;
-                }
-                if (r >= 0) {
-                  const uint32_t p = end_abs - soff[r];
-                  if (p >= 9u && p < slen[r]) atomicMin(&fhit[r], p);
-                }
-              }
-            }
-          }
+        if (own && (acc & 1u)) {
+          const Candidate c{u, lo, hi};
+          const uint32_t idx = atomicAdd(ccount, 1u);
+          if (idx < kCandCap)
+            cand[idx] = c;
+          else
+            confirm_candidate(c, args.ad, bloom_b + lane4, exact_s, lo_al, soff, slen, nr, fhit);
         }
       }
     }
     consumer_bar();
 
-    // ------------------------------ phase H: one warp per read ------------------------------
-    for (uint32_t r = warp; r < nr; r += kCW) {
-      const uint32_t len = slen[r];
-      const uint32_t off = soff[r] - lo_al;
-      if (len > len_cap) {
-        if (lane == 0) atomicAdd(&args.a.counters[kCntError], 1ull);
-        continue;
-      }
-      const uint8_t *kb = kbuf + off;
-      for (uint32_t pos0 = 0; pos0 < len; pos0 += 32) {
-        const uint32_t pos = pos0 + lane;
-        if (pos < len) {
-          const uint32_t k = kb[pos];
-          const bool hi = pos0 >= Lh;  // warp-uniform: Lh is a multiple of 32
-          const uint32_t col = hi ? pos - Lh : pos;
-          atomicAdd(&hist[k * Lh + col], hi ? 0x10000u : 1u);
-          if ((k & 63u) == 0u) {
-            // quality outside the shared-memory window: count this base exactly in global memory
-            unsigned long long *row = args.a.rows + (size_t)pos * kRow;
-            atomicAdd(&row[kColContent + (k >> 6)], 1ull);
-            const int sc = (int)qualb[off + pos] - 33;
-            if (sc >= 0 && sc < 91)
-              atomicAdd(&row[sc], 1ull);
-            else
-              n_invalid++;
-          }
-        }
-      }
-      if (lane == 0) {
-        if (len) atomicAdd(&lenhist[len - 1], 1u);
-        if (kAdapters) {
-          const uint32_t fh = fhit[r];
-          if (fh != kNoHit) {
-            if (fh + 1u < len) atomicAdd(&kmerhist[fh + 1u], 1u);
-            fhit[r] = kNoHit;
+    // ---------------- phase A2: confirm queued Bloom positives, spread over all threads ----------------
+    if (kAdapters) {
+      const uint32_t nc = min(*ccount, kCandCap);
+      for (uint32_t i = tid; i < nc * 8u; i += kCThreads)  // one (unit, window) pair per thread: all warps share it
+        confirm_window(cand[i >> 3], (int)(i & 7u), args.ad, smem + L.bloom + lane * 4u, exact_s, lo_al, soff, slen,
+                       nr, fhit);
+    }
+
+    // ---------------- phase H: one warp per read, lane <-> position, one shared atomic per base ----------------
+    // Every 32-position step is straight-line code: which half-word it counts in and its column
+    // offset are compile-time constants (kLh template); only the lane predicate pos < len is dynamic.
+    // Explicit shared-space PTX keeps a step at ISETP + LDS.U8 + IMAD + ATOMS.
+#define QB_STEP(sidx)                                                                               \
+  if (rem > (sidx) * 32u) {                                                                         \
+    constexpr uint32_t pos0 = (sidx) * 32u;                                                         \
+    constexpr bool hi_half = pos0 >= Lh;                                                            \
+    const uint32_t k = lds_u8(kb_s + pos0);                                                         \
+    red_shared_add(k * Lh4 + hist_s + (hi_half ? pos0 - Lh : pos0) * 4u, hi_half ? 0x10000u : 1u);  \
+  }
+    {
+      const uint32_t kbuf_s = smem_u32(kbuf) + lane - lo_al;
+      const uint32_t hist_s = smem_u32(hist_lane);
+      for (uint32_t r = warp; r < nr; r += kCW) {
+        const uint32_t len = slen[r];
+        if (len > len_cap) continue;  // reported in the bookkeeping pass below
+        const uint32_t kb_s = kbuf_s + soff[r];
+        const uint32_t rem = len > lane ? len - lane : 0u;  // lane handles positions lane, lane+32, ... < len
+        QB_STEP(0) QB_STEP(1) QB_STEP(2)
+        if (len > 96u) {
+          QB_STEP(3) QB_STEP(4)
+          if constexpr (Lh == 96u) {
+            QB_STEP(5)
+          } else if (len > 160u) {
+            QB_STEP(5) QB_STEP(6) QB_STEP(7)
+            if (len > 256u) { QB_STEP(8) QB_STEP(9) }
           }
         }
       }
     }
+#undef QB_STEP
+    consumer_bar();  // K bytes, candidates and fhit of this tile are final / no longer needed
+
+    // ---------------- bookkeeping: per-read counters, one thread per read ----------------
+    for (uint32_t r = tid; r < nr; r += kCThreads) {
+      const uint32_t len = slen[r];
+      if (len > len_cap) {
+        atomicAdd(&args.a.counters[kCntError], 1ull);
+        continue;
+      }
+      if (len) atomicAdd(&lenhist[len - 1u], 1u);  // quack.c:219
+      if (kAdapters) {
+        const uint32_t fh = fhit[r];
+        if (fh != kNoHit) {
+          if (fh + 1u < len) atomicAdd(&kmerhist[fh + 1u], 1u);  // quack.c:215-217
+          fhit[r] = kNoHit;
+        }
+      }
+    }
+    if (kAdapters && tid == 0) *ccount = 0;
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars[2 * s + 1]);  // stage buffers free for the producer
-    consumer_bar();                                  // K buffer free for the next phase A
 
     reads_since_flush += nr;
     if (reads_since_flush + RT > 65535u) {  // u16 counters: flush before any bin can wrap
+      consumer_bar();
       flush();
       reads_since_flush = 0;
     }
   }
+  consumer_bar();
   flush();
   n_invalid = warp_sum(n_invalid);
   if (lane == 0 && n_invalid) atomicAdd(&args.a.counters[kCntInvalidQual], n_invalid);
@@ -493,16 +652,16 @@ FusedPlan fused_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int
   FusedPlan p;
   memset(&p, 0, sizeof p);
   if (len_cap == 0) return p;
-  uint32_t half = ((len_cap + 1u) / 2u + 31u) & ~31u;
-  if (half < 32u) half = 32u;
+  if (len_cap > 320u) return p;  // beyond the shared-memory histogram: simple kernel
+  const uint32_t half = len_cap <= 192u ? 96u : 160u;  // the two instantiations of fused_kernel
   p.half_len = half;
   p.qbase = qbase;
   if (batch_max_len == 0 || batch_max_len > len_cap) batch_max_len = len_cap;
   for (uint32_t stages = kMaxStages; stages >= 2; stages--) {
     const SmemLayout L0 = smem_layout(half, len_cap, 0, stages, adapters);
     if (L0.total + 128u >= smem_optin) continue;
-    uint32_t avail = smem_optin - L0.total - 128u;  // L0 already holds every +16 pad
-    uint32_t tile = (avail / (2u * stages + 1u)) & ~15u;
+    uint32_t avail = smem_optin - L0.total - 128u;  // L0 already holds every pad
+    uint32_t tile = (avail / (2u * stages)) & ~15u;
     if (tile > 32768u) tile = 32768u;
     if (tile < 64u) continue;
     uint32_t rt = ((tile - 32u) / batch_max_len) & ~3u;
@@ -521,9 +680,11 @@ FusedPlan fused_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int
 }
 
 cudaError_t fused_configure() {
-  cudaError_t e = cudaFuncSetAttribute(fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(fused_kernel<true, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+  if ((e = cudaFuncSetAttribute(fused_kernel<false, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+  if ((e = cudaFuncSetAttribute(fused_kernel<true, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+  return cudaFuncSetAttribute(fused_kernel<false, 160>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
 }
 
 cudaError_t launch_fused(const BatchView &b, const Accum &a, const AdapterSet &ad, const FusedPlan &plan,
@@ -540,10 +701,17 @@ cudaError_t launch_fused(const BatchView &b, const Accum &a, const AdapterSet &a
     const uint32_t v = (uint32_t)atoi(g);
     if (v >= 1 && v < grid) grid = v;
   }
-  if (ad.enabled)
-    fused_kernel<true><<<grid, kThreads, plan.smem_bytes, stream>>>(args);
-  else
-    fused_kernel<false><<<grid, kThreads, plan.smem_bytes, stream>>>(args);
+  if (plan.half_len == 96u) {
+    if (ad.enabled)
+      fused_kernel<true, 96><<<grid, kThreads, plan.smem_bytes, stream>>>(args);
+    else
+      fused_kernel<false, 96><<<grid, kThreads, plan.smem_bytes, stream>>>(args);
+  } else {
+    if (ad.enabled)
+      fused_kernel<true, 160><<<grid, kThreads, plan.smem_bytes, stream>>>(args);
+    else
+      fused_kernel<false, 160><<<grid, kThreads, plan.smem_bytes, stream>>>(args);
+  }
   return cudaGetLastError();
 }
 

@@ -26,9 +26,15 @@ constexpr int kNumCounters = 4;
 constexpr uint32_t kBloomWords = 256;          // words per bank copy (power of two)
 constexpr uint32_t kBloomBytes = kBloomWords * 32 * 4;  // 32 KiB, one copy per shared-memory bank
 
+constexpr uint32_t kExactSlots = 2048;         // open-addressing table of the exact key set (8 KiB)
+constexpr uint32_t kExactEmpty = 0xFFFFFFFFu;
+constexpr uint32_t kExactMul = 0x9E3779B1u;
+__host__ __device__ inline uint32_t exact_slot(uint32_t key) { return (key * kExactMul) >> 21; }  // 11 bits
+
 struct AdapterSet {
   const uint32_t *bitmap;  // exact membership, 2^20 bits, device global (stays in L2)
   const uint32_t *bloom;   // [kBloomWords][32] blocked Bloom filter, bank-replicated, device global
+  const uint32_t *exact;   // [kExactSlots] linear-probing table of the keys, or nullptr if they do not fit
   uint32_t bloom_mul;      // odd multiplier M: p = key * M
   int enabled;             // 0: no -a (kmer_count handled at finish)
 };

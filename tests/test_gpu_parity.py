@@ -110,7 +110,7 @@ def test_adapter_first_hit_every_position(table, keys):
             s = bytearray(b"C" * l)
             m = min(len(ad), l - at)
             s[at: at + m] = ad[:m]
-            if at + 40 < l:
+            if at + 51 <= l:
                 s[at + 40: at + 40 + 11] = ad[:11]
             reads.append((bytes(s), b"I" * l))
     reads.append((b"CCCCCCCCCCCCGATCGGAAGA", b"I" * 22))       # hit ends on the last base
@@ -203,3 +203,17 @@ def test_empty_and_reset(keys):
         assert ctx.finish(0).n_reads == 500
         ctx.reset(0)
         assert ctx.finish(0).n_reads == 0
+
+
+@pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
+def test_large_adapter_set(kernel):
+    """An adapter file with thousands of k-mers does not fit the shared-memory key table: the kernels then
+    confirm filter hits against the 2^20-bit map in L2.  Dense set -> many first hits."""
+    rng = np.random.default_rng(99)
+    recs = [rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=60).tobytes() for _ in range(120)]
+    table = po.AdapterTable.from_records(recs)
+    keys = table.keys()
+    assert len(keys) > 3000
+    batch = util.random_batch(123, 20000, 40, 150, plant=0.3, plant_seq=recs[5])
+    got = run_gpu(batch, 150, keys, kernel)
+    util.assert_same(got, po.accumulate_batch(*batch, table), "large set")
