@@ -148,6 +148,16 @@ int qb_dbatch_info(const qb_dbatch *b, uint32_t *n_reads, uint64_t *n_bytes);
 void qb_dbatch_free(qb_ctx *ctx, qb_dbatch *b);
 /* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
 uint64_t qb_launch_count(const qb_ctx *ctx);
+/* Live kernel timing: after qb_profile_enable(ctx, n) every statistics-kernel launch is bracketed by
+ * a CUDA event pair on the stream it is launched on (up to n launches, then recording stops).
+ * qb_profile_collect() synchronises and returns the per-launch durations in ms and the algorithmic
+ * bytes (2*bases + 8*reads) of each launch; it returns the number of launches
+ * written (<= cap) and resets the recorder.  qb_profile_enable(ctx, 0) switches it off. */
+int qb_profile_enable(qb_ctx *ctx, int max_launches);
+int qb_profile_collect(qb_ctx *ctx, float *ms_out, uint64_t *bytes_out, int cap);
+/* CUDA-event stopwatch on the main stream of one device (the stream qb_dbatch_run launches on). */
+int qb_timer_start(qb_ctx *ctx, int device_index);
+int qb_timer_stop(qb_ctx *ctx, int device_index, float *ms);
 /* Measured pinned H2D bandwidth of device_index in GB/s (best of `iters` copies of `bytes`). */
 int qb_measure_h2d(qb_ctx *ctx, int device_index, uint64_t bytes, int iters, double *gbs);
 

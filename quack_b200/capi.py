@@ -82,6 +82,10 @@ def lib() -> C.CDLL:
     L.qb_dbatch_free.restype = None
     L.qb_launch_count.argtypes = [vp]
     L.qb_launch_count.restype = C.c_uint64
+    L.qb_profile_enable.argtypes = [vp, C.c_int]
+    L.qb_profile_collect.argtypes = [vp, C.POINTER(C.c_float), _u64p, C.c_int]
+    L.qb_timer_start.argtypes = [vp, C.c_int]
+    L.qb_timer_stop.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     L.qb_measure_h2d.argtypes = [vp, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
     L.qb_base_code.argtypes = [C.c_int]
     L.qb_adapter_record_keys.argtypes = [C.c_char_p, C.c_size_t, _u32p, C.c_size_t]
@@ -250,6 +254,26 @@ class Context:
         self._chk(lib().qb_dbatch_generate(self.h, device_index, seed, mate, first_read, n_reads, len_min, len_max,
                                            adapter_rate, C.byref(h)))
         return DeviceBatch(self, h)
+
+    def profile_enable(self, max_launches: int):
+        self._chk(lib().qb_profile_enable(self.h, max_launches))
+
+    def profile_collect(self, cap: int = 4096):
+        """[(ms, algorithmic_bytes)] of the launches recorded since profile_enable()."""
+        ms = (C.c_float * cap)()
+        by = (C.c_uint64 * cap)()
+        n = lib().qb_profile_collect(self.h, ms, by, cap)
+        if n < 0:
+            self._chk(n)
+        return [(ms[i], by[i]) for i in range(n)]
+
+    def timer_start(self, device_index: int = 0):
+        self._chk(lib().qb_timer_start(self.h, device_index))
+
+    def timer_stop(self, device_index: int = 0) -> float:
+        ms = C.c_float()
+        self._chk(lib().qb_timer_stop(self.h, device_index, C.byref(ms)))
+        return ms.value
 
     @property
     def launch_count(self) -> int:

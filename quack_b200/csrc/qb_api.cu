@@ -81,6 +81,7 @@ struct Device {
   uint32_t *d_bitmap = nullptr, *d_bloom = nullptr, *d_exact = nullptr;
   std::vector<Slot> slots;
   cudaStream_t main_stream = nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;  // qb_timer_*
   ncclComm_t comm = nullptr;  // in-process communicator (n_devices > 1)
   uint32_t *l2_scratch = nullptr;
   size_t l2_words = 0;
@@ -103,6 +104,10 @@ struct qb_ctx {
   ncclComm_t rank_comm = nullptr;  // multi-process communicator
   int n_ranks = 1, rank = 0;
   unsigned long long *h_result = nullptr;  // pinned staging for qb_finish
+  // live profiling of kernel launches
+  struct ProfRec { cudaEvent_t e0, e1; uint64_t bytes; int dev; };
+  std::vector<ProfRec> prof;
+  int prof_cap = 0;
 };
 
 struct qb_dbatch {
@@ -181,13 +186,26 @@ int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaS
     } else
       kernel = QB_KERNEL_FUSED;
   }
-  cudaError_t e = kernel == QB_KERNEL_FUSED ? qb::launch_fused(v, ac, ad, plan, stream)
-                                            : qb::launch_simple(v, ac, ad, d.sm_count, stream);
-  if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  qb_ctx::ProfRec *rec = nullptr;
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->launches++;
+    if ((int)ctx->prof.size() < ctx->prof_cap) {
+      qb_ctx::ProfRec r{};
+      if (cudaEventCreate(&r.e0) == cudaSuccess && cudaEventCreate(&r.e1) == cudaSuccess) {
+        r.bytes = 2 * v.n_bytes + 8ull * v.n_reads;
+        r.dev = d.id;
+        ctx->prof.push_back(r);
+        rec = &ctx->prof.back();
+      }
+    }
   }
+  cudaEvent_t e0 = rec ? rec->e0 : nullptr, e1 = rec ? rec->e1 : nullptr;
+  if (e0) cudaEventRecord(e0, stream);
+  cudaError_t e = kernel == QB_KERNEL_FUSED ? qb::launch_fused(v, ac, ad, plan, stream)
+                                            : qb::launch_simple(v, ac, ad, d.sm_count, stream);
+  if (e1) cudaEventRecord(e1, stream);
+  if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return QB_OK;
 }
 
@@ -358,7 +376,13 @@ void qb_destroy(qb_ctx *ctx) {
     cudaFree(d.d_bloom);
     cudaFree(d.d_exact);
     cudaFree(d.l2_scratch);
+    if (d.t0) cudaEventDestroy(d.t0);
+    if (d.t1) cudaEventDestroy(d.t1);
     if (d.main_stream) cudaStreamDestroy(d.main_stream);
+  }
+  for (auto &r : ctx->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
   }
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
   delete ctx;
@@ -607,6 +631,64 @@ int qb_invalid_quality_count(qb_ctx *ctx, int mate, uint64_t *out) {
 }
 
 uint64_t qb_launch_count(const qb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int qb_profile_enable(qb_ctx *ctx, int max_launches) {
+  if (!ctx || max_launches < 0) return QB_ERR_ARG;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  for (auto &r : ctx->prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->prof.clear();
+  ctx->prof.reserve(max_launches);  // launch_batch keeps pointers into the vector: never reallocate
+  ctx->prof_cap = max_launches;
+  return QB_OK;
+}
+
+int qb_profile_collect(qb_ctx *ctx, float *ms_out, uint64_t *bytes_out, int cap) {
+  if (!ctx || cap < 0) return QB_ERR_ARG;
+  int rc = qb_sync(ctx);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  int n = 0;
+  for (auto &r : ctx->prof) {
+    if (n < cap) {
+      float ms = 0;
+      cudaSetDevice(r.dev);
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) ms = -1.f;
+      if (ms_out) ms_out[n] = ms;
+      if (bytes_out) bytes_out[n] = r.bytes;
+      n++;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->prof.clear();
+  return n;
+}
+
+int qb_timer_start(qb_ctx *ctx, int device_index) {
+  if (!ctx || device_index < 0 || device_index >= (int)ctx->dev.size()) return QB_ERR_ARG;
+  Device &d = ctx->dev[device_index];
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  if (!d.t0) {
+    QB_CUDA(ctx, cudaEventCreate(&d.t0));
+    QB_CUDA(ctx, cudaEventCreate(&d.t1));
+  }
+  QB_CUDA(ctx, cudaEventRecord(d.t0, d.main_stream));
+  return QB_OK;
+}
+
+int qb_timer_stop(qb_ctx *ctx, int device_index, float *ms) {
+  if (!ctx || !ms || device_index < 0 || device_index >= (int)ctx->dev.size()) return QB_ERR_ARG;
+  Device &d = ctx->dev[device_index];
+  if (!d.t0) return fail(ctx, QB_ERR_ARG, "qb_timer_stop without qb_timer_start");
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  QB_CUDA(ctx, cudaEventRecord(d.t1, d.main_stream));
+  QB_CUDA(ctx, cudaEventSynchronize(d.t1));
+  QB_CUDA(ctx, cudaEventElapsedTime(ms, d.t0, d.t1));
+  return QB_OK;
+}
 
 // ---------------------------------------------------------------------- device-resident batches
 
