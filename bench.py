@@ -215,7 +215,8 @@ class Arena:
 def bench_ours(args):
     import torch
     import torch.distributed as dist
-    from quack_b200 import build, capi, synth
+    import quack_b200
+    from quack_b200 import capi, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,7 +225,7 @@ def bench_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: quack_b200 has no CPU fallback")
-    if not os.path.exists(build.lib_path()):
+    if not os.path.exists(quack_b200.lib_path()):
         raise SystemExit("libquack_b200.so missing: run python -c 'import __graft_entry__ as g; g.build()'")
     torch.cuda.set_device(local_rank)
     if world > 1:

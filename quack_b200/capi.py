@@ -95,6 +95,23 @@ def lib() -> C.CDLL:
     L.qb_host_alloc.restype = vp
     L.qb_host_free.argtypes = [vp]
     L.qb_host_free.restype = None
+    # host program pieces linked into the same library (quack_b200/host/*.c)
+    L.fqr_open.argtypes = [C.c_char_p]
+    L.fqr_open.restype = vp
+    L.fqr_close.argtypes = [vp]
+    L.fqr_close.restype = None
+    L.fqr_fill.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, C.c_uint32, _u32p, _u64p, _u32p]
+    L.fqr_status.argtypes = [vp]
+    L.fqr_next.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.fqr_next.restype = C.c_long
+    L.fqr_bytes_in.argtypes = [vp]
+    L.fqr_bytes_in.restype = C.c_uint64
+    L.fqr_inflate_seconds.argtypes = [vp]
+    L.fqr_inflate_seconds.restype = C.c_double
+    L.fqr_read_adapter_keys.argtypes = [C.c_char_p, C.POINTER(_u32p)]
+    L.fqr_read_adapter_keys.restype = C.c_long
+    L.qr_render_to_path.argtypes = [vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_int, C.c_char_p,
+                                    C.c_char_p]
     L.qb_microbench.argtypes = [C.c_char_p, C.c_size_t]
     L.qb_adapter_filter_info.argtypes = [vp, _u32p, C.POINTER(C.c_double)]
     _lib = L
@@ -304,3 +321,68 @@ def microbench() -> str:
     if rc:
         raise QbError(rc, "qb_microbench")
     return buf.value.decode()
+
+
+# ------------------------------------------------------------------ host program pieces (C, in the same .so)
+
+def read_adapters(path: str) -> np.ndarray:
+    """read_adapters(), reference quack.c:154-178, through the host reader: keys in reference order."""
+    p = _u32p()
+    n = lib().fqr_read_adapter_keys(path.encode(), C.byref(p))
+    if n < 0:
+        raise OSError(f"cannot open {path}")
+    out = np.ctypeslib.as_array(p, shape=(max(n, 1),))[:n].copy()
+    C.CDLL(None).free(p)
+    return out
+
+
+def parse_records(path: str):
+    """[(seq, qual or None)] and the final status, record by record through the host reader."""
+    L = lib()
+    r = L.fqr_open(path.encode())
+    if not r:
+        raise OSError(path)
+    out = []
+    s, q, ql = C.c_void_p(), C.c_void_p(), C.c_size_t()
+    while True:
+        n = L.fqr_next(r, C.byref(s), C.byref(q), C.byref(ql))
+        if n < 0:
+            break
+        out.append((C.string_at(s, n), C.string_at(q, ql.value) if q.value else None))
+    L.fqr_close(r)
+    return out, int(n)
+
+
+def read_batches(path: str, cap_bytes: int, cap_reads: int):
+    """All batches the host reader packs from a file: [(seq, qual, offset, length, max_len)], status."""
+    L = lib()
+    r = L.fqr_open(path.encode())
+    if not r:
+        raise OSError(path)
+    batches = []
+    more = 1
+    while more > 0:
+        seq = np.zeros(cap_bytes + 64, dtype=np.uint8)
+        qual = np.zeros(cap_bytes + 64, dtype=np.uint8)
+        off = np.zeros(cap_reads, dtype=np.uint32)
+        ln = np.zeros(cap_reads, dtype=np.uint32)
+        n, nb, ml = C.c_uint32(), C.c_uint64(), C.c_uint32()
+        more = L.fqr_fill(r, seq.ctypes.data, qual.ctypes.data, off.ctypes.data, ln.ctypes.data, cap_bytes, cap_reads,
+                          C.byref(n), C.byref(nb), C.byref(ml))
+        batches.append((seq[: nb.value], qual[: nb.value], off[: n.value], ln[: n.value], ml.value))
+    status = L.fqr_status(r)
+    L.fqr_close(r)
+    return batches, status
+
+
+def render_svg(first: "Result", second: "Result | None", adapters_used: bool, name: str | None, path: str):
+    """transform() + draw() of the reference (quack.c:230-856) restated: SVG for raw accumulators."""
+    r1 = np.ascontiguousarray(first.rows, dtype=np.uint64)
+    r2 = np.ascontiguousarray(second.rows, dtype=np.uint64) if second is not None else None
+    rc = lib().qr_render_to_path(r1.ctypes.data, first.max_length, first.n_reads,
+                                 r2.ctypes.data if r2 is not None else None,
+                                 second.max_length if second is not None else 0,
+                                 second.n_reads if second is not None else 0, int(adapters_used),
+                                 name.encode() if name is not None else None, path.encode())
+    if rc:
+        raise OSError(path)

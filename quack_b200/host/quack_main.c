@@ -1,0 +1,257 @@
+/* quack_main.c -- the `quack` command line on top of the B200 statistics library.
+ *
+ * Same options, same usage texts, same exit codes and the same SVG on stdout as the reference main()
+ * (quack.c:54-132, 858-928).  What changed is the middle: instead of calling read_fastq() once per
+ * mate, one host thread per mate runs the batching reader (fq_reader.c), packs records into the pinned
+ * slots handed out by qb_acquire() and submits them (qb_submit), so both mates are decoded
+ * concurrently while copies and kernels overlap on the GPU(s); qb_finish() then returns the
+ * accumulator in base_information layout for the unchanged transform/draw stage (render.c).
+ *
+ * Extra knobs live in the environment so that the five reference options stay untouched:
+ *   QB_DEVICES=N        number of GPUs to spread batches over (default 1)
+ *   QB_BATCH_MB=M       pinned slot size in MiB for seq[] and for qual[] (default 64)
+ *   QB_LEN_CAP=L        longest read accepted (default 65536)
+ *   QB_KERNEL=0|1|2     auto | simple | fused
+ *   QB_STATS_JSON=path  write reads/s, bases/s and stage times there (stdout stays the SVG)
+ */
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "../../include/quack_b200.h"
+#include "fq_reader.h"
+#include "render.h"
+
+static const char *program_version = "quack 1.1.1";
+
+static const char *usage_head =
+    "Usage: quack [OPTION...]\n"
+    "quack -- A FASTQ quality assessment tool\n\n"
+    "  -1, --forward file.1.fq.gz      Forward strand\n"
+    "  -2, --reverse file.2.fq.gz      Reverse strand\n";
+
+struct options {
+  const char *name, *forward, *reverse, *unpaired, *adapters;
+};
+
+/* quack.c:59-132, behaviour preserved case by case ("Config / flags") */
+static struct options parse_options(int argc, char **argv) {
+  struct options o = {NULL, NULL, NULL, NULL, NULL};
+  if (argc == 1 || argc == 2) {
+    if (argc == 1 || !strcmp(argv[1], "--help") || !strcmp(argv[1], "--usage") || !strcmp(argv[1], "-?"))
+      printf("%s"
+             "  -a, --adapters adapters.fa.gz   (Optional) Adapters file\n"
+             "  -n, --name NAME                 (Optional) Display in output\n"
+             "  -u, --unpaired unpaired.fq.gz   Data (only use with -u)\n"
+             "  -?, --help                      Give this help list\n"
+             "      --usage                     (use alone)\n"
+             "  -V, --version                   Print program version (use alone)\n"
+             "Report bugs to <thrash@igbb.msstate.edu>.\n",
+             usage_head);
+    if (argc == 2 && (!strcmp(argv[1], "-V") || !strcmp(argv[1], "--version"))) {
+      printf("%s\n", program_version);
+      exit(0);
+    }
+  }
+  if (argc > 2 && argc % 2 != 0) {
+    for (int i = 1; i < argc; i += 2) {
+      const char *f = argv[i];
+      if (!strcmp(f, "--forward") || !strcmp(f, "-1"))
+        o.forward = argv[i + 1];
+      else if (!strcmp(f, "--reverse") || !strcmp(f, "-2"))
+        o.reverse = argv[i + 1];
+      else if (!strcmp(f, "--adapters") || !strcmp(f, "-a"))
+        o.adapters = argv[i + 1];
+      else if (!strcmp(f, "--unpaired") || !strcmp(f, "-u"))
+        o.unpaired = argv[i + 1];
+      else if (!strcmp(f, "--name") || !strcmp(f, "-n"))
+        o.name = argv[i + 1];
+      else {
+        fprintf(stderr,
+                "%s"
+                "  -a, --adapters adapters.fa.gz    Adapters file\n"
+                "  -n, --name NAME            Display in output\n"
+                "  -u, --unpaired unpaired.fq.gz        Data (only use with -u)\n"
+                "  -?, --help                 Give this help list\n"
+                "      --usage                (use alone)\n"
+                "  -V, --version              Print program version (use alone)\n"
+                "Report bugs to <thrash@igbb.msstate.edu>.\n",
+                usage_head);
+        exit(EXIT_FAILURE);
+      }
+    }
+  }
+  return o;
+}
+
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+struct mate_job {
+  qb_ctx *ctx;
+  int mate;
+  const char *path;
+  int rc;                /* 0 ok, else a qb_status / reader failure */
+  char err[256];
+  uint64_t reads, bases, text_bytes;
+  double inflate_s, wall_s;
+  int stream_status;
+};
+
+/* reader thread of one mate: inflate + frame + pack + submit, until the stream ends */
+static void *mate_thread(void *arg) {
+  struct mate_job *j = (struct mate_job *)arg;
+  const double t0 = now_s();
+  fqr_reader *r = fqr_open(j->path);
+  if (!r) {
+    j->rc = -100;
+    snprintf(j->err, sizeof j->err, "cannot open %s", j->path);
+    return NULL;
+  }
+  int more = 1;
+  while (more) {
+    qb_batch b;
+    if ((j->rc = qb_acquire(j->ctx, &b))) break;
+    uint32_t n = 0, max_len = 0;
+    uint64_t nb = 0;
+    more = fqr_fill(r, b.seq, b.qual, b.offset, b.length, b.cap_bytes, b.cap_reads, &n, &nb, &max_len);
+    if (more < 0) {
+      j->rc = QB_ERR_CAPACITY;
+      snprintf(j->err, sizeof j->err, "%s: a record is longer than a batch slot (raise QB_BATCH_MB)", j->path);
+      qb_submit(j->ctx, &b, j->mate, 0, 0, 0);
+      break;
+    }
+    if ((j->rc = qb_submit(j->ctx, &b, j->mate, n, nb, max_len))) break;
+    j->reads += n;
+    j->bases += nb;
+  }
+  if (j->rc > -100 && j->rc != 0 && !j->err[0]) snprintf(j->err, sizeof j->err, "%s", qb_last_error(j->ctx));
+  j->stream_status = fqr_status(r);
+  j->inflate_s = fqr_inflate_seconds(r);
+  j->text_bytes = fqr_bytes_in(r);
+  fqr_close(r);
+  j->wall_s = now_s() - t0;
+  return NULL;
+}
+
+static long env_long(const char *name, long dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atol(v) : dflt;
+}
+
+int main(int argc, char **argv) {
+  const struct options o = parse_options(argc, argv);
+  const int paired = o.forward != NULL && o.reverse != NULL;
+  const int unpaired = o.unpaired != NULL;
+  const int adapters = o.adapters != NULL;
+  if (paired == unpaired) { /* quack.c:872-875 */
+    printf("%s\n", "Usage: quack [OPTION...]\nTry `quack --help' or `quack --usage' for more information.");
+    exit(1);
+  }
+  const double t_start = now_s();
+
+  uint32_t *keys = NULL;
+  long n_keys = 0;
+  if (adapters) { /* read_adapters(), quack.c:877 */
+    n_keys = fqr_read_adapter_keys(o.adapters, &keys);
+    if (n_keys < 0) {
+      fprintf(stderr, "quack: cannot open adapters file %s\n", o.adapters);
+      return 2;
+    }
+  }
+
+  qb_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.n_devices = (int)env_long("QB_DEVICES", 1);
+  cfg.len_cap = (uint32_t)env_long("QB_LEN_CAP", 65536);
+  cfg.n_mates = paired ? 2 : 1;
+  cfg.adapters_enabled = adapters;
+  cfg.adapter_keys = keys;
+  cfg.n_adapter_keys = (uint32_t)n_keys;
+  cfg.batch_bytes = (uint64_t)env_long("QB_BATCH_MB", 64) << 20;
+  cfg.ring_depth = (int)env_long("QB_RING", 3);
+  cfg.kernel = (int)env_long("QB_KERNEL", QB_KERNEL_AUTO);
+  qb_ctx *ctx = NULL;
+  if (qb_create(&cfg, &ctx)) {
+    fprintf(stderr, "quack: %s\n", qb_last_error(NULL));
+    return 2;
+  }
+
+  struct mate_job jobs[2];
+  pthread_t th[2];
+  memset(jobs, 0, sizeof jobs);
+  for (int m = 0; m < cfg.n_mates; m++) {
+    jobs[m].ctx = ctx;
+    jobs[m].mate = m;
+    jobs[m].path = paired ? (m == 0 ? o.forward : o.reverse) : o.unpaired;
+    pthread_create(&th[m], NULL, mate_thread, &jobs[m]);
+  }
+  for (int m = 0; m < cfg.n_mates; m++) pthread_join(th[m], NULL);
+  for (int m = 0; m < cfg.n_mates; m++)
+    if (jobs[m].rc) {
+      fprintf(stderr, "quack: %s\n", jobs[m].err[0] ? jobs[m].err : "statistics path failed");
+      qb_destroy(ctx);
+      return 2;
+    }
+  const double t_stream = now_s();
+
+  qr_data data[2];
+  memset(data, 0, sizeof data);
+  for (int m = 0; m < cfg.n_mates; m++) {
+    data[m].rows = (uint64_t *)malloc(sizeof(uint64_t) * QB_ROW_U64 * (size_t)cfg.len_cap);
+    if (qb_finish(ctx, m, data[m].rows, cfg.len_cap, &data[m].max_length, &data[m].n_reads)) {
+      fprintf(stderr, "quack: %s\n", qb_last_error(ctx));
+      qb_destroy(ctx);
+      return 2;
+    }
+    if (data[m].n_reads == 0 || data[m].max_length == 0) {
+      /* the reference dereferences a NULL accumulator here (quack.c:450) */
+      fprintf(stderr, "quack: no reads in %s\n", jobs[m].path);
+      qb_destroy(ctx);
+      return 2;
+    }
+  }
+  const double t_finish = now_s();
+
+  qr_begin_document(paired, adapters, o.name, stdout);
+  for (int m = 0; m < cfg.n_mates; m++) {
+    qr_transform(&data[m], stderr);
+    qr_draw(&data[m], m, adapters, stdout);
+  }
+  qr_end_document(o.name, stdout);
+  fflush(stdout);
+  const double t_end = now_s();
+
+  const char *js = getenv("QB_STATS_JSON");
+  if (js && *js) {
+    FILE *f = fopen(js, "w");
+    if (f) {
+      uint64_t reads = 0, bases = 0, text = 0;
+      double inflate = 0;
+      for (int m = 0; m < cfg.n_mates; m++) {
+        reads += jobs[m].reads, bases += jobs[m].bases, text += jobs[m].text_bytes;
+        if (jobs[m].inflate_s > inflate) inflate = jobs[m].inflate_s;
+      }
+      const double stream_s = t_stream - t_start;
+      fprintf(f,
+              "{\"reads\": %llu, \"bases\": %llu, \"text_bytes\": %llu, \"devices\": %d, \"launches\": %llu, "
+              "\"stream_s\": %.6f, \"finish_s\": %.6f, \"render_s\": %.6f, \"total_s\": %.6f, "
+              "\"host_gzip_decode_s_max_over_mates\": %.6f, \"host_gzip_decode_MBps\": %.2f, "
+              "\"reads_per_s\": %.1f, \"bases_per_s\": %.1f}\n",
+              (unsigned long long)reads, (unsigned long long)bases, (unsigned long long)text, cfg.n_devices,
+              (unsigned long long)qb_launch_count(ctx), stream_s, t_finish - t_stream, t_end - t_finish, t_end - t_start,
+              inflate, inflate > 0 ? (double)text / cfg.n_mates / inflate / 1e6 : 0.0, (double)reads / stream_s,
+              (double)bases / stream_s);
+      fclose(f);
+    }
+  }
+  for (int m = 0; m < cfg.n_mates; m++) free(data[m].rows);
+  free(keys);
+  qb_destroy(ctx);
+  return 0;
+}

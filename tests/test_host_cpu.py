@@ -1,0 +1,171 @@
+"""Host side of the drop-in (C, CPU only): the batching record reader against the reference reader's
+golden parses, adapter keys from a FASTA file, and the transform+draw restatement against the SVGs the
+unmodified reference binary printed (tests/golden/svg) -- byte for byte."""
+import gzip
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import qb_testutil as util
+from oracle import pyoracle as po
+from quack_b200 import build, capi
+from quack_b200.build import quack_bin
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    build()
+
+
+FILES = {"kat_t": "kat_t.fq", "kat_k": "kat_k.fq", "framing": "framing.fq", "rand_small": "rand_small.fq.gz"}
+
+
+def test_reader_matches_reference_parse(golden_dir):
+    gold = json.load(open(os.path.join(golden_dir, "golden_parse.json")))
+    for name in ("framing", "kat_k"):
+        recs, rc = capi.parse_records(os.path.join(golden_dir, FILES[name]))
+        assert rc == gold[name]["rc"]
+        assert [[s.decode("latin1"), q.decode("latin1") if q else None] for s, q in recs] == gold[name]["records"]
+
+
+@pytest.mark.parametrize("name", sorted(FILES))
+def test_reader_equals_oracle_reader(name, golden_dir):
+    path = os.path.join(golden_dir, FILES[name])
+    assert capi.parse_records(path) == po.parse_records(path)
+
+
+def test_reader_tricky_streams(tmp_path):
+    cases = {
+        "empty": b"",
+        "only_garbage": b"no header here\n\n",
+        "header_at_eof": b"@",
+        "no_final_newline": b"@a\nACGT\n+\nIIII",
+        "crlf": b"@a x\r\nACGT\r\n+\r\nIIII\r\n@b\r\nAC\r\n+\r\nII\r\n",
+        "multi_line": b"@a\nAC\nGT\nAC\n+a\nII\nII\nII\n@b\nA\n+\nI\n",
+        "qual_starts_with_at": b"@a\nACGT\n+\n@III\n@b\nAC\n+\n@@\n",
+        "truncated_qual": b"@a\nACGTACGT\n+\nIII\n",
+        "qual_too_long": b"@a\nACGT\n+\nIIIIII\n@b\nAC\n+\nII\n",
+        "fasta_then_fastq": b">f\nACGT\n@a\nAC\n+\nII\n",
+        "zero_length": b"@a\n\n+\n\n@b\nAC\n+\nII\n",
+        "lone_cr_line": b"@a\n\r\nAC\n+\nIII\n",
+    }
+    for name, data in cases.items():
+        p = tmp_path / (name + ".fq")
+        p.write_bytes(data)
+        assert capi.parse_records(str(p)) == po.parse_records(str(p)), name
+    g = tmp_path / "multi_member.fq.gz"
+    g.write_bytes(gzip.compress(b"@a\nACGT\n+\nIIII\n") + gzip.compress(b"@b\nAC\n+\nII\n"))
+    recs, rc = capi.parse_records(str(g))
+    assert recs == [(b"ACGT", b"IIII"), (b"AC", b"II")] and rc == -1
+
+
+def test_batches_cover_the_file_in_order(golden_dir):
+    path = os.path.join(golden_dir, "rand_small.fq.gz")
+    recs, _ = po.parse_records(path)
+    batches, status = capi.read_batches(path, cap_bytes=7000, cap_reads=40)
+    assert status == -1 and len(batches) > 20
+    got = []
+    for seq, qual, off, ln, ml in batches:
+        assert len(off) <= 40 and len(seq) <= 7000 and (len(ln) == 0 or ml == ln.max())
+        assert np.array_equal(off[1:], np.cumsum(ln)[:-1].astype(np.uint32)) and (len(off) == 0 or off[0] == 0)
+        got += [(seq[o: o + l].tobytes(), qual[o: o + l].tobytes()) for o, l in zip(off, ln)]
+    assert got == recs
+    # truncated stream: everything before the bad record is delivered, then the stream is over (quack.c:193)
+    batches, status = capi.read_batches(os.path.join(golden_dir, "framing.fq"), 1 << 16, 100)
+    assert status == -2 and sum(len(b[2]) for b in batches) == 3
+
+
+def test_read_adapters_from_fasta(golden_dir, adapters_fa, tmp_path):
+    gold = np.load(os.path.join(golden_dir, "golden_adapter_keys.npy"))
+    keys = capi.read_adapters(adapters_fa)
+    assert len(keys) == 769 and np.array_equal(np.unique(keys), gold)
+    gz = tmp_path / "a.fa.gz"
+    gz.write_bytes(gzip.compress(open(adapters_fa, "rb").read()))
+    assert np.array_equal(capi.read_adapters(str(gz)), keys)
+
+
+def _gold_result(raw, name, tag):
+    ml, n = raw[f"{name}.{tag}.meta"]
+    return capi.Result(raw[f"{name}.{tag}.rows"], int(ml), int(n))
+
+
+def _golden_svg(golden_dir, name):
+    p = os.path.join(golden_dir, "svg", name + ".svg")
+    return open(p, "rb").read() if os.path.exists(p) else gzip.open(p + ".gz", "rb").read()
+
+
+RENDER = {  # golden svg -> (first fixture, second fixture, adapters, name)
+    "u_kat_t": ("kat_t", None, False, None),
+    "u_kat_t_ad": ("kat_t", None, True, None),
+    "u_kat_t_ad_name": ("kat_t", None, True, "tiny"),
+    "u_kat_k_ad": ("kat_k", None, True, None),
+    "pe_kat_t_kat_k_ad_name": ("kat_t", "kat_k", True, "pair"),
+    "u_rand": ("rand_small", None, False, None),
+    "u_rand_ad": ("rand_small", None, True, None),
+    "pe_rand_kat_k": ("rand_small", "kat_k", False, None),
+    "pe_rand_rand_ad_name": ("rand_small", "rand_small", True, "rand x2"),
+}
+
+
+@pytest.mark.parametrize("svg", sorted(RENDER))
+def test_render_is_byte_identical_to_reference(svg, golden_dir, tmp_path):
+    first, second, ad, name = RENDER[svg]
+    raw = np.load(os.path.join(golden_dir, "golden_raw.npz"))
+    tag = "ad" if ad else "noad"
+    out = str(tmp_path / "o.svg")
+    capi.render_svg(_gold_result(raw, first, tag), _gold_result(raw, second, tag) if second else None, ad, name, out)
+    got = open(out, "rb").read()
+    want = _golden_svg(golden_dir, svg)
+    md5 = json.load(open(os.path.join(golden_dir, "svg", "index.json")))["md5"][svg]
+    assert hashlib.md5(want).hexdigest() == md5
+    if got != want:
+        gl, wl = got.split(b"\n"), want.split(b"\n")
+        for i, (a, b) in enumerate(zip(gl, wl)):
+            assert a == b, f"line {i + 1}: {a[:160]!r} != {b[:160]!r}"
+        assert len(gl) == len(wl)
+
+
+@pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref not built")
+def test_render_vs_live_reference_random_and_binning(tmp_path):
+    """Fresh inputs through the reference binary itself, incl. reads > 3000 bp (100-bp binning) and a
+    phred64-looking file (encoding detection)."""
+    rng = np.random.default_rng(12)
+    specs = {"long": (40, 2500, 3400, 2, 41), "phred64": (300, 50, 120, 31, 71), "mid": (500, 1, 480, 0, 60)}  # <= 500: the reference keeps averages[500] on the stack
+    for name, (n, lmin, lmax, qlo, qhi) in specs.items():
+        p = str(tmp_path / f"{name}.fq")
+        with open(p, "wb") as f:
+            for i in range(n):
+                l = int(rng.integers(lmin, lmax + 1))
+                s = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=l).tobytes()
+                q = (rng.integers(qlo, qhi + 1, size=l).astype(np.uint8) + 33).tobytes()
+                f.write(b"@r%d\n%s\n+\n%s\n" % (i, s, q))
+        for ad in (None, util.ADAPTER_FA):
+            want = po.ref_svg(["-u", p] + (["-a", ad] if ad else []))
+            res = po.ref_read_fastq(p, ad)   # raw arrays from the reference; only the renderer is under test
+            out = str(tmp_path / "o.svg")
+            capi.render_svg(capi.Result(res.rows, res.max_length, res.n_reads), None, ad is not None, None, out)
+            assert open(out, "rb").read() == want, (name, ad)
+
+
+def test_cli_usage_and_exit_codes():
+    q = quack_bin()
+    run = lambda *a: subprocess.run([q, *a], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    r = run("-V")
+    assert (r.returncode, r.stdout) == (0, b"quack 1.1.1\n")
+    r = run()
+    assert r.returncode == 1 and r.stdout.startswith(b"Usage: quack [OPTION...]\nquack -- A FASTQ") and \
+        r.stdout.endswith(b"Try `quack --help' or `quack --usage' for more information.\n")
+    r = run("-x", "y", "-u")  # even argc: nothing parsed
+    assert r.returncode == 1
+    r = run("--bogus", "1")
+    assert r.returncode == 1 and r.stderr.startswith(b"Usage: quack") and r.stdout == b""
+    if po.have_ref():
+        for args in ([], ["-V"], ["--help"], ["-?"], ["--usage"], ["--bogus", "1"], ["-u", "x", "-1", "a", "-2", "b"],
+                     ["-n", "name"], ["-1", "only_forward"]):
+            ref = subprocess.run([po.REF_BIN, *args], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            got = run(*args)
+            assert (got.returncode, got.stdout, got.stderr) == (ref.returncode, ref.stdout, ref.stderr), args
