@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
     L.qb_dbatch_free.restype = None
     L.qb_launch_count.argtypes = [vp]
     L.qb_launch_count.restype = C.c_uint64
+    L.qb_kernel_counts.argtypes = [vp, _u64p, _u64p]
     L.qb_profile_enable.argtypes = [vp, C.c_int]
     L.qb_profile_collect.argtypes = [vp, C.POINTER(C.c_float), _u64p, C.c_int]
     L.qb_timer_start.argtypes = [vp, C.c_int]
@@ -295,6 +296,13 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(lib().qb_launch_count(self.h))
+
+    @property
+    def kernel_counts(self):
+        """(launches of the simple kernel, launches of the fused kernel)."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._chk(lib().qb_kernel_counts(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def measure_h2d(self, nbytes: int = 256 << 20, iters: int = 5, device_index: int = 0) -> float:
         g = C.c_double()

@@ -95,7 +95,7 @@ struct qb_ctx {
   std::mutex mu;
   uint64_t next_slot = 0;
   std::string err;
-  uint64_t launches = 0;
+  uint64_t launches = 0, launches_fused = 0, launches_simple = 0;
   size_t acc_u64 = 0;  // len_cap*97 + counters
   qb::AdapterSet ad_host_template{};
   uint32_t bloom_mul = 0;
@@ -173,23 +173,31 @@ qb::Accum accum(const qb_ctx *ctx, const Device &d, int mate) {
 int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaStream_t stream) {
   if (v.n_reads == 0) return QB_OK;
   const qb::AdapterSet ad = adapter_set(ctx, d);
-  const qb::Accum ac = accum(ctx, d, mate);
+  qb::Accum ac = accum(ctx, d, mate);
   int kernel = ctx->cfg.kernel;
   qb::FusedPlan plan{};
   if (kernel != QB_KERNEL_SIMPLE) {
-    plan = qb::fused_plan(ctx->cfg.len_cap, v.max_len, ad.enabled, d.sm_count, (uint32_t)d.smem_optin, ctx->qbase);
+    // The shared-memory histogram is sized by the longest read of THIS batch (the caller's max_len
+    // promise; a longer read is counted as an error and fails qb_finish), not by len_cap: a context
+    // opened for 65536-bp reads still runs short-read batches on the fused kernel.
+    uint32_t eff_cap = ctx->cfg.len_cap;
+    if (v.max_len && v.max_len < eff_cap) eff_cap = v.max_len < 11u ? 11u : v.max_len;
+    plan = qb::fused_plan(eff_cap, v.max_len, ad.enabled, d.sm_count, (uint32_t)d.smem_optin, ctx->qbase);
     if (!plan.ok) {
       if (kernel == QB_KERNEL_FUSED)
-        return fail(ctx, QB_ERR_CAPACITY, "len_cap %u does not fit the fused kernel's shared-memory histogram",
-                    ctx->cfg.len_cap);
+        return fail(ctx, QB_ERR_CAPACITY, "reads of up to %u bp do not fit the fused kernel's shared-memory histogram",
+                    eff_cap);
       kernel = QB_KERNEL_SIMPLE;
-    } else
+    } else {
       kernel = QB_KERNEL_FUSED;
+      ac.len_cap = eff_cap;
+    }
   }
   qb_ctx::ProfRec *rec = nullptr;
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->launches++;
+    (kernel == QB_KERNEL_FUSED ? ctx->launches_fused : ctx->launches_simple)++;
     if ((int)ctx->prof.size() < ctx->prof_cap) {
       qb_ctx::ProfRec r{};
       if (cudaEventCreate(&r.e0) == cudaSuccess && cudaEventCreate(&r.e1) == cudaSuccess) {
@@ -592,7 +600,7 @@ int qb_finish(qb_ctx *ctx, int mate, uint64_t *rows_out, uint64_t rows_cap, uint
   unsigned long long *rows = ctx->h_result;
   const unsigned long long *cnt = rows + (size_t)cap * qb::kRow;
   if (cnt[qb::kCntError])
-    return fail(ctx, QB_ERR_CAPACITY, "%llu tile(s)/read(s) exceeded len_cap or the batch layout rules; result invalid",
+    return fail(ctx, QB_ERR_CAPACITY, "%llu tile(s)/read(s) exceeded len_cap, the max_len given at submit, or the batch layout rules; result invalid",
                 cnt[qb::kCntError]);
   uint64_t ml = 0;
   for (uint32_t i = 0; i < cap; i++)
@@ -631,6 +639,13 @@ int qb_invalid_quality_count(qb_ctx *ctx, int mate, uint64_t *out) {
 }
 
 uint64_t qb_launch_count(const qb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int qb_kernel_counts(const qb_ctx *ctx, uint64_t *n_simple, uint64_t *n_fused) {
+  if (!ctx) return QB_ERR_ARG;
+  if (n_simple) *n_simple = ctx->launches_simple;
+  if (n_fused) *n_fused = ctx->launches_fused;
+  return QB_OK;
+}
 
 int qb_profile_enable(qb_ctx *ctx, int max_launches) {
   if (!ctx || max_launches < 0) return QB_ERR_ARG;

@@ -217,3 +217,37 @@ def test_large_adapter_set(kernel):
     batch = util.random_batch(123, 20000, 40, 150, plant=0.3, plant_seq=recs[5])
     got = run_gpu(batch, 150, keys, kernel)
     util.assert_same(got, po.accumulate_batch(*batch, table), "large set")
+
+
+def test_auto_kernel_is_planned_per_batch(table, keys):
+    """len_cap only sizes the accumulator: a context opened for 65536-bp reads (the CLI default) still
+    runs short-read batches on the fused kernel, and falls back to the simple kernel only for a batch
+    whose longest read is beyond the shared-memory histogram."""
+    short = util.random_batch(41, 20000, 35, 300, plant=0.2)
+    long_ = util.random_batch(42, 300, 200, 900, plant=0.2)
+    with capi.Context(65536, adapter_keys=keys) as ctx:
+        ctx.accumulate_host(0, *short)
+        res = ctx.finish(0)
+        assert ctx.kernel_counts == (0, ctx.launch_count) and ctx.launch_count >= 1
+        util.assert_same(res, po.accumulate_batch(*short, table), "short reads, big len_cap")
+        n_fused = ctx.launch_count
+        ctx.accumulate_host(0, *long_)
+        res = ctx.finish(0)
+        assert ctx.kernel_counts == (ctx.launch_count - n_fused, n_fused) and ctx.launch_count > n_fused
+    want = po.accumulate_batch(*long_, table)
+    w1 = po.accumulate_batch(*short, table)
+    rows = want.rows.copy()
+    rows[: w1.max_length] += w1.rows
+    assert res.n_reads == want.n_reads + w1.n_reads and res.max_length == want.max_length
+    assert np.array_equal(res.rows, rows)
+
+
+def test_max_len_promise_is_enforced(keys):
+    """A batch submitted with a max_len smaller than its longest read is rejected loudly, not mis-counted."""
+    batch = util.random_batch(43, 200, 100, 100)
+    with capi.Context(304, adapter_keys=keys, kernel=capi.KERNEL_FUSED) as ctx:
+        b = ctx.upload(*batch, max_len=50)
+        b.run(0)
+        with pytest.raises(capi.QbError):
+            ctx.finish(0)
+        b.free()
