@@ -16,7 +16,8 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 
 
 def lib_path() -> str:
-    return os.path.join(LIBDIR, "libquack_b200.so")
+    # QB_LIB: an alternative build of the library (kernel experiments, e.g. a different warp count)
+    return os.environ.get("QB_LIB") or os.path.join(LIBDIR, "libquack_b200.so")
 
 
 def quack_bin() -> str:
@@ -55,7 +56,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             subprocess.run(["gcc", "-O3", "-std=c11", "-D_DEFAULT_SOURCE", "-fPIC", "-Wall", "-c", c, "-o", o,
                             "-I" + os.path.join(HERE, "..", "include")], check=True)
             objs.append(o)
-        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", out, *srcs, *objs, "-ldl", "-lz", "-lpthread"]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("QB_NVCC_EXTRA", "").split(), "-shared", "-o", out, *srcs, *objs,
+               "-ldl", "-lz", "-lpthread"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)

@@ -78,7 +78,7 @@ struct Device {
   int smem_optin = 0;
   std::vector<unsigned long long *> acc;  // per mate: [len_cap*97 rows][kNumCounters]
   unsigned long long *reduce_buf = nullptr;
-  uint32_t *d_bitmap = nullptr, *d_bloom = nullptr, *d_exact = nullptr;
+  uint32_t *d_bitmap = nullptr, *d_anchor = nullptr, *d_exact = nullptr;
   std::vector<Slot> slots;
   cudaStream_t main_stream = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;  // qb_timer_*
@@ -98,8 +98,8 @@ struct qb_ctx {
   uint64_t launches = 0, launches_fused = 0, launches_simple = 0;
   size_t acc_u64 = 0;  // len_cap*97 + counters
   qb::AdapterSet ad_host_template{};
-  uint32_t bloom_mul = 0;
-  double bloom_fp = 0;
+  uint32_t n_anchors = 0;     // distinct 7-mer anchors of the adapter set
+  double anchor_density = 0;  // n_anchors / 2^14: filter pass rate per probe on random bases
   uint32_t qbase = 33;  // score bin s = q - qbase, s in [0,62] counted in shared memory
   ncclComm_t rank_comm = nullptr;  // multi-process communicator
   int n_ranks = 1, rank = 0;
@@ -154,9 +154,8 @@ inline size_t pad_reads(uint32_t n) { return ((size_t)n + 3 & ~(size_t)3) + 16; 
 qb::AdapterSet adapter_set(const qb_ctx *ctx, const Device &d) {
   qb::AdapterSet a;
   a.bitmap = d.d_bitmap;
-  a.bloom = d.d_bloom;
+  a.anchor = d.d_anchor;
   a.exact = d.d_exact;
-  a.bloom_mul = ctx->bloom_mul;
   a.enabled = ctx->cfg.adapters_enabled ? 1 : 0;
   return a;
 }
@@ -272,13 +271,14 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
     if (v >= 33 && v <= 64) ctx->qbase = (uint32_t)v;
   }
 
-  std::vector<uint32_t> bitmap, bloom, exact;
+  std::vector<uint32_t> bitmap, anchor, exact;
   if (cfg.adapters_enabled) {
     if (cfg.n_adapter_keys && !cfg.adapter_keys) {
       delete ctx;
       return fail(nullptr, QB_ERR_ARG, "adapter_keys is NULL");
     }
-    qb::build_adapter_images(cfg.adapter_keys, cfg.n_adapter_keys, bitmap, bloom, exact, ctx->bloom_mul, ctx->bloom_fp);
+    qb::build_adapter_images(cfg.adapter_keys, cfg.n_adapter_keys, bitmap, anchor, exact, ctx->n_anchors,
+                             ctx->anchor_density);
   }
 
 #define QB_CREATE_CUDA(call)                                                                          \
@@ -314,8 +314,8 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
     if (cfg.adapters_enabled) {
       QB_CREATE_CUDA(cudaMalloc(&d.d_bitmap, bitmap.size() * 4));
       QB_CREATE_CUDA(cudaMemcpy(d.d_bitmap, bitmap.data(), bitmap.size() * 4, cudaMemcpyHostToDevice));
-      QB_CREATE_CUDA(cudaMalloc(&d.d_bloom, bloom.size() * 4));
-      QB_CREATE_CUDA(cudaMemcpy(d.d_bloom, bloom.data(), bloom.size() * 4, cudaMemcpyHostToDevice));
+      QB_CREATE_CUDA(cudaMalloc(&d.d_anchor, anchor.size() * 4));
+      QB_CREATE_CUDA(cudaMemcpy(d.d_anchor, anchor.data(), anchor.size() * 4, cudaMemcpyHostToDevice));
       if (!exact.empty()) {
         QB_CREATE_CUDA(cudaMalloc(&d.d_exact, exact.size() * 4));
         QB_CREATE_CUDA(cudaMemcpy(d.d_exact, exact.data(), exact.size() * 4, cudaMemcpyHostToDevice));
@@ -381,7 +381,7 @@ void qb_destroy(qb_ctx *ctx) {
     for (auto p : d.acc) cudaFree(p);
     cudaFree(d.reduce_buf);
     cudaFree(d.d_bitmap);
-    cudaFree(d.d_bloom);
+    cudaFree(d.d_anchor);
     cudaFree(d.d_exact);
     cudaFree(d.l2_scratch);
     if (d.t0) cudaEventDestroy(d.t0);
@@ -893,11 +893,11 @@ int qb_microbench(char *report, size_t cap) {
   return qb::run_microbench(sm, report, cap) == cudaSuccess ? QB_OK : QB_ERR_CUDA;
 }
 
-// tools: the filter parameters chosen for the adapter set (false-positive rate over all 2^20 keys)
-int qb_adapter_filter_info(const qb_ctx *ctx, uint32_t *mul, double *fp_rate) {
+// tools: the anchor filter built for the adapter set (distinct 7-mer anchors, pass rate on random bases)
+int qb_adapter_filter_info(const qb_ctx *ctx, uint32_t *n_anchors, double *density) {
   if (!ctx) return QB_ERR_ARG;
-  if (mul) *mul = ctx->bloom_mul;
-  if (fp_rate) *fp_rate = ctx->bloom_fp;
+  if (n_anchors) *n_anchors = ctx->n_anchors;
+  if (density) *density = ctx->anchor_density;
   return QB_OK;
 }
 

@@ -44,11 +44,9 @@ uint32_t key_to_internal(uint32_t ref_key) {
   return k;
 }
 
-static inline uint32_t bw_index(uint32_t p) { return (p >> 7) & 255u; }
-
 void build_adapter_images(const uint32_t *ref_keys, uint32_t n, std::vector<uint32_t> &bitmap,
-                          std::vector<uint32_t> &bloom, std::vector<uint32_t> &exact, uint32_t &mul,
-                          double &fp_rate) {
+                          std::vector<uint32_t> &anchor, std::vector<uint32_t> &exact, uint32_t &n_anchors,
+                          double &anchor_density) {
   bitmap.assign(QB_KEY_SPACE / 32, 0);
   std::vector<uint32_t> keys;
   keys.reserve(n);
@@ -59,43 +57,44 @@ void build_adapter_images(const uint32_t *ref_keys, uint32_t n, std::vector<uint
       keys.push_back(k);
     }
   }
-  // pick the multiplier with the fewest false positives over the whole key space (2^20 probes each)
-  static const uint32_t cand[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u,
-                                  0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
-  uint32_t best_mul = cand[0];
-  uint64_t best_fp = ~0ull;
-  std::vector<uint32_t> words(256), best_words(256);
-  for (uint32_t m : cand) {
-    std::fill(words.begin(), words.end(), 0u);
-    for (uint32_t k : keys) {
-      const uint32_t p = k * m;
-      words[bw_index(p)] |= (1u << (k & 31u)) | (1u << ((p >> 15) & 31u));
+  // Anchor filter: every 10-mer window [s, s+9] contains exactly one 7-mer that starts at a position
+  // congruent to 3 mod 4 (start s, s+1, s+2 or s+3).  A window can only be in the set if that 7-mer is
+  // one of the 7-mers found at offsets 0..3 of a set member, so the kernel probes one 7-mer per 4 bases
+  // against this exact 2^14-bit map and confirms the 4 windows around a hit against the exact key set.
+  anchor.assign(kAnchorWords, 0);
+  n_anchors = 0;
+  for (uint32_t k : keys)
+    for (uint32_t o = 0; o < 4; o++) {
+      const uint32_t a = (k >> (2 * o)) & (kAnchorSpace - 1);
+      if (!((anchor[a >> 5] >> (a & 31)) & 1u)) {
+        anchor[a >> 5] |= 1u << (a & 31);
+        n_anchors++;
+      }
     }
-    uint64_t fp = 0;
-    for (uint32_t k = 0; k < QB_KEY_SPACE; k++) {
-      const uint32_t p = k * m;
-      const uint32_t w = words[bw_index(p)];
-      if (((w >> (k & 31u)) & (w >> ((p >> 15) & 31u)) & 1u) && !((bitmap[k >> 5] >> (k & 31)) & 1u)) fp++;
-    }
-    if (fp < best_fp) {
-      best_fp = fp;
-      best_mul = m;
-      best_words = words;
-    }
-  }
-  mul = best_mul;
-  fp_rate = (double)best_fp / (double)QB_KEY_SPACE;
-  bloom.resize(256 * 32);
-  for (uint32_t w = 0; w < 256; w++)
-    for (uint32_t b = 0; b < 32; b++) bloom[w * 32 + b] = best_words[w];  // one copy per bank
+  anchor_density = (double)n_anchors / (double)kAnchorSpace;
   exact.clear();
-  if (keys.size() * 3 <= kExactSlots) {
+  if (keys.size() * 3 <= kExactSlots) {  // cuckoo insertion; at this load it needs a handful of moves at most
     exact.assign(kExactSlots, kExactEmpty);
+    bool ok = true;
     for (uint32_t k : keys) {
-      uint32_t i = exact_slot(k);
-      while (exact[i] != kExactEmpty) i = (i + 1u) & (kExactSlots - 1u);
-      exact[i] = k;
+      uint32_t cur = k;
+      bool second = false, placed = false;
+      for (int kick = 0; kick < 1000 && !placed; kick++) {
+        const uint32_t slot = (second ? exact_off2(cur) : exact_off1(cur)) / 4u;
+        if (exact[slot] == kExactEmpty) {
+          exact[slot] = cur;
+          placed = true;
+        } else {
+          std::swap(cur, exact[slot]);
+          second = (slot < kExactHalf);  // the evicted key lived in this half: try its other slot
+        }
+      }
+      if (!placed) {
+        ok = false;
+        break;
+      }
     }
+    if (!ok) exact.clear();  // kernels then confirm against the 2^20-bit map in L2
   }
 }
 

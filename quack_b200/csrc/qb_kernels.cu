@@ -6,14 +6,14 @@
 //                   for len_cap beyond what the shared-memory histogram holds (still CUDA).
 //   fused_kernel  : persistent, one CTA per SM.  A producer warp streams tiles of whole reads
 //                   (seq bytes, qual bytes, offsets, lengths) into shared memory with 1-D TMA bulk
-//                   copies (cp.async.bulk + mbarrier, 3 stages).  Consumer warps then make two
+//                   copies (cp.async.bulk + mbarrier, 2-4 stages).  31 consumer warps then make two
 //                   passes over the staged tile:
-//                     phase A (flat, one aligned 4-byte word per lane): SWAR base -> 2-bit code,
+//                     phase A (flat, one aligned 16-byte unit per lane): SWAR base -> 2-bit code,
 //                       score byte -> 6-bit bin, fused into one key byte K = code<<6 | bin per
-//                       base, written to a K buffer; with -a, the 4 adapter 10-mer windows ending
-//                       in the lane's word are tested against a bank-replicated blocked Bloom
-//                       filter in shared memory (one conflict-free LDS per window) and confirmed
-//                       against the exact 2^20-bit set in L2 only on a filter hit.
+//                       base, written over the quality bytes; with -a, one 7-mer "anchor" per 4
+//                       bases is tested against an exact 2^14-bit map in shared memory (every 10-mer
+//                       window contains exactly one anchor), hits are queued and the 4 windows around
+//                       each are confirmed against the exact key set.
 //                     phase H (one warp per read, lane <-> position): one shared-memory atomic
 //                       per base into a JOINT (code,score) x position histogram of packed u16
 //                       counters whose bank is the position mod 32, so a warp's 32 updates never
@@ -115,13 +115,27 @@ cudaError_t launch_simple(const BatchView &b, const Accum &a, const AdapterSet &
 }
 
 // ------------------------------------------------------------------------------------------
-// fused kernel
+// fused kernel (v3)
+//
+// The kernel is bound by instruction issue (4 warp instructions per cycle per SM) and, second, by
+// shared-memory wavefronts, not by HBM: at 2 bytes per base the HBM roofline leaves 2.9 SM cycles per 32
+// bases.  Everything below is organised to spend as few warp instructions per base as possible:
+//   * one CTA-wide barrier per tile (two with -a); stages are released through the mbarrier, the
+//     per-read counters of a tile are settled while the next tile is in flight;
+//   * phase A is flat SWAR over aligned 16-byte units (4 bases per 32-bit lane operation);
+//   * phase H is straight-line code per read: N byte loads, N multiply-adds, N shared atomics, selected
+//     once per tile when all reads of the tile have the same length (reduction barrier), else per read;
+//   * the adapter scan probes ONE 7-mer per 4 bases (the anchor that every 10-mer window must contain)
+//     instead of one 10-mer per base; anchor hits are queued and confirmed against the exact key set.
 // ------------------------------------------------------------------------------------------
 
 constexpr int kCW = kFusedConsumerWarps;       // consumer warps
 constexpr int kCThreads = kCW * 32;
 constexpr int kThreads = kCThreads + 32;       // + producer warp
-constexpr int kMaxStages = 3;
+constexpr int kMaxStages = 4;
+constexpr uint32_t kPadAfter = 48;             // readable bytes behind a staged buffer (look-ahead unit)
+constexpr uint32_t kCandCap = 768;             // anchor hits queued per tile (one entry per anchor)
+constexpr uint32_t kIdxCap = kMaxTileReads + 8;  // staged offsets/lengths: tile reads + alignment slack
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -130,10 +144,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar_s) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -142,9 +156,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "@p bra QB_DONE;\n"
       "bra QB_WAIT;\n"
       "QB_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
+      "}\n" ::"r"(bar_s),
       "r"(parity)
       : "memory");
+}
+// Producer-side wait: the producer lane has nothing else to do, so it must not burn issue slots of the
+// consumer warps that share its scheduler: long hardware suspend hint plus a sleep between polls.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar_s, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar_s), "r"(parity), "r"(2000u)
+        : "memory");
+    if (done) break;
+    __nanosleep(100);
+  }
 }
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -158,11 +190,32 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+template <uint32_t kOff>
 __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
-  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+  asm volatile("red.shared.add.u32 [%0+%2], %1;" ::"r"(addr), "r"(v), "n"(kOff) : "memory");
 }
 __device__ __forceinline__ void consumer_bar() {
   asm volatile("bar.sync 1, %0;" ::"n"(kCThreads) : "memory");
+}
+// barrier of the consumer warps that also ANDs a predicate over all of them
+__device__ __forceinline__ uint32_t consumer_bar_and(uint32_t pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.u32 q, %1, 0;\n"
+      "bar.red.and.pred p, 1, %2, q;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(out)
+      : "r"(pred), "n"(kCThreads)
+      : "memory");
+  return out;
 }
 
 struct FusedArgs {
@@ -173,19 +226,14 @@ struct FusedArgs {
   uint32_t n_tiles;
 };
 
-constexpr uint32_t kPadBefore = 16;   // readable bytes in front of a staged buffer (halo lanes, windows)
-constexpr uint32_t kPadAfter = 256;   // readable bytes behind it (last partial warp step)
-constexpr uint32_t kCandCap = 512;    // Bloom-positive candidates queued per tile
-
-struct Candidate {
-  int32_t unit;      // 8-byte unit index in the staged tile
-  uint32_t lo, hi;   // 2-bit codes of the 24 bases ending with this unit's 8 bases (see phase A)
-};
-
-// shared-memory carve-up, all offsets multiples of 16 bytes
+// shared-memory carve-up, all offsets multiples of 16 bytes.  Everything a tile needs (bytes, index
+// slices, its description and its two mbarriers) sits in one stage block at fixed offsets, so the tile
+// loop carries a single stage address.
 struct SmemLayout {
-  uint32_t hist, bloom, exact, lenhist, kmerhist, cand, stage0, stage_stride, seq_off, qual_off, soff_off, slen_off,
-      fhit_off, meta, bars, total;
+  uint32_t hist, afilt, exact, lenhist, kmerhist, cand, fhit, ccount, stage0, stage_stride;
+  uint32_t buf;                                  // bytes of one staged byte buffer (seq or qual)
+  uint32_t o_qual, o_soff, o_slen, o_meta, o_full, o_empty;  // offsets inside a stage block
+  uint32_t total;
 };
 
 __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
@@ -193,32 +241,33 @@ __host__ __device__ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15
 __host__ __device__ inline SmemLayout smem_layout(uint32_t half_len, uint32_t len_cap, uint32_t tile_bytes,
                                                   uint32_t stages, int adapters) {
   SmemLayout L;
-  const uint32_t buf = kPadBefore + tile_bytes + kPadAfter;
+  L.buf = tile_bytes + kPadAfter;
   uint32_t o = 0;
   L.hist = o;
   o += 256u * half_len * 4u;
-  L.bloom = o;
-  o += adapters ? kBloomBytes : 0u;
+  L.afilt = o;
+  o += adapters ? kAnchorSmemBytes : 0u;
   L.exact = o;
   o += adapters ? kExactSlots * 4u : 0u;
   L.lenhist = o;
   o += align16(len_cap * 4u);
   L.kmerhist = o;
-  o += align16(len_cap * 4u);
+  o += adapters ? align16(len_cap * 4u) : 0u;
   L.cand = o;
-  o += adapters ? align16(kCandCap * (uint32_t)sizeof(Candidate)) : 0u;
+  o += adapters ? 2u * kCandCap * 8u : 0u;
+  L.fhit = o;
+  o += adapters ? 2u * kMaxTileReads * 4u : 0u;
+  L.ccount = o;
+  o += 16u;  // 3 candidate counters, rotating per tile
   L.stage0 = o;
-  L.seq_off = kPadBefore;
-  L.qual_off = buf + kPadBefore;
-  L.soff_off = 2u * buf;
-  L.slen_off = L.soff_off + kMaxTileReads * 4u;
-  L.fhit_off = L.slen_off + kMaxTileReads * 4u;
-  L.stage_stride = L.fhit_off + kMaxTileReads * 4u;
+  L.o_qual = L.buf;
+  L.o_soff = 2u * L.buf;
+  L.o_slen = L.o_soff + kIdxCap * 4u;
+  L.o_meta = L.o_slen + kIdxCap * 4u;  // uint4: lo_al, n_reads, span, first index slot
+  L.o_full = L.o_meta + 16u;
+  L.o_empty = L.o_full + 8u;
+  L.stage_stride = L.o_meta + 32u;
   o += stages * L.stage_stride;
-  L.meta = o;
-  o += 16u * kMaxStages + 16u;  // per stage: lo_al, n_reads, span, pad; then 2 candidate counters
-  L.bars = o;
-  o += 16u * kMaxStages;  // full, empty per stage
   L.total = o;
   return L;
 }
@@ -232,7 +281,7 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
   return d;
 }
 
-// loop-invariant SWAR constants, kept in registers
+// loop-invariant SWAR constants
 struct KeyConsts {
   uint32_t m5b, x43, m1f, x07, x14, a7f, a3f, m80, mc0, one, qsub;
   __device__ __forceinline__ explicit KeyConsts(uint32_t qbase)
@@ -264,6 +313,16 @@ __device__ __forceinline__ uint32_t key_bytes_bad(uint32_t nc) { return (~nc & 0
 __device__ __forceinline__ bool word_bad(uint32_t qw, uint32_t qsub) {
   const uint32_t qs = qw - qsub;
   return ((qs | (qs + 0x01010101u)) & 0xC0C0C0C0u) != 0u;
+}
+
+// 4 bases' 2-bit codes gathered from bits 7:6 of the 4 bytes of x into the TOP byte of the result,
+// first base least significant (other result bytes are scratch)
+__device__ __forceinline__ uint32_t gather_codes(uint32_t x) { return (x & 0xC0C0C0C0u) * 0x00041041u; }
+// 16 bases (4 words of key bytes or of ~nc) -> 32 bits, first base least significant
+__device__ __forceinline__ uint32_t pack16(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+  const uint32_t lo = __byte_perm(gather_codes(c0), gather_codes(c1), 0x0073);  // bytes: c0.top, c1.top
+  const uint32_t hi = __byte_perm(gather_codes(c2), gather_codes(c3), 0x0073);
+  return __byte_perm(lo, hi, 0x5410);
 }
 
 // largest r with soff[r] <= abs (reads of a tile are in ascending offset order), -1 if none
@@ -301,38 +360,226 @@ __device__ __noinline__ uint32_t exact_word(uint32_t sw, uint32_t qw, uint32_t a
   return n_invalid;
 }
 
-// rare path: window t (0..7) of a Bloom-positive unit.  Re-test it against the filter, then against the
-// exact key set (shared-memory hash table; the 2^20-bit map in L2 if the set was too big for it).
-__device__ __forceinline__ void confirm_window(const Candidate c, int t, const AdapterSet ad,
-                                               const uint8_t *bloom_lane, const uint32_t *exact_s, uint32_t lo_al,
-                                               const uint32_t *soff, const uint32_t *slen, uint32_t nr,
-                                               uint32_t *fhit) {
-  const uint32_t key = __funnelshift_r(c.lo, c.hi, 14 + 2 * t) & 0xFFFFFu;
-  const uint32_t p = key * ad.bloom_mul;
-  const uint32_t word = *reinterpret_cast<const uint32_t *>(bloom_lane + (p & 0x7F80u));
-  if (!((word >> (key & 31u)) & (word >> ((p >> 15) & 31u)) & 1u)) return;
-  bool member = false;
-  if (ad.exact) {
-    for (uint32_t i = exact_slot(key);; i = (i + 1u) & (kExactSlots - 1u)) {
-      const uint32_t v = exact_s[i];
-      if (v == key) member = true;
-      if (v == key || v == kExactEmpty) break;
+// ---- phase H building blocks ----
+// Shared-memory instruction throughput (the MIO queue), not issue, bounds this phase: a byte load costs
+// about as much as two word loads and a shared atomic ~1.3 cycles whatever the number of active lanes.
+// So a read is walked in WORD steps -- lane l loads the 4 key bytes of positions 128 s + 4 l .. + 3 (two
+// aligned 32-bit loads and a funnel shift, since reads start at any byte) and issues 4 atomics -- and its
+// last <= 32 positions in one BYTE step (lane <-> position).
+//
+// Column of a position inside a histogram row.  Positions [0, Lh) count in the low half-word of a u32
+// counter, [Lh, 2 Lh) in the high half-word.  Within a half, position 4 q + t sits in column
+// t * Lh/4 + q, so the t-th atomic of a word step touches consecutive banks across the lanes; the high
+// half is rotated by kRot columns so that a word step which straddles Lh still puts every lane in its own
+// bank.  Any 32 consecutive positions of one half also fall into 32 different banks (byte steps).
+template <uint32_t Lh>
+struct HLayout {
+  static constexpr uint32_t kRot = (Lh == 96u) ? 24u : 8u;  // Lh = 96: 128 = Lh + 32; Lh = 160: 256 = Lh + 96
+  __host__ __device__ static inline uint32_t column(uint32_t pos, uint32_t &unit) {
+    const bool hi = pos >= Lh;
+    const uint32_t pp = hi ? pos - Lh : pos;
+    uint32_t col = (pp & 3u) * (Lh / 4u) + (pp >> 2);
+    if (hi) {
+      col += kRot;
+      if (col >= Lh) col -= Lh;
     }
-  } else {
-    member = (ad.bitmap[key >> 5] >> (key & 31u)) & 1u;
+    unit = hi ? 0x10000u : 1u;
+    return col;
   }
-  if (!member) return;
-  const uint32_t abs = lo_al + (uint32_t)(c.unit * 8 + t);  // byte on which the window ends
-  const int r = find_read(soff, nr, abs);
-  if (r < 0) return;
-  const uint32_t pos = abs - soff[r];
-  if (pos >= 9u && pos < slen[r]) atomicMin(&fhit[r], pos);  // whole window inside the read
+};
+
+// per-lane constants of the word steps: shared address of the lane's 4 columns (row 0) and the counter unit
+template <uint32_t Lh>
+struct HLane {
+  static constexpr int kWordSteps = (int)((2u * Lh + 127u) / 128u);
+  uint32_t hb[kWordSteps][4];
+  uint32_t unit[kWordSteps];
+  __device__ __forceinline__ void init(uint32_t hist_s, uint32_t lane) {
+#pragma unroll
+    for (int s = 0; s < kWordSteps; s++) {
+      const uint32_t p = 128u * s + 4u * lane;
+      uint32_t u = 0;
+#pragma unroll
+      for (int t = 0; t < 4; t++) hb[s][t] = hist_s + 4u * HLayout<Lh>::column(min(p + t, 2u * Lh - 1u), u);
+      unit[s] = p < 2u * Lh ? u : 0u;
+    }
+  }
+};
+
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int t) {  // one PRMT / shift
+  return t == 3 ? w >> 24 : __byte_perm(w, 0u, 0x4440u | (uint32_t)t);
 }
 
-__device__ __noinline__ void confirm_candidate(const Candidate c, const AdapterSet ad, const uint8_t *bloom_lane,
-                                               const uint32_t *exact_s, uint32_t lo_al, const uint32_t *soff,
-                                               const uint32_t *slen, uint32_t nr, uint32_t *fhit) {
-  for (int t = 0; t < 8; t++) confirm_window(c, t, ad, bloom_lane, exact_s, lo_al, soff, slen, nr, fhit);
+// shape of a read of length L: full word steps, then a partial word step (kind 2), a byte step (kind 1) or nothing
+__device__ __forceinline__ uint32_t h_shape(uint32_t L) {
+  const uint32_t rem = L & 127u;
+  return (L >> 7) * 3u + (rem == 0u ? 0u : (rem <= 32u ? 1u : 2u));
+}
+
+// the 4 key bytes of positions 128 s + 4 lane .. + 3 of the read whose lane-th word starts at kw (any alignment)
+__device__ __forceinline__ uint32_t h_load_word(uint32_t kw) {
+  const uint32_t al = kw & ~3u;
+  const uint32_t w0 = lds_u32(al), w1 = lds_u32(al + 4u);
+  return __funnelshift_r(w0, w1, kw << 3);  // shift = 8 * (kw & 3): the funnel shift wraps at 32
+}
+__device__ __forceinline__ void h_red_word(uint32_t k4, const uint32_t (&hb)[4], uint32_t i0, uint32_t i1, uint32_t i2,
+                                           uint32_t i3, uint32_t row_bytes) {
+  red_shared_add<0>(byte_of(k4, 0) * row_bytes + hb[0], i0);
+  red_shared_add<0>(byte_of(k4, 1) * row_bytes + hb[1], i1);
+  red_shared_add<0>(byte_of(k4, 2) * row_bytes + hb[2], i2);
+  red_shared_add<0>(byte_of(k4, 3) * row_bytes + hb[3], i3);
+}
+
+// One read.  kb = shared address of the read's first key byte; NWF full word steps; KIND as in h_shape.
+// pinc[] = increments of the partial word step, binc / bhb = increment and column address of the byte step.
+template <uint32_t Lh, int NWF, int KIND>
+struct HRead {
+  static constexpr int kWords = NWF + (KIND == 2 ? 1 : 0);
+  uint32_t k4[kWords > 0 ? kWords : 1];
+  uint32_t kbyte;
+  __device__ __forceinline__ void load(uint32_t kb, uint32_t lane) {
+#pragma unroll
+    for (int s = 0; s < kWords; s++) k4[s] = h_load_word(kb + 128u * s + 4u * lane);
+    if (KIND == 1) kbyte = lds_u8(kb + 128u * NWF + lane);
+  }
+  __device__ __forceinline__ void red(const HLane<Lh> &hl, const uint32_t (&pinc)[4], uint32_t bhb, uint32_t binc) const {
+#pragma unroll
+    for (int s = 0; s < NWF; s++) h_red_word(k4[s], hl.hb[s], hl.unit[s], hl.unit[s], hl.unit[s], hl.unit[s], Lh * 4u);
+    if (KIND == 2) h_red_word(k4[NWF], hl.hb[NWF], pinc[0], pinc[1], pinc[2], pinc[3], Lh * 4u);
+    if (KIND == 1) red_shared_add<0>(kbyte * (Lh * 4u) + bhb, binc);
+  }
+};
+
+// increments / addresses of the tail of a read of length L (lanes behind the read's end add 0 to whatever
+// bin the stray byte selects, which keeps the steps free of predicates and branches)
+template <uint32_t Lh, int NWF, int KIND>
+__device__ __forceinline__ void h_tail(const HLane<Lh> &hl, uint32_t hist_s, uint32_t L, uint32_t lane, uint32_t (&pinc)[4],
+                                       uint32_t &bhb, uint32_t &binc) {
+  pinc[0] = pinc[1] = pinc[2] = pinc[3] = 0;
+  bhb = hist_s;
+  binc = 0;
+  if (KIND == 2) {
+    const uint32_t p = 128u * NWF + 4u * lane;
+#pragma unroll
+    for (int t = 0; t < 4; t++) pinc[t] = p + t < L ? hl.unit[NWF < HLane<Lh>::kWordSteps ? NWF : 0] : 0u;
+  }
+  if (KIND == 1) {
+    const uint32_t p = 128u * NWF + lane;
+    uint32_t u;
+    bhb = hist_s + 4u * HLayout<Lh>::column(min(p, 2u * Lh - 1u), u);
+    binc = p < L ? u : 0u;
+  }
+}
+
+// all reads of the tile have length L and lie back to back from kb0: two reads in flight per warp
+template <uint32_t Lh, int NWF, int KIND>
+__device__ __forceinline__ void h_uniform(const HLane<Lh> &hl, uint32_t hist_s, uint32_t kb0, uint32_t L, uint32_t nr,
+                                          uint32_t warp, uint32_t lane) {
+  uint32_t pinc[4], bhb, binc;
+  h_tail<Lh, NWF, KIND>(hl, hist_s, L, lane, pinc, bhb, binc);
+  uint32_t kb = kb0 + warp * L;
+  const uint32_t stride = (uint32_t)kCW * L;
+  uint32_t r = warp;
+  for (; r + kCW < nr; r += 2 * kCW) {
+    HRead<Lh, NWF, KIND> a, b;
+    a.load(kb, lane);
+    b.load(kb + stride, lane);
+    a.red(hl, pinc, bhb, binc);
+    b.red(hl, pinc, bhb, binc);
+    kb += 2u * stride;
+  }
+  if (r < nr) {
+    HRead<Lh, NWF, KIND> a;
+    a.load(kb, lane);
+    a.red(hl, pinc, bhb, binc);
+  }
+}
+template <uint32_t Lh, int NWF, int KIND>
+__device__ __forceinline__ void h_one(const HLane<Lh> &hl, uint32_t hist_s, uint32_t kb, uint32_t L, uint32_t lane) {
+  uint32_t pinc[4], bhb, binc;
+  h_tail<Lh, NWF, KIND>(hl, hist_s, L, lane, pinc, bhb, binc);
+  HRead<Lh, NWF, KIND> a;
+  a.load(kb, lane);
+  a.red(hl, pinc, bhb, binc);
+}
+
+// an opaque copy: keeps a launch constant in a register instead of re-deriving it from the constant bank
+// and the kernel parameters inside the tile loop
+__device__ __forceinline__ uint32_t pin(uint32_t x) {
+  asm volatile("mov.u32 %0, %0;" : "+r"(x));
+  return x;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_u128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ T *shared_ptr(uint32_t addr) {
+  return reinterpret_cast<T *>(__cvta_shared_to_generic((size_t)addr));
+}
+
+// rare path of phase A: re-key the words of a 16-byte unit whose quality bytes fall outside the window,
+// counting their bases exactly
+__device__ __noinline__ uint32_t fix_bad_unit(uint4 sv, uint4 qv, uint4 &K, uint32_t n0, uint32_t n1, uint32_t n2,
+                                              uint32_t n3, uint32_t qsub, uint32_t abs0, uint32_t idx_s, uint32_t nr,
+                                              const Accum a) {
+  const uint32_t *soff = shared_ptr<const uint32_t>(idx_s);
+  const uint32_t *slen = soff + kIdxCap;
+  uint32_t n_invalid = 0;
+  if (word_bad(qv.x, qsub)) K.x = key_bytes_bad(n0), n_invalid += exact_word(sv.x, qv.x, abs0, soff, slen, nr, a);
+  if (word_bad(qv.y, qsub)) K.y = key_bytes_bad(n1), n_invalid += exact_word(sv.y, qv.y, abs0 + 4u, soff, slen, nr, a);
+  if (word_bad(qv.z, qsub)) K.z = key_bytes_bad(n2), n_invalid += exact_word(sv.z, qv.z, abs0 + 8u, soff, slen, nr, a);
+  if (word_bad(qv.w, qsub)) K.w = key_bytes_bad(n3), n_invalid += exact_word(sv.w, qv.w, abs0 + 12u, soff, slen, nr, a);
+  return n_invalid;
+}
+
+// One window of a queued anchor hit.  `lo`/`hi` hold the 25 bases from the start of 16-byte unit `unit`
+// (2 bits per base, first base least significant); `w` is the window start in bases from the unit start.
+// A window found in the exact key set (shared-memory hash table; the 2^20-bit map in L2 if the set was
+// too big for it) whose 10 bases lie inside one read lowers that read's first-hit position.  A hit that
+// ends on the last base of its read is dropped: it can only be the first hit if there is no other, and
+// then the reference counts nothing (quack.c:215).
+__device__ __forceinline__ void confirm_window(uint32_t lo, uint32_t hi, uint32_t unit, uint32_t w, const AdapterSet ad,
+                                               uint32_t exact_s, uint32_t lo_al, uint32_t idx_s, uint32_t nr,
+                                               uint32_t uniform_len, uint32_t fhit_s) {
+  const uint32_t key = __funnelshift_r(lo, hi, 2u * w) & 0xFFFFFu;
+  bool member;
+  if (ad.exact)
+    member = lds_u32(exact_s + exact_off1(key)) == key || lds_u32(exact_s + exact_off2(key)) == key;
+  else
+    member = (ad.bitmap[key >> 5] >> (key & 31u)) & 1u;
+  if (!member) return;
+  const uint32_t abs = lo_al + unit * 16u + w + 9u;  // byte on which the window ends
+  uint32_t r, pos, len;
+  if (uniform_len) {  // reads of one length, back to back: divide instead of searching
+    const uint32_t d = abs - lds_u32(idx_s);
+    if ((int32_t)d < 0) return;
+    // d < 2^16 and (d + 0.5) / len is never closer than 1/(2 len) to an integer: the float quotient is exact
+    r = (uint32_t)(((float)d + 0.5f) * __frcp_rn((float)uniform_len));
+    pos = d - r * uniform_len;
+    len = uniform_len;
+    if (r >= nr) return;
+  } else {
+    const uint32_t *soff = shared_ptr<const uint32_t>(idx_s);
+    const int rr = find_read(soff, nr, abs);
+    if (rr < 0) return;
+    r = (uint32_t)rr;
+    pos = abs - soff[r];
+    len = soff[kIdxCap + r];
+  }
+  if (pos >= 9u && pos + 1u < len) atomicMin(shared_ptr<uint32_t>(fhit_s) + r, pos);  // whole window inside the read
 }
 
 template <bool kAdapters, uint32_t kLh>
@@ -347,44 +594,37 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
   uint32_t *hist = reinterpret_cast<uint32_t *>(smem + L.hist);
   uint32_t *lenhist = reinterpret_cast<uint32_t *>(smem + L.lenhist);
   uint32_t *kmerhist = reinterpret_cast<uint32_t *>(smem + L.kmerhist);
-  Candidate *cand = reinterpret_cast<Candidate *>(smem + L.cand);
-  const uint32_t *exact_s = reinterpret_cast<const uint32_t *>(smem + L.exact);
-  uint32_t *meta = reinterpret_cast<uint32_t *>(smem + L.meta);
-  uint32_t *cand_count = meta + 4 * kMaxStages;  // [2], alternating per tile
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L.bars);  // [2*s] full, [2*s+1] empty
+  uint32_t *fhit_all = reinterpret_cast<uint32_t *>(smem + L.fhit);  // [2][kMaxTileReads]
 
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31u;
   const uint32_t warp = tid >> 5;
+  const uint32_t smem_s = smem_u32(smem);
 
-  // ---- prologue: zero histograms, load the Bloom filter, init barriers ----
-  for (uint32_t i = tid; i < 256u * Lh; i += kThreads) hist[i] = 0;
+  // ---- prologue: zero histograms, load the adapter filter, init barriers ----
+  {
+    uint4 *h4 = reinterpret_cast<uint4 *>(hist);
+    for (uint32_t i = tid; i < 64u * Lh; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
+  }
   for (uint32_t i = tid; i < len_cap; i += kThreads) {
     lenhist[i] = 0;
-    kmerhist[i] = 0;
+    if (kAdapters) kmerhist[i] = 0;
   }
   if (kAdapters) {
-    uint32_t *bw = reinterpret_cast<uint32_t *>(smem + L.bloom);
-    for (uint32_t i = tid; i < kBloomWords * 32u; i += kThreads) bw[i] = args.ad.bloom[i];
+    uint32_t *af = reinterpret_cast<uint32_t *>(smem + L.afilt);
+    for (uint32_t i = tid; i < kAnchorWords * kAnchorCopies; i += kThreads) af[i] = args.ad.anchor[i / kAnchorCopies];
     uint32_t *ex = reinterpret_cast<uint32_t *>(smem + L.exact);
     if (args.ad.exact)
       for (uint32_t i = tid; i < kExactSlots; i += kThreads) ex[i] = args.ad.exact[i];
-  }
-  for (uint32_t s = 0; s < S; s++) {
-    uint8_t *st = smem + L.stage0 + s * L.stage_stride;
-    uint32_t *fh = reinterpret_cast<uint32_t *>(st + L.fhit_off);
-    for (uint32_t i = tid; i < kMaxTileReads; i += kThreads) fh[i] = kNoHit;
-    // pads are read (never consumed) by halo lanes: keep them defined
-    for (uint32_t i = tid; i < kPadBefore / 4; i += kThreads) {
-      reinterpret_cast<uint32_t *>(st)[i] = 0;
-      reinterpret_cast<uint32_t *>(st + L.qual_off - kPadBefore)[i] = 0;
-    }
+    for (uint32_t i = tid; i < 2u * kMaxTileReads; i += kThreads) fhit_all[i] = kNoHit;
   }
   if (tid == 0) {
-    cand_count[0] = cand_count[1] = 0;
+    uint32_t *cc = reinterpret_cast<uint32_t *>(smem + L.ccount);
+    cc[0] = cc[1] = cc[2] = cc[3] = 0;
     for (uint32_t s = 0; s < S; s++) {
-      mbar_init(&bars[2 * s], 1);
-      mbar_init(&bars[2 * s + 1], kCW);
+      uint8_t *st = smem + L.stage0 + s * L.stage_stride;
+      mbar_init(reinterpret_cast<uint64_t *>(st + L.o_full), 1);
+      mbar_init(reinterpret_cast<uint64_t *>(st + L.o_empty), kCW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -397,10 +637,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
     // =============================== producer warp ===============================
     if (lane == 0) {
       unsigned long long reads_seen = 0;
-      uint32_t it = 0;
-      for (uint32_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t s = it % S, use = it / S;
-        if (use > 0) mbar_wait(&bars[2 * s + 1], (use & 1u) ^ 1u);
+      uint32_t s = 0, ph = 1;  // a fresh "empty" barrier passes a wait on parity 1
+      for (uint32_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x) {
+        uint8_t *st = smem + L.stage0 + s * L.stage_stride;
+        uint64_t *full = reinterpret_cast<uint64_t *>(st + L.o_full);
+        mbar_wait_relaxed(smem_u32(st + L.o_empty), ph);
         const uint32_t r0 = tile * RT;
         const uint32_t r1 = min(r0 + RT, n_reads);
         uint32_t nr = r1 - r0;
@@ -413,21 +654,23 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
           span = 0;
           nr = 0;
         }
-        uint8_t *st = smem + L.stage0 + s * L.stage_stride;
-        meta[4 * s + 0] = lo_al;
-        meta[4 * s + 1] = nr;
-        meta[4 * s + 2] = span;
-        const uint32_t idx_bytes = ((nr + 3u) & ~3u) * 4u;
-        mbar_arrive_expect_tx(&bars[2 * s], 2u * span + 2u * idx_bytes);
+        const uint32_t r0_al = r0 & ~3u;  // TMA sources are 16-byte aligned
+        const uint32_t idx_bytes = nr ? ((r1 - r0_al + 3u) & ~3u) * 4u : 0u;
+        *reinterpret_cast<uint4 *>(st + L.o_meta) = make_uint4(lo_al, nr, span, r0 - r0_al);
+        mbar_arrive_expect_tx(full, 2u * span + 2u * idx_bytes);
         if (span) {
-          bulk_g2s(st + L.seq_off, args.b.seq + lo_al, span, &bars[2 * s]);
-          bulk_g2s(st + L.qual_off, args.b.qual + lo_al, span, &bars[2 * s]);
+          bulk_g2s(st, args.b.seq + lo_al, span, full);
+          bulk_g2s(st + L.o_qual, args.b.qual + lo_al, span, full);
         }
         if (idx_bytes) {
-          bulk_g2s(st + L.soff_off, args.b.offset + r0, idx_bytes, &bars[2 * s]);
-          bulk_g2s(st + L.slen_off, args.b.length + r0, idx_bytes, &bars[2 * s]);
+          bulk_g2s(st + L.o_soff, args.b.offset + r0_al, idx_bytes, full);
+          bulk_g2s(st + L.o_slen, args.b.length + r0_al, idx_bytes, full);
         }
         reads_seen += nr;
+        if (++s == S) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
       if (reads_seen) atomicAdd(&args.a.counters[kCntReads], reads_seen);
     }
@@ -435,10 +678,25 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
   }
 
   // ================================= consumer warps =================================
+  // launch constants the tile loop needs, pinned in registers; everything else is an immediate
+  const uint32_t qsub = pin(plan.qbase * 0x01010101u);
   const KeyConsts kc(plan.qbase);
-  const uint32_t qsub = kc.qsub;
-  constexpr uint32_t Lh4 = Lh * 4u;
-  uint8_t *const hist_lane = smem + L.hist + lane * 4u;  // byte address of this lane's bank column
+  const uint32_t buf = pin(L.buf);                         // stage + buf = quality / key bytes
+  const uint32_t o_meta = pin(L.o_meta);                   // soff = o_meta - 2*kIdxCap*4, slen = o_meta - kIdxCap*4
+  const uint32_t stride = pin(L.stage_stride);
+  const uint32_t stage0_s = pin(smem_s + L.stage0);
+  const uint32_t stage_end_s = pin(smem_s + L.stage0 + S * L.stage_stride);
+  const uint32_t hist_s = smem_s + L.hist;
+  HLane<Lh> hl;  // this lane's histogram columns for the word steps
+  hl.init(hist_s, lane);
+  const uint32_t tid16 = tid * 16u;
+  const uint32_t afilt_lane_s = smem_s + L.afilt + (lane >> 2) * 4u;  // this lane's copy of the anchor map
+  const uint32_t exact_s = smem_s + L.exact;
+  const uint32_t ccount_s = smem_s + L.ccount;
+  const uint32_t cand_s = smem_s + L.cand;
+  const uint32_t fhit_s0 = smem_s + L.fhit;
+  const uint32_t lenhist_s = smem_s + L.lenhist;
+  const uint32_t kmerhist_s = smem_s + L.kmerhist;
   unsigned long long n_invalid = 0;
   uint32_t reads_since_flush = 0;
 
@@ -446,9 +704,9 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
     // all consumer warps have passed the barrier that ends phase H
     const uint32_t npos = min(2u * Lh, len_cap);
     for (uint32_t pos = tid; pos < npos; pos += kCThreads) {
-      const bool hi = pos >= Lh;
-      const uint32_t col = hi ? pos - Lh : pos;
-      const uint32_t sh = hi ? 16u : 0u;
+      uint32_t unit;
+      const uint32_t col = HLayout<Lh>::column(pos, unit);
+      const uint32_t sh = unit == 1u ? 0u : 16u;
       unsigned long long *row = args.a.rows + (size_t)pos * kRow;
       uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
       for (uint32_t sp = 0; sp < 63; sp++) {  // s = 63 rows are the dummies
@@ -470,11 +728,14 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
       if (c1) atomicAdd(&row[kColContent + 1], (unsigned long long)c1);
       if (c2) atomicAdd(&row[kColContent + 2], (unsigned long long)c2);
       if (c3) atomicAdd(&row[kColContent + 3], (unsigned long long)c3);
-      const uint32_t lc = lenhist[pos], kcnt = kmerhist[pos];
+      const uint32_t lc = lenhist[pos];
       if (lc) atomicAdd(&row[kColLength], (unsigned long long)lc);
-      if (kcnt) atomicAdd(&row[kColKmer], (unsigned long long)kcnt);
       lenhist[pos] = 0;
-      kmerhist[pos] = 0;
+      if (kAdapters) {
+        const uint32_t kcnt = kmerhist[pos];
+        if (kcnt) atomicAdd(&row[kColKmer], (unsigned long long)kcnt);
+        kmerhist[pos] = 0;
+      }
     }
     consumer_bar();
     uint4 *h4 = reinterpret_cast<uint4 *>(hist);
@@ -482,169 +743,231 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
     consumer_bar();
   };
 
-  uint32_t it = 0;
+  // first-hit positions of the previous tile -> adapter histogram (quack.c:215-217), one thread per read
+  auto settle_hits = [&](uint32_t buf_index, uint32_t nr_prev) {
+    if (tid < nr_prev) {  // a tile holds at most kMaxTileReads <= kCThreads reads
+      const uint32_t a = fhit_s0 + (buf_index * kMaxTileReads + tid) * 4u;
+      const uint32_t p = lds_u32(a);
+      if (p != kNoHit) {
+        red_shared_add<4>(kmerhist_s + p * 4u, 1u);  // bin p + 1
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(kNoHit) : "memory");
+      }
+    }
+  };
+
+  uint32_t st = stage0_s;  // shared-space address of the current stage block
+  uint32_t ph = 0, it = 0, nr_prev = 0;
+  uint32_t cslot = 0;  // it % 3
   for (uint32_t tile = blockIdx.x; tile < args.n_tiles; tile += gridDim.x, ++it) {
-    const uint32_t s = it % S, use = it / S;
-    mbar_wait(&bars[2 * s], use & 1u);
-    const uint32_t lo_al = meta[4 * s + 0];
-    const uint32_t nr = meta[4 * s + 1];
-    const uint32_t span = meta[4 * s + 2];
-    uint8_t *st = smem + L.stage0 + s * L.stage_stride;
-    const uint32_t *soff = reinterpret_cast<const uint32_t *>(st + L.soff_off);
-    const uint32_t *slen = reinterpret_cast<const uint32_t *>(st + L.slen_off);
-    uint32_t *fhit = reinterpret_cast<uint32_t *>(st + L.fhit_off);
-    uint8_t *kbuf = st + L.qual_off;  // phase A overwrites the quality bytes with the key bytes K
-    uint32_t *ccount = &cand_count[it & 1u];
+    mbar_wait(st + o_meta + 16u, ph);
+    const uint4 mt = lds_u128(st + o_meta);
+    const uint32_t lo_al = mt.x, nr = mt.y, span = mt.z;
+    const uint32_t idx_s = st + o_meta - 2u * kIdxCap * 4u + mt.w * 4u;  // soff[]; slen[] is kIdxCap entries behind
+    const uint32_t kbuf_s = st + buf;  // phase A overwrites the quality bytes with the key bytes K
+
+    // is the tile uniform (all reads of one length, back to back)?  one compare per read, ANDed by the barrier
+    uint32_t len0 = 0, soff0 = 0;
+    if (nr) {
+      soff0 = lds_u32(idx_s);
+      len0 = lds_u32(idx_s + kIdxCap * 4u);
+    }
+    uint32_t my_ok = 1u;
+    if (tid < nr) {
+      const uint32_t o = lds_u32(idx_s + tid * 4u), l = lds_u32(idx_s + (kIdxCap + tid) * 4u);
+      my_ok = (l == len0 && o == soff0 + tid * len0) ? 1u : 0u;
+    }
 
     // ---------------- phase A: flat over the tile, K written in place of the quality bytes ----------------
     if (!kAdapters) {
-      const uint4 *s4 = reinterpret_cast<const uint4 *>(st + L.seq_off);
-      uint4 *q4 = reinterpret_cast<uint4 *>(st + L.qual_off);
-      const uint32_t nvec = span >> 4;
-      for (uint32_t v = tid; v < nvec; v += kCThreads) {
-        const uint4 sv = s4[v], qv = q4[v];
+      for (uint32_t v16 = tid16; v16 < span; v16 += kCThreads * 16u) {
+        const uint32_t a = st + v16;
+        const uint4 sv = lds_u128(a), qv = lds_u128(a + buf);
         uint32_t n0, n1, n2, n3, bad = 0;
         uint4 K;
         K.x = key_bytes(sv.x, qv.x, kc, n0, bad);
         K.y = key_bytes(sv.y, qv.y, kc, n1, bad);
         K.z = key_bytes(sv.z, qv.z, kc, n2, bad);
         K.w = key_bytes(sv.w, qv.w, kc, n3, bad);
-        if (bad & 0xC0C0C0C0u) {  // rare: re-key the offending words to the dummy rows, count them exactly
-          const uint32_t abs0 = lo_al + v * 16u;
-          if (word_bad(qv.x, qsub)) K.x = key_bytes_bad(n0), n_invalid += exact_word(sv.x, qv.x, abs0, soff, slen, nr, args.a);
-          if (word_bad(qv.y, qsub)) K.y = key_bytes_bad(n1), n_invalid += exact_word(sv.y, qv.y, abs0 + 4u, soff, slen, nr, args.a);
-          if (word_bad(qv.z, qsub)) K.z = key_bytes_bad(n2), n_invalid += exact_word(sv.z, qv.z, abs0 + 8u, soff, slen, nr, args.a);
-          if (word_bad(qv.w, qsub)) K.w = key_bytes_bad(n3), n_invalid += exact_word(sv.w, qv.w, abs0 + 12u, soff, slen, nr, args.a);
-        }
-        q4[v] = K;
+        if (bad & 0xC0C0C0C0u)  // rare: re-key the offending words to the dummy rows, count them exactly
+          n_invalid += fix_bad_unit(sv, qv, K, n0, n1, n2, n3, qsub, lo_al + v16, idx_s, nr, args.a);
+        sts_u128(a + buf, K);
       }
     } else {
-      // One 8-byte unit (8 bases) per lane.  A warp step covers 30 new units; lanes 0 and 1 re-read the
-      // two units in front so that every 10-mer window ending in lanes 2..31 finds its 9 earlier bases
-      // inside the warp (two shuffles).  Halo lanes compute but never store or report.
-      const uint2 *s8 = reinterpret_cast<const uint2 *>(st + L.seq_off);
-      uint2 *q8 = reinterpret_cast<uint2 *>(st + L.qual_off);
-      const uint8_t *bloom_b = smem + L.bloom;
-      const uint32_t lane4 = lane * 4u;
-      const int n8 = (int)(span >> 3);
-      const uint32_t nsteps = ((uint32_t)n8 + 29u) / 30u;
-      const uint32_t M = args.ad.bloom_mul;
-      for (uint32_t step = warp; step < nsteps; step += kCW) {
-        const int u = (int)(step * 30u + lane) - 2;  // -2, -1 land in the pad in front; > n8 in the pad behind
-        const uint2 sv = s8[u], qv = q8[u];
-        uint32_t n0, n1, bad = 0;
-        uint2 K;
+      // One 16-byte unit per lane.  A warp step covers 31 new units; lane 31 re-reads the unit behind them
+      // so that the 7-mer anchors starting at bases 3, 7, 11, 15 of lanes 0..30 find their bases (one
+      // shuffle).  The look-ahead lane computes but never stores or reports.
+      const uint32_t ccnt_s = ccount_s + cslot * 4u;
+      const uint32_t cq_s = cand_s + (it & 1u) * (kCandCap * 8u);
+      const uint32_t n16 = span >> 4;
+      for (uint32_t u0 = warp * 31u; u0 < n16; u0 += kCW * 31u) {
+        const uint32_t u = u0 + lane;
+        const uint32_t a = st + min(u, n16) * 16u;  // at most the 16 bytes behind the span are read
+        const uint4 sv = lds_u128(a), qv = lds_u128(a + buf);
+        uint32_t n0, n1, n2, n3, bad = 0;
+        uint4 K;
         K.x = key_bytes(sv.x, qv.x, kc, n0, bad);
         K.y = key_bytes(sv.y, qv.y, kc, n1, bad);
-        const bool own = lane >= 2u && u < n8;
+        K.z = key_bytes(sv.z, qv.z, kc, n2, bad);
+        K.w = key_bytes(sv.w, qv.w, kc, n3, bad);
+        const bool own = lane < 31u && u < n16;
         if (own) {
-          if (bad & 0xC0C0C0C0u) {
-            const uint32_t abs0 = lo_al + (uint32_t)u * 8u;
-            if (word_bad(qv.x, qsub)) K.x = key_bytes_bad(n0), n_invalid += exact_word(sv.x, qv.x, abs0, soff, slen, nr, args.a);
-            if (word_bad(qv.y, qsub)) K.y = key_bytes_bad(n1), n_invalid += exact_word(sv.y, qv.y, abs0 + 4u, soff, slen, nr, args.a);
-          }
-          q8[u] = K;
+          if (bad & 0xC0C0C0C0u)
+            n_invalid += fix_bad_unit(sv, qv, K, n0, n1, n2, n3, qsub, lo_al + u * 16u, idx_s, nr, args.a);
+          sts_u128(a + buf, K);
         }
-        // 8 bases -> 16 bits, first base least significant (codes are the inverted bits 7:6 of n0/n1)
-        const uint32_t c0 = ~n0 & 0xC0C0C0C0u, c1 = ~n1 & 0xC0C0C0C0u;
-        const uint32_t p16 = ((c0 * 0x41041u) >> 24) | (((c1 * 0x41041u) >> 16) & 0xFF00u);
-        const uint32_t prev = __shfl_up_sync(0xffffffffu, p16, 1);
-        const uint32_t pp = __shfl_up_sync(0xffffffffu, p16, 2);
-        const uint32_t lo = (pp & 0xFFFFu) | (prev << 16);  // 16 earlier bases
-        const uint32_t hi = p16;                             // my 8 bases
-        uint32_t acc = 0;
-#pragma unroll
-        for (int t = 0; t < 8; t++) {
-          const uint32_t wj = __funnelshift_r(lo, hi, 14 + 2 * t);  // low 20 bits: window ending at my base t
-          const uint32_t p = wj * M;                                // low 20 bits depend on the window only
-          const uint32_t word = *reinterpret_cast<const uint32_t *>(bloom_b + ((p & 0x7F80u) | lane4));
-          acc |= __funnelshift_r(word, 0u, wj) & __funnelshift_r(word, 0u, p >> 15);
-        }
-        if (own && (acc & 1u)) {
-          const Candidate c{u, lo, hi};
-          const uint32_t idx = atomicAdd(ccount, 1u);
-          if (idx < kCandCap)
-            cand[idx] = c;
-          else
-            confirm_candidate(c, args.ad, bloom_b + lane4, exact_s, lo_al, soff, slen, nr, fhit);
-        }
-      }
-    }
-    consumer_bar();
-
-    // ---------------- phase A2: confirm queued Bloom positives, spread over all threads ----------------
-    if (kAdapters) {
-      const uint32_t nc = min(*ccount, kCandCap);
-      for (uint32_t i = tid; i < nc * 8u; i += kCThreads)  // one (unit, window) pair per thread: all warps share it
-        confirm_window(cand[i >> 3], (int)(i & 7u), args.ad, smem + L.bloom + lane * 4u, exact_s, lo_al, soff, slen,
-                       nr, fhit);
-    }
-
-    // ---------------- phase H: one warp per read, lane <-> position, one shared atomic per base ----------------
-    // Every 32-position step is straight-line code: which half-word it counts in and its column
-    // offset are compile-time constants (kLh template); only the lane predicate pos < len is dynamic.
-    // Explicit shared-space PTX keeps a step at ISETP + LDS.U8 + IMAD + ATOMS.
-#define QB_STEP(sidx)                                                                               \
-  if (rem > (sidx) * 32u) {                                                                         \
-    constexpr uint32_t pos0 = (sidx) * 32u;                                                         \
-    constexpr bool hi_half = pos0 >= Lh;                                                            \
-    const uint32_t k = lds_u8(kb_s + pos0);                                                         \
-    red_shared_add(k * Lh4 + hist_s + (hi_half ? pos0 - Lh : pos0) * 4u, hi_half ? 0x10000u : 1u);  \
-  }
-    {
-      const uint32_t kbuf_s = smem_u32(kbuf) + lane - lo_al;
-      const uint32_t hist_s = smem_u32(hist_lane);
-      for (uint32_t r = warp; r < nr; r += kCW) {
-        const uint32_t len = slen[r];
-        if (len > len_cap) continue;  // reported in the bookkeeping pass below
-        const uint32_t kb_s = kbuf_s + soff[r];
-        const uint32_t rem = len > lane ? len - lane : 0u;  // lane handles positions lane, lane+32, ... < len
-        QB_STEP(0) QB_STEP(1) QB_STEP(2)
-        if (len > 96u) {
-          QB_STEP(3) QB_STEP(4)
-          if constexpr (Lh == 96u) {
-            QB_STEP(5)
-          } else if (len > 160u) {
-            QB_STEP(5) QB_STEP(6) QB_STEP(7)
-            if (len > 256u) { QB_STEP(8) QB_STEP(9) }
+        // 16 bases -> 32 bits.  The codes come from the base bytes alone (~n): the look-ahead lane may
+        // read quality bytes another warp is already replacing with its keys.
+        const uint32_t p = pack16(~n0, ~n1, ~n2, ~n3);
+        const uint32_t nx = __shfl_down_sync(0xffffffffu, p, 1);
+        // anchor j = the 7-mer starting at base 4j+3: row = its bits 13:5 (32-byte rows), bit = its bits 4:0
+        const uint32_t e0 = __funnelshift_r(p, nx, 6), e1 = __funnelshift_r(p, nx, 14);
+        const uint32_t e2 = __funnelshift_r(p, nx, 22), e3 = __funnelshift_r(p, nx, 30);
+        const uint32_t w0 = lds_u32(afilt_lane_s + (e0 & 0x3FE0u)), w1 = lds_u32(afilt_lane_s + (e1 & 0x3FE0u));
+        const uint32_t w2 = lds_u32(afilt_lane_s + (e2 & 0x3FE0u)), w3 = lds_u32(afilt_lane_s + (e3 & 0x3FE0u));
+        const uint32_t m0 = __funnelshift_r(w0, 0u, e0), m1 = __funnelshift_r(w1, 0u, e1);
+        const uint32_t m2 = __funnelshift_r(w2, 0u, e2), m3 = __funnelshift_r(w3, 0u, e3);
+        const bool hit = own && ((m0 | m1 | m2 | m3) & 1u);
+        if (__ballot_sync(0xffffffffu, hit)) {
+          if (hit) {  // one queue entry per anchor that passed: 25 bases, anchor index, unit
+            uint32_t mask = (m0 & 1u) | ((m1 & 1u) << 1) | ((m2 & 1u) << 2) | ((m3 & 1u) << 3);
+            uint32_t idx = atomicAdd(shared_ptr<uint32_t>(ccnt_s), (uint32_t)__popc(mask));
+            const uint32_t hi18 = (nx & 0x3FFFFu) | (u << 20);  // 18 bits of bases, 2 of anchor index, 12 of unit
+            while (mask) {
+              const uint32_t j = __ffs(mask) - 1u;
+              mask &= mask - 1u;
+              if (idx < kCandCap) sts_u64(cq_s + idx * 8u, p, hi18 | (j << 18));  // beyond the cap: tile re-scanned below
+              idx++;
+            }
           }
         }
       }
     }
-#undef QB_STEP
-    consumer_bar();  // K bytes, candidates and fhit of this tile are final / no longer needed
+    const uint32_t uniform = consumer_bar_and(my_ok);  // K bytes and the candidate queue of this tile are complete
 
-    // ---------------- bookkeeping: per-read counters, one thread per read ----------------
-    for (uint32_t r = tid; r < nr; r += kCThreads) {
-      const uint32_t len = slen[r];
-      if (len > len_cap) {
+    // ---------------- per-read counters, one thread per read (quack.c:219) ----------------
+    if (tid < nr) {
+      const uint32_t len = lds_u32(idx_s + (kIdxCap + tid) * 4u);
+      if (len > len_cap)
         atomicAdd(&args.a.counters[kCntError], 1ull);
-        continue;
-      }
-      if (len) atomicAdd(&lenhist[len - 1u], 1u);  // quack.c:219
-      if (kAdapters) {
-        const uint32_t fh = fhit[r];
-        if (fh != kNoHit) {
-          if (fh + 1u < len) atomicAdd(&kmerhist[fh + 1u], 1u);  // quack.c:215-217
-          fhit[r] = kNoHit;
+      else if (len)
+        red_shared_add<0>(lenhist_s + (len - 1u) * 4u, 1u);
+    }
+    if (kAdapters) {
+      if (it) settle_hits((it & 1u) ^ 1u, nr_prev);  // every warp finished the previous tile's confirmations
+      if (tid == 0)  // counter of tile it+2: idle since tile it-1
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ccount_s + (cslot == 0 ? 2u : cslot - 1u) * 4u), "r"(0u) : "memory");
+      // ---------------- phase A2: confirm queued anchor hits, one (hit, window offset) pair per thread ----------------
+      const uint32_t total = lds_u32(ccount_s + cslot * 4u);
+      const uint32_t fhit_s = fhit_s0 + (it & 1u) * (kMaxTileReads * 4u);
+      const uint32_t ulen = uniform ? len0 : 0u;
+      if (total <= kCandCap) {
+        const uint32_t cq_s = cand_s + (it & 1u) * (kCandCap * 8u);
+        for (uint32_t i = tid; i < total * 4u; i += kCThreads) {
+          const uint2 c = lds_u64(cq_s + (i >> 2) * 8u);
+          // anchor j starts at base 4j+3 of its unit; the windows that contain it start at bases 4j .. 4j+3
+          confirm_window(c.x, c.y & 0x3FFFFu, c.y >> 20, ((c.y >> 16) & 12u) + (i & 3u), args.ad, exact_s, lo_al, idx_s,
+                         nr, ulen, fhit_s);
+        }
+      } else {  // queue overflow (adapter-dimer-like data): test every window of the tile exactly
+        const uint32_t n16 = span >> 4;
+        for (uint32_t i = tid; i < n16 * 4u; i += kCThreads) {
+          const uint32_t unit = i >> 2, t = i & 3u;
+          const uint4 ka = lds_u128(kbuf_s + unit * 16u), kb = lds_u128(kbuf_s + unit * 16u + 16u);
+          const uint32_t lo = pack16(ka.x, ka.y, ka.z, ka.w), hi = pack16(kb.x, kb.y, kb.z, kb.w);
+          for (uint32_t j = 0; j < 4u; j++)
+            confirm_window(lo, hi, unit, 4u * j + t, args.ad, exact_s, lo_al, idx_s, nr, ulen, fhit_s);
         }
       }
     }
-    if (kAdapters && tid == 0) *ccount = 0;
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bars[2 * s + 1]);  // stage buffers free for the producer
 
+    // ---------------- phase H: one warp per read, one shared atomic per base ----------------
+    {
+      const uint32_t k0_s = kbuf_s - lo_al;  // + absolute offset of a read = shared address of its first key byte
+#define QB_SHAPES(FN)                                                                      \
+  FN(0, 1) FN(0, 2) FN(1, 0) FN(1, 1) FN(1, 2) FN(2, 0) FN(2, 1) FN(2, 2) FN(3, 0)
+      if (uniform) {
+        if (len0 && len0 <= len_cap) {
+          switch (h_shape(len0)) {
+#define QB_CASE(nwf, kind)                                                                  \
+  case (nwf)*3 + (kind):                                                                    \
+    if constexpr (128u * (nwf) + ((kind) ? 1u : 0u) <= 2u * Lh)                              \
+      h_uniform<Lh, nwf, kind>(hl, hist_s, k0_s + soff0, len0, nr, warp, lane);              \
+    break;
+            QB_SHAPES(QB_CASE)
+#undef QB_CASE
+          }
+        }
+      } else {
+        for (uint32_t r = warp; r < nr; r += kCW) {
+          const uint32_t len = lds_u32(idx_s + (kIdxCap + r) * 4u);
+          if (len == 0 || len > len_cap) continue;  // reported in the bookkeeping pass above
+          const uint32_t kb = k0_s + lds_u32(idx_s + r * 4u);
+          switch (h_shape(len)) {
+#define QB_CASE(nwf, kind)                                                                  \
+  case (nwf)*3 + (kind):                                                                    \
+    if constexpr (128u * (nwf) + ((kind) ? 1u : 0u) <= 2u * Lh) h_one<Lh, nwf, kind>(hl, hist_s, kb, len, lane); \
+    break;
+            QB_SHAPES(QB_CASE)
+#undef QB_CASE
+          }
+        }
+      }
+#undef QB_SHAPES
+    }
+    // The stage goes back to the producer.  Its next TMA write must be ordered behind the (generic-proxy)
+    // writes of key bytes into the buffer: those all happened before the barrier above, so one proxy
+    // fence by the arriving lane covers them.
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(st + o_meta + 24u);
+    }
+
+    nr_prev = nr;
     reads_since_flush += nr;
     if (reads_since_flush + RT > 65535u) {  // u16 counters: flush before any bin can wrap
       consumer_bar();
       flush();
       reads_since_flush = 0;
     }
+    st += stride;
+    if (st == stage_end_s) {
+      st = stage0_s;
+      ph ^= 1u;
+    }
+    if (++cslot == 3u) cslot = 0;
   }
   consumer_bar();
+  if (kAdapters && it) {
+    settle_hits((it & 1u) ^ 1u, nr_prev);
+    consumer_bar();
+  }
   flush();
   n_invalid = warp_sum(n_invalid);
   if (lane == 0 && n_invalid) atomicAdd(&args.a.counters[kCntInvalidQual], n_invalid);
+}
+
+// tile geometry: one phase-A round per tile (every consumer thread takes one 16-byte unit), reads shared
+// evenly by the consumer warps in phase H, and as many stages as shared memory allows (the loads of a
+// tile need about two tile times to land)
+static uint32_t choose_reads_per_tile(uint32_t bytes, uint32_t max_len) {
+  if (bytes < max_len + 32u) return 0;
+  uint32_t rt_max = (bytes - 32u) / max_len;
+  if (rt_max > kMaxTileReads) rt_max = kMaxTileReads;
+  // warp instructions per tile and warp: ~130 for phase A and the tile bookkeeping, 4 + 3.6 per 32-base
+  // step for every read the warp takes in phase H
+  const double per_read = 4.0 + 3.6 * (double)((max_len + 31u) / 32u);
+  uint32_t best = rt_max;
+  double best_score = 0;
+  for (uint32_t rt = rt_max; rt >= 1u && rt + (uint32_t)kCW > rt_max; rt--) {
+    const double rounds = (double)((rt + (uint32_t)kCW - 1u) / (uint32_t)kCW);
+    const double score = (double)rt / (130.0 + rounds * per_read);
+    if (score > best_score * 1.01) {
+      best_score = score;
+      best = rt;
+    }
+  }
+  return best;
 }
 
 FusedPlan fused_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int sm_count,
@@ -657,25 +980,45 @@ FusedPlan fused_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int
   p.half_len = half;
   p.qbase = qbase;
   if (batch_max_len == 0 || batch_max_len > len_cap) batch_max_len = len_cap;
-  for (uint32_t stages = kMaxStages; stages >= 2; stages--) {
-    const SmemLayout L0 = smem_layout(half, len_cap, 0, stages, adapters);
-    if (L0.total + 128u >= smem_optin) continue;
-    uint32_t avail = smem_optin - L0.total - 128u;  // L0 already holds every pad
-    uint32_t tile = (avail / (2u * stages)) & ~15u;
-    if (tile > 32768u) tile = 32768u;
-    if (tile < 64u) continue;
-    uint32_t rt = ((tile - 32u) / batch_max_len) & ~3u;
-    if (rt > kMaxTileReads) rt = kMaxTileReads;
-    if (rt < 4u) continue;
-    if (stages == kMaxStages && rt < 32u) continue;  // prefer fewer, larger stages for long reads
-    p.stages = stages;
-    p.tile_bytes = tile;
-    p.reads_per_tile = rt;
-    p.smem_bytes = smem_layout(half, len_cap, tile, stages, adapters).total;
-    p.grid = (uint32_t)sm_count;
-    p.ok = 1;
-    return p;
+  // bytes all consumer threads cover in one phase-A pass (with -a each warp spends a lane on look-ahead);
+  // a tile holds as many passes as come closest to 32 KB (the per-tile costs -- barrier, waits, set-up --
+  // are what is left to amortise), in as many stages as then fit (two are enough at this size)
+  const uint32_t pass_bytes = adapters ? (uint32_t)kCW * 31u * 16u : (uint32_t)kCThreads * 16u;
+  uint32_t passes = (32768u + pass_bytes / 2u) / pass_bytes ? (32768u + pass_bytes / 2u) / pass_bytes : 1u;
+  uint32_t max_stages = kMaxStages;
+  if (const char *e = getenv("QB_TILE_PASSES")) {  // tuning hooks (tools/sweep_tiles.py)
+    const int v = atoi(e);
+    if (v >= 1 && v <= 16) passes = (uint32_t)v;
   }
+  if (const char *e = getenv("QB_STAGES")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= (int)kMaxStages) max_stages = (uint32_t)v;
+  }
+  const uint32_t round_bytes = passes * pass_bytes;
+  auto tile_avail = [&](uint32_t stages) -> uint32_t {
+    const SmemLayout L0 = smem_layout(half, len_cap, 0, stages, adapters);
+    if (L0.total + 128u >= smem_optin) return 0;
+    return ((smem_optin - L0.total - 128u) / (2u * stages)) & ~15u;  // L0 already holds every pad
+  };
+  uint32_t rt = choose_reads_per_tile(round_bytes, batch_max_len);
+  uint32_t stages = 0;
+  for (uint32_t st = max_stages; st >= 2 && rt; st--)
+    if (tile_avail(st) >= align16(rt * batch_max_len + 32u)) {
+      stages = st;
+      break;
+    }
+  if (!stages) {  // long reads: whatever two stages hold
+    stages = 2;
+    rt = choose_reads_per_tile(tile_avail(2), batch_max_len);
+    if (!rt) return p;
+  }
+  if (align16(rt * batch_max_len + 32u) > 65536u) return p;  // queue entries address 4096 16-byte units
+  p.stages = stages;
+  p.tile_bytes = align16(rt * batch_max_len + 32u);
+  p.reads_per_tile = rt;
+  p.smem_bytes = smem_layout(half, len_cap, p.tile_bytes, stages, adapters).total;
+  p.grid = (uint32_t)sm_count;
+  p.ok = 1;
   return p;
 }
 

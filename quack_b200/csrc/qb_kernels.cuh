@@ -23,25 +23,27 @@ constexpr int kNumCounters = 4;
 // Internal key order: first base of the window LEAST significant (2 bits per base, codes
 // A0 T1 C2 G3).  The public API takes the reference order (first base most significant);
 // qb_api.cu converts.
-constexpr uint32_t kBloomWords = 256;          // words per bank copy (power of two)
-constexpr uint32_t kBloomBytes = kBloomWords * 32 * 4;  // 32 KiB, one copy per shared-memory bank
+constexpr uint32_t kAnchorBases = 7;                       // anchor = 7-mer, one probed per 4 bases
+constexpr uint32_t kAnchorSpace = 1u << (2 * kAnchorBases);  // 2^14 anchors
+constexpr uint32_t kAnchorWords = kAnchorSpace / 32;       // 512 words: exact bitmap
+constexpr uint32_t kAnchorCopies = 8;                      // copies in shared memory (row = 8 words = 32 B)
+constexpr uint32_t kAnchorSmemBytes = kAnchorWords * kAnchorCopies * 4;  // 16 KiB
 
-constexpr uint32_t kExactSlots = 2048;         // open-addressing table of the exact key set (8 KiB)
+// exact key set in shared memory: a cuckoo table of two halves, so membership is two loads, no loop
+constexpr uint32_t kExactSlots = 2048;         // 2 x 1024 slots (8 KiB)
+constexpr uint32_t kExactHalf = kExactSlots / 2;
 constexpr uint32_t kExactEmpty = 0xFFFFFFFFu;
-constexpr uint32_t kExactMul = 0x9E3779B1u;
-__host__ __device__ inline uint32_t exact_slot(uint32_t key) { return (key * kExactMul) >> 21; }  // 11 bits
+constexpr uint32_t kExactMul1 = 0x9E3779B1u, kExactMul2 = 0x85EBCA6Bu;
+// byte offsets of the two candidate slots of a key
+__host__ __device__ inline uint32_t exact_off1(uint32_t key) { return ((key * kExactMul1) >> 20) & 0xFFCu; }
+__host__ __device__ inline uint32_t exact_off2(uint32_t key) { return (((key * kExactMul2) >> 20) & 0xFFCu) + kExactHalf * 4u; }
 
 struct AdapterSet {
   const uint32_t *bitmap;  // exact membership, 2^20 bits, device global (stays in L2)
-  const uint32_t *bloom;   // [kBloomWords][32] blocked Bloom filter, bank-replicated, device global
-  const uint32_t *exact;   // [kExactSlots] linear-probing table of the keys, or nullptr if they do not fit
-  uint32_t bloom_mul;      // odd multiplier M: p = key * M
+  const uint32_t *anchor;  // [kAnchorWords] exact bitmap of the 7-mer anchors, device global
+  const uint32_t *exact;   // [kExactSlots] cuckoo table of the keys, or nullptr if they do not fit
   int enabled;             // 0: no -a (kmer_count handled at finish)
 };
-
-__host__ __device__ inline uint32_t bloom_word_index(uint32_t p) { return (p >> 7) & (kBloomWords - 1); }
-__host__ __device__ inline uint32_t bloom_bit1(uint32_t key) { return key & 31u; }
-__host__ __device__ inline uint32_t bloom_bit2(uint32_t p) { return (p >> 15) & 31u; }
 
 // ---- one batch in device memory ---------------------------------------------------------
 struct BatchView {
@@ -66,14 +68,17 @@ struct FusedPlan {
   uint32_t tile_bytes;      // capacity of one stage buffer (seq or qual), multiple of 16
   uint32_t reads_per_tile;  // multiple of 4, <= kMaxTileReads
   uint32_t stages;
-  uint32_t qbase;           // score field s' = q - qbase, s' in [1,63] counted in shared memory
+  uint32_t qbase;           // score field s = q - qbase, s in [0,62] counted in shared memory
   uint32_t smem_bytes;
   uint32_t grid;
   int ok;                   // 0: len_cap does not fit -> use the simple kernel
 };
 
-constexpr uint32_t kMaxTileReads = 256;
-constexpr int kFusedConsumerWarps = 31;  // + 1 producer warp = 1024 threads, 1 CTA per SM
+constexpr uint32_t kMaxTileReads = 248;   // reads per tile (8 per consumer warp at 31 warps)
+#ifndef QB_CW
+#define QB_CW 15
+#endif
+constexpr int kFusedConsumerWarps = QB_CW;  // + 1 producer warp = 512 threads (up to 128 registers each), 1 CTA per SM
 
 FusedPlan fused_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int sm_count,
                      uint32_t smem_optin, uint32_t qbase);

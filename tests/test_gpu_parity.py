@@ -251,3 +251,23 @@ def test_max_len_promise_is_enforced(keys):
         with pytest.raises(capi.QbError):
             ctx.finish(0)
         b.free()
+
+
+def test_adapter_dimers_overflow_the_hit_queue(table, keys):
+    """Reads made of adapter sequence end to end: every anchor passes the filter, the per-tile queue of
+    anchor hits overflows and the kernel falls back to testing every window of the tile exactly."""
+    ads = [r for r in util.adapter_records() if len(r) >= 30]
+    rng = np.random.default_rng(7)
+    reads = []
+    for i in range(6000):
+        s = b"".join(ads[int(k)] for k in rng.integers(0, len(ads), size=6))
+        l = 150 if i % 3 else int(rng.integers(40, 151))
+        reads.append((s[:l], bytes(rng.integers(35, 74, size=l).astype(np.uint8))))
+    batch = util.pack(reads)
+    want = po.accumulate_batch(*batch, table)
+    assert want.rows[:, 96].sum() > 5000
+    for kernel in KERNELS:
+        util.assert_same(run_gpu(batch, 150, keys, kernel), want, KNAME[kernel])
+    uniform = util.pack([(s[:150].ljust(150, b"A"), q[:150].ljust(150, b"I")) for s, q in reads])
+    util.assert_same(run_gpu(uniform, 150, keys, capi.KERNEL_FUSED, resident=True),
+                     po.accumulate_batch(*uniform, table), "uniform dimers")
