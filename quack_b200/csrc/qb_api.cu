@@ -100,7 +100,7 @@ struct qb_ctx {
   qb::AdapterSet ad_host_template{};
   uint32_t n_anchors = 0;     // distinct 7-mer anchors of the adapter set
   double anchor_density = 0;  // n_anchors / 2^14: filter pass rate per probe on random bases
-  uint32_t qbase = 33;  // score bin s = q - qbase, s in [0,62] counted in shared memory
+  uint32_t qbase = 33;  // score bin s = q - qbase, s in [0,46] counted in shared memory
   ncclComm_t rank_comm = nullptr;  // multi-process communicator
   int n_ranks = 1, rank = 0;
   unsigned long long *h_result = nullptr;  // pinned staging for qb_finish

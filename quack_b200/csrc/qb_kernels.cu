@@ -175,7 +175,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar_s, uint32_t parit
         : "r"(bar_s), "r"(parity), "r"(2000u)
         : "memory");
     if (done) break;
-    __nanosleep(100);
+    __nanosleep(400);
   }
 }
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
@@ -188,6 +188,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32_at(uint32_t off, uint32_t base) {  // [base + off], base uniform
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + off));
   return v;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
@@ -226,6 +231,13 @@ struct FusedArgs {
   uint32_t n_tiles;
 };
 
+// Histogram rows: key byte K = s << 2 | code, s = q - qbase.  Scores s in [0, kScoreBins) count in shared
+// memory (Phred 0..46 with the default qbase 33: every Illumina/ONT/PacBio scale in use); row s =
+// kScoreBins is the dummy that re-keyed words land in; anything above takes the exact global path.  Putting
+// the score in the high bits keeps the unused scores at the END of the row space, so they cost no memory.
+constexpr uint32_t kScoreBins = 47;
+constexpr uint32_t kHistRows = (kScoreBins + 1u) * 4u;  // 192 rows of Lh packed u16 pairs
+
 // shared-memory carve-up, all offsets multiples of 16 bytes.  Everything a tile needs (bytes, index
 // slices, its description and its two mbarriers) sits in one stage block at fixed offsets, so the tile
 // loop carries a single stage address.
@@ -244,7 +256,7 @@ __host__ __device__ inline SmemLayout smem_layout(uint32_t half_len, uint32_t le
   L.buf = tile_bytes + kPadAfter;
   uint32_t o = 0;
   L.hist = o;
-  o += 256u * half_len * 4u;
+  o += kHistRows * half_len * 4u;
   L.afilt = o;
   o += adapters ? kAnchorSmemBytes : 0u;
   L.exact = o;
@@ -283,18 +295,18 @@ __device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
 
 // loop-invariant SWAR constants
 struct KeyConsts {
-  uint32_t m5b, x43, m1f, x07, x14, a7f, a3f, m80, mc0, one, qsub;
+  uint32_t m5b, x43, m1f, x07, x14, a7f, a3f, m80, m03, x11, qsub;
   __device__ __forceinline__ explicit KeyConsts(uint32_t qbase)
       : m5b(0x5B5B5B5Bu), x43(0x43434343u), m1f(0x1F1F1F1Fu), x07(0x07070707u), x14(0x14141414u),
-        a7f(0x7F7F7F7Fu), a3f(0x3F3F3F3Fu), m80(0x80808080u), mc0(0xC0C0C0C0u), one(0x01010101u),
-        qsub(qbase * 0x01010101u) {}
+        a7f(0x7F7F7F7Fu), a3f(0x3F3F3F3Fu), m80(0x80808080u), m03(0x03030303u),
+        x11((64u - kScoreBins) * 0x01010101u), qsub(qbase * 0x01010101u) {}
 };
 
 // Phase A arithmetic for one aligned word of 4 bases + 4 quality bytes.  Returns the 4 key bytes
-//   K = code << 6 | s,   code = A0 T1 C2 G3 (quack.c:150),   s = q - qbase in [0,62]
+//   K = s << 2 | code,   code = A0 T1 C2 G3 (quack.c:150),   s = q - qbase in [0, kScoreBins)
 // `nc` gets the inverted codes in bits 7:6 of each byte (other bits undefined); `bad` accumulates
-// qs | (qs + 1), whose bits 7:6 are non-zero iff some quality byte is outside the window: then the
-// caller re-keys the word to s = 63 (rows nobody reads) and counts its 4 bases exactly.
+// qs | (qs + 64 - kScoreBins), whose bits 7:6 are non-zero iff some quality byte is outside the window:
+// then the caller re-keys the word to the dummy row and counts its 4 bases exactly.
 __device__ __forceinline__ uint32_t key_bytes(uint32_t sw, uint32_t qw, const KeyConsts &c, uint32_t &nc,
                                               uint32_t &bad) {
   // per byte: bit7 of n_cg is 0 iff (b & 0x5B) == 0x43; bit6 of n_g / n_t is 0 iff (b & 0x1F) == 7 / 0x14
@@ -302,17 +314,19 @@ __device__ __forceinline__ uint32_t key_bytes(uint32_t sw, uint32_t qw, const Ke
   const uint32_t n_g = lop3<0x6A>(sw, c.m1f, c.x07) + c.a3f;
   const uint32_t n_t = lop3<0x6A>(sw, c.m1f, c.x14) + c.a3f;
   nc = lop3<0xE4>(n_cg, n_g & n_t, c.m80);  // bit 7 from n_cg, the rest from n_g & n_t
-  // a borrow can only start at a byte that is itself out of range, and that byte ends >= 0xC0
+  // a borrow / carry can only start at a byte that is itself out of range, and that byte is flagged
   const uint32_t qs = qw - c.qsub;
-  bad = lop3<0xFE>(bad, qs, qs + c.one);
-  return lop3<0xF2>(qs, nc, c.mc0);  // qs | (~nc & 0xC0C0C0C0)
+  bad = lop3<0xFE>(bad, qs, qs + c.x11);
+  return lop3<0xF2>(qs << 2, nc >> 6, c.m03);  // (qs << 2) | (~(nc >> 6) & 0x03030303)
 }
-// key bytes of a word that has an out-of-window quality byte: code << 6 | 63
-__device__ __forceinline__ uint32_t key_bytes_bad(uint32_t nc) { return (~nc & 0xC0C0C0C0u) | 0x3F3F3F3Fu; }
+// key bytes of a word that has an out-of-window quality byte: dummy row, code kept
+__device__ __forceinline__ uint32_t key_bytes_bad(uint32_t nc) {
+  return (~(nc >> 6) & 0x03030303u) | ((kScoreBins << 2) * 0x01010101u);
+}
 
 __device__ __forceinline__ bool word_bad(uint32_t qw, uint32_t qsub) {
   const uint32_t qs = qw - qsub;
-  return ((qs | (qs + 0x01010101u)) & 0xC0C0C0C0u) != 0u;
+  return ((qs | (qs + (64u - kScoreBins) * 0x01010101u)) & 0xC0C0C0C0u) != 0u;
 }
 
 // 4 bases' 2-bit codes gathered from bits 7:6 of the 4 bytes of x into the TOP byte of the result,
@@ -323,6 +337,13 @@ __device__ __forceinline__ uint32_t pack16(uint32_t c0, uint32_t c1, uint32_t c2
   const uint32_t lo = __byte_perm(gather_codes(c0), gather_codes(c1), 0x0073);  // bytes: c0.top, c1.top
   const uint32_t hi = __byte_perm(gather_codes(c2), gather_codes(c3), 0x0073);
   return __byte_perm(lo, hi, 0x5410);
+}
+
+// the same from 4 words of key bytes, whose codes sit in bits 1:0 (rare path)
+__device__ __forceinline__ uint32_t pack16_keys(uint4 k) {
+  const uint32_t g0 = ((k.x & 0x03030303u) * 0x00041041u >> 18) & 0xFFu, g1 = ((k.y & 0x03030303u) * 0x00041041u >> 18) & 0xFFu;
+  const uint32_t g2 = ((k.z & 0x03030303u) * 0x00041041u >> 18) & 0xFFu, g3 = ((k.w & 0x03030303u) * 0x00041041u >> 18) & 0xFFu;
+  return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
 }
 
 // largest r with soff[r] <= abs (reads of a tile are in ascending offset order), -1 if none
@@ -604,7 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
   // ---- prologue: zero histograms, load the adapter filter, init barriers ----
   {
     uint4 *h4 = reinterpret_cast<uint4 *>(hist);
-    for (uint32_t i = tid; i < 64u * Lh; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < kHistRows / 4u * Lh; i += kThreads) h4[i] = make_uint4(0, 0, 0, 0);
   }
   for (uint32_t i = tid; i < len_cap; i += kThreads) {
     lenhist[i] = 0;
@@ -690,7 +711,8 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
   HLane<Lh> hl;  // this lane's histogram columns for the word steps
   hl.init(hist_s, lane);
   const uint32_t tid16 = tid * 16u;
-  const uint32_t afilt_lane_s = smem_s + L.afilt + (lane >> 2) * 4u;  // this lane's copy of the anchor map
+  const uint32_t afilt_s = smem_s + L.afilt;
+  const uint32_t afilt_copy = (lane >> 2) * 4u;  // this lane's copy of the anchor map (8 copies, 32-byte rows)
   const uint32_t exact_s = smem_s + L.exact;
   const uint32_t ccount_s = smem_s + L.ccount;
   const uint32_t cand_s = smem_s + L.cand;
@@ -709,11 +731,11 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
       const uint32_t sh = unit == 1u ? 0u : 16u;
       unsigned long long *row = args.a.rows + (size_t)pos * kRow;
       uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-      for (uint32_t sp = 0; sp < 63; sp++) {  // s = 63 rows are the dummies
-        const uint32_t v0 = (hist[(sp)*Lh + col] >> sh) & 0xFFFFu;
-        const uint32_t v1 = (hist[(64u + sp) * Lh + col] >> sh) & 0xFFFFu;
-        const uint32_t v2 = (hist[(128u + sp) * Lh + col] >> sh) & 0xFFFFu;
-        const uint32_t v3 = (hist[(192u + sp) * Lh + col] >> sh) & 0xFFFFu;
+      for (uint32_t sp = 0; sp < kScoreBins; sp++) {  // the rows of s = kScoreBins are the dummies
+        const uint32_t v0 = (hist[(4u * sp + 0u) * Lh + col] >> sh) & 0xFFFFu;
+        const uint32_t v1 = (hist[(4u * sp + 1u) * Lh + col] >> sh) & 0xFFFFu;
+        const uint32_t v2 = (hist[(4u * sp + 2u) * Lh + col] >> sh) & 0xFFFFu;
+        const uint32_t v3 = (hist[(4u * sp + 3u) * Lh + col] >> sh) & 0xFFFFu;
         const uint32_t tot = v0 + v1 + v2 + v3;
         c0 += v0, c1 += v1, c2 += v2, c3 += v3;
         if (tot) {
@@ -739,7 +761,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
     }
     consumer_bar();
     uint4 *h4 = reinterpret_cast<uint4 *>(hist);
-    for (uint32_t i = tid; i < 64u * Lh; i += kCThreads) h4[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < kHistRows / 4u * Lh; i += kCThreads) h4[i] = make_uint4(0, 0, 0, 0);
     consumer_bar();
   };
 
@@ -822,21 +844,28 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
         // anchor j = the 7-mer starting at base 4j+3: row = its bits 13:5 (32-byte rows), bit = its bits 4:0
         const uint32_t e0 = __funnelshift_r(p, nx, 6), e1 = __funnelshift_r(p, nx, 14);
         const uint32_t e2 = __funnelshift_r(p, nx, 22), e3 = __funnelshift_r(p, nx, 30);
-        const uint32_t w0 = lds_u32(afilt_lane_s + (e0 & 0x3FE0u)), w1 = lds_u32(afilt_lane_s + (e1 & 0x3FE0u));
-        const uint32_t w2 = lds_u32(afilt_lane_s + (e2 & 0x3FE0u)), w3 = lds_u32(afilt_lane_s + (e3 & 0x3FE0u));
+        // (e & 0x3FE0) | copy offset in one LOP3; the table base is the load's immediate
+        const uint32_t w0 = lds_u32_at(lop3<0xEA>(e0, 0x3FE0u, afilt_copy), afilt_s);
+        const uint32_t w1 = lds_u32_at(lop3<0xEA>(e1, 0x3FE0u, afilt_copy), afilt_s);
+        const uint32_t w2 = lds_u32_at(lop3<0xEA>(e2, 0x3FE0u, afilt_copy), afilt_s);
+        const uint32_t w3 = lds_u32_at(lop3<0xEA>(e3, 0x3FE0u, afilt_copy), afilt_s);
         const uint32_t m0 = __funnelshift_r(w0, 0u, e0), m1 = __funnelshift_r(w1, 0u, e1);
         const uint32_t m2 = __funnelshift_r(w2, 0u, e2), m3 = __funnelshift_r(w3, 0u, e3);
         const bool hit = own && ((m0 | m1 | m2 | m3) & 1u);
         if (__ballot_sync(0xffffffffu, hit)) {
           if (hit) {  // one queue entry per anchor that passed: 25 bases, anchor index, unit
-            uint32_t mask = (m0 & 1u) | ((m1 & 1u) << 1) | ((m2 & 1u) << 2) | ((m3 & 1u) << 3);
-            uint32_t idx = atomicAdd(shared_ptr<uint32_t>(ccnt_s), (uint32_t)__popc(mask));
-            const uint32_t hi18 = (nx & 0x3FFFFu) | (u << 20);  // 18 bits of bases, 2 of anchor index, 12 of unit
-            while (mask) {
-              const uint32_t j = __ffs(mask) - 1u;
-              mask &= mask - 1u;
-              if (idx < kCandCap) sts_u64(cq_s + idx * 8u, p, hi18 | (j << 18));  // beyond the cap: tile re-scanned below
-              idx++;
+            const uint32_t b0 = m0 & 1u, b1 = m1 & 1u, b2 = m2 & 1u, b3 = m3 & 1u;
+            const uint32_t idx = atomicAdd(shared_ptr<uint32_t>(ccnt_s), b0 + b1 + b2 + b3);
+            if (idx + 4u <= kCandCap) {  // beyond the cap: the tile is re-scanned below
+              const uint32_t hi18 = (nx & 0x3FFFFu) | (u << 20);  // 18 bits of bases, 2 of anchor index, 12 of unit
+              uint32_t a = cq_s + idx * 8u;
+              if (b0) sts_u64(a, p, hi18);
+              a += b0 * 8u;
+              if (b1) sts_u64(a, p, hi18 | (1u << 18));
+              a += b1 * 8u;
+              if (b2) sts_u64(a, p, hi18 | (2u << 18));
+              a += b2 * 8u;
+              if (b3) sts_u64(a, p, hi18 | (3u << 18));
             }
           }
         }
@@ -860,7 +889,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
       const uint32_t total = lds_u32(ccount_s + cslot * 4u);
       const uint32_t fhit_s = fhit_s0 + (it & 1u) * (kMaxTileReads * 4u);
       const uint32_t ulen = uniform ? len0 : 0u;
-      if (total <= kCandCap) {
+      if (total + 4u <= kCandCap) {  // every push found room
         const uint32_t cq_s = cand_s + (it & 1u) * (kCandCap * 8u);
         for (uint32_t i = tid; i < total * 4u; i += kCThreads) {
           const uint2 c = lds_u64(cq_s + (i >> 2) * 8u);
@@ -873,7 +902,7 @@ __global__ void __launch_bounds__(kThreads, 1) fused_kernel(const FusedArgs args
         for (uint32_t i = tid; i < n16 * 4u; i += kCThreads) {
           const uint32_t unit = i >> 2, t = i & 3u;
           const uint4 ka = lds_u128(kbuf_s + unit * 16u), kb = lds_u128(kbuf_s + unit * 16u + 16u);
-          const uint32_t lo = pack16(ka.x, ka.y, ka.z, ka.w), hi = pack16(kb.x, kb.y, kb.z, kb.w);
+          const uint32_t lo = pack16_keys(ka), hi = pack16_keys(kb);
           for (uint32_t j = 0; j < 4u; j++)
             confirm_window(lo, hi, unit, 4u * j + t, args.ad, exact_s, lo_al, idx_s, nr, ulen, fhit_s);
         }

@@ -68,7 +68,7 @@ struct FusedPlan {
   uint32_t tile_bytes;      // capacity of one stage buffer (seq or qual), multiple of 16
   uint32_t reads_per_tile;  // multiple of 4, <= kMaxTileReads
   uint32_t stages;
-  uint32_t qbase;           // score field s = q - qbase, s in [0,62] counted in shared memory
+  uint32_t qbase;           // score field s = q - qbase, s in [0,46] counted in shared memory
   uint32_t smem_bytes;
   uint32_t grid;
   int ok;                   // 0: len_cap does not fit -> use the simple kernel

@@ -92,9 +92,9 @@ def test_all_byte_values(kernel, table, keys):
 
 
 @pytest.mark.parametrize("kernel", KERNELS, ids=KNAME.get)
-@pytest.mark.parametrize("qlo,qhi", [(0, 90), (31, 71), (60, 62)], ids=["full", "phred64", "edge"])
+@pytest.mark.parametrize("qlo,qhi", [(0, 90), (31, 71), (44, 49), (60, 62)], ids=["full", "phred64", "edge", "high"])
 def test_score_ranges(kernel, qlo, qhi, table, keys):
-    """Scores beyond the shared-memory window (Phred > 62, e.g. phred64 files) take the exact slow path."""
+    """Scores beyond the shared-memory window (Phred > 46, e.g. phred64 files) take the exact slow path."""
     batch = util.random_batch(77, 8000, 100, 151, qlo=qlo, qhi=qhi)
     got = run_gpu(batch, 151, keys, kernel)
     util.assert_same(got, po.accumulate_batch(*batch, table), f"scores {qlo}-{qhi}")
