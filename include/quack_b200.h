@@ -50,9 +50,10 @@ typedef enum {
 } qb_status;
 
 typedef enum {
-  QB_KERNEL_AUTO = 0,      /* fused kernel when the batch's longest read fits its shared-memory histogram */
+  QB_KERNEL_AUTO = 0,      /* warp-tile kernel when the batch's longest read fits its shared-memory histogram */
   QB_KERNEL_SIMPLE = 1,    /* one warp per read, global atomics: any len_cap, slow */
-  QB_KERNEL_FUSED = 2      /* TMA-staged tiles, joint (base,score) shared-memory histogram */
+  QB_KERNEL_FUSED = 2,     /* CTA-wide TMA-staged tiles, joint (base,score) shared-memory histogram (v3) */
+  QB_KERNEL_WTILE = 3      /* autonomous warps, each with its own TMA-staged tile ring (v4, the default) */
 } qb_kernel;
 
 typedef struct qb_ctx qb_ctx;       /* one per process; owns devices, streams, accumulators */
@@ -148,8 +149,9 @@ int qb_dbatch_info(const qb_dbatch *b, uint32_t *n_reads, uint64_t *n_bytes);
 void qb_dbatch_free(qb_ctx *ctx, qb_dbatch *b);
 /* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
 uint64_t qb_launch_count(const qb_ctx *ctx);
-/* How many of those launches took the simple / the fused kernel (the fused one is chosen per batch
- * whenever the batch's longest read fits its shared-memory histogram, whatever len_cap is). */
+/* How many of those launches took the simple kernel / one of the shared-memory kernels (warp-tile or
+ * fused; chosen per batch whenever the batch's longest read fits the shared-memory histogram,
+ * whatever len_cap is). */
 int qb_kernel_counts(const qb_ctx *ctx, uint64_t *n_simple, uint64_t *n_fused);
 /* Live kernel timing: after qb_profile_enable(ctx, n) every statistics-kernel launch is bracketed by
  * a CUDA event pair on the stream it is launched on (up to n launches, then recording stops).

@@ -76,6 +76,7 @@ struct Device {
   int id = 0;
   int sm_count = 0;
   int smem_optin = 0;
+  int smem_reserved = 0;  // shared memory the driver keeps per block: dynamic shared memory starts behind it
   std::vector<unsigned long long *> acc;  // per mate: [len_cap*97 rows][kNumCounters]
   unsigned long long *reduce_buf = nullptr;
   uint32_t *d_bitmap = nullptr, *d_anchor = nullptr, *d_exact = nullptr;
@@ -175,28 +176,36 @@ int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaS
   qb::Accum ac = accum(ctx, d, mate);
   int kernel = ctx->cfg.kernel;
   qb::FusedPlan plan{};
+  qb::WtilePlan wplan{};
   if (kernel != QB_KERNEL_SIMPLE) {
     // The shared-memory histogram is sized by the longest read of THIS batch (the caller's max_len
     // promise; a longer read is counted as an error and fails qb_finish), not by len_cap: a context
-    // opened for 65536-bp reads still runs short-read batches on the fused kernel.
+    // opened for 65536-bp reads still runs short-read batches on the shared-memory kernels.
     uint32_t eff_cap = ctx->cfg.len_cap;
     if (v.max_len && v.max_len < eff_cap) eff_cap = v.max_len < 11u ? 11u : v.max_len;
-    plan = qb::fused_plan(eff_cap, v.max_len, ad.enabled, d.sm_count, (uint32_t)d.smem_optin, ctx->qbase);
-    if (!plan.ok) {
-      if (kernel == QB_KERNEL_FUSED)
-        return fail(ctx, QB_ERR_CAPACITY, "reads of up to %u bp do not fit the fused kernel's shared-memory histogram",
-                    eff_cap);
-      kernel = QB_KERNEL_SIMPLE;
-    } else {
+    if (kernel != QB_KERNEL_FUSED)
+      wplan = qb::wtile_plan(eff_cap, v.max_len, ad.enabled, d.sm_count, (uint32_t)d.smem_optin,
+                             (uint32_t)d.smem_reserved, ctx->qbase);
+    if (kernel != QB_KERNEL_WTILE && !wplan.ok)
+      plan = qb::fused_plan(eff_cap, v.max_len, ad.enabled, d.sm_count, (uint32_t)d.smem_optin, ctx->qbase);
+    if (wplan.ok) {
+      kernel = QB_KERNEL_WTILE;
+      ac.len_cap = eff_cap;
+    } else if (plan.ok) {
       kernel = QB_KERNEL_FUSED;
       ac.len_cap = eff_cap;
+    } else {
+      if (kernel != QB_KERNEL_AUTO)
+        return fail(ctx, QB_ERR_CAPACITY, "reads of up to %u bp do not fit the shared-memory histogram of kernel %d",
+                    eff_cap, kernel);
+      kernel = QB_KERNEL_SIMPLE;
     }
   }
   qb_ctx::ProfRec *rec = nullptr;
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->launches++;
-    (kernel == QB_KERNEL_FUSED ? ctx->launches_fused : ctx->launches_simple)++;
+    (kernel == QB_KERNEL_SIMPLE ? ctx->launches_simple : ctx->launches_fused)++;
     if ((int)ctx->prof.size() < ctx->prof_cap) {
       qb_ctx::ProfRec r{};
       if (cudaEventCreate(&r.e0) == cudaSuccess && cudaEventCreate(&r.e1) == cudaSuccess) {
@@ -209,8 +218,9 @@ int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaS
   }
   cudaEvent_t e0 = rec ? rec->e0 : nullptr, e1 = rec ? rec->e1 : nullptr;
   if (e0) cudaEventRecord(e0, stream);
-  cudaError_t e = kernel == QB_KERNEL_FUSED ? qb::launch_fused(v, ac, ad, plan, stream)
-                                            : qb::launch_simple(v, ac, ad, d.sm_count, stream);
+  cudaError_t e = kernel == QB_KERNEL_WTILE   ? qb::launch_wtile(v, ac, ad, wplan, stream)
+                  : kernel == QB_KERNEL_FUSED ? qb::launch_fused(v, ac, ad, plan, stream)
+                                              : qb::launch_simple(v, ac, ad, d.sm_count, stream);
   if (e1) cudaEventRecord(e1, stream);
   if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return QB_OK;
@@ -303,7 +313,9 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
     QB_CREATE_CUDA(cudaSetDevice(d.id));
     QB_CREATE_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.id));
     QB_CREATE_CUDA(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.id));
+    QB_CREATE_CUDA(cudaDeviceGetAttribute(&d.smem_reserved, cudaDevAttrReservedSharedMemoryPerBlock, d.id));
     QB_CREATE_CUDA(qb::fused_configure());
+    QB_CREATE_CUDA(qb::wtile_configure());
     QB_CREATE_CUDA(cudaStreamCreateWithFlags(&d.main_stream, cudaStreamNonBlocking));
     d.acc.resize(cfg.n_mates);
     for (int m = 0; m < cfg.n_mates; m++) {

@@ -80,6 +80,33 @@ constexpr uint32_t kMaxTileReads = 248;   // reads per tile (8 per consumer warp
 #endif
 constexpr int kFusedConsumerWarps = QB_CW;  // + 1 producer warp = 512 threads (up to 128 registers each), 1 CTA per SM
 
+// ---- warp-tile kernel geometry (qb_wtile.cu; computed on the host, see wtile_plan) --------
+#ifndef QB_WW
+#define QB_WW 24
+#endif
+constexpr int kWtileWarps = QB_WW;  // autonomous warps per CTA (one CTA per SM)
+
+struct WtilePlan {
+  uint32_t nsets;            // histogram sets of 128 positions (1: reads <= 192 bp, 2: <= 320 bp), + 64 tail positions
+  uint32_t reads_per_tile;   // R <= 32 whole reads per warp tile
+  uint32_t tile_bytes;       // capacity of one staged byte buffer (seq or qual), multiple of 16
+  uint32_t buf;              // tile_bytes + pad
+  uint32_t wblock;           // bytes of one warp block (barriers, tile headers, queue, 2 stages x 2 buffers)
+  uint32_t smem_base;        // shared address the dynamic shared memory must start at (checked by the kernel)
+  uint32_t smem_bytes;
+  uint32_t tail_s, afilt_s, exact_s, lenhist_s, kmerhist_s;  // shared addresses of the CTA-wide arrays
+  uint32_t region_s[3], region_n[3];                         // warp blocks: region_n[i] blocks from region_s[i]
+  uint32_t qbase;            // score field s = q - qbase
+  uint32_t grid;
+  int ok;                    // 0: the batch does not fit -> another kernel
+};
+
+WtilePlan wtile_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int sm_count, uint32_t smem_optin,
+                     uint32_t smem_reserved, uint32_t qbase);
+cudaError_t launch_wtile(const BatchView &b, const Accum &a, const AdapterSet &ad, const WtilePlan &plan,
+                         cudaStream_t stream);
+cudaError_t wtile_configure();  // opt in to the large dynamic shared memory once per device
+
 FusedPlan fused_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int sm_count,
                      uint32_t smem_optin, uint32_t qbase);
 

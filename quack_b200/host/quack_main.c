@@ -11,7 +11,7 @@
  *   QB_DEVICES=N        number of GPUs to spread batches over (default 1)
  *   QB_BATCH_MB=M       pinned slot size in MiB for seq[] and for qual[] (default 64)
  *   QB_LEN_CAP=L        longest read accepted (default 65536)
- *   QB_KERNEL=0|1|2     auto | simple | fused
+ *   QB_KERNEL=0|1|2|3   auto | simple | fused | wtile
  *   QB_STATS_JSON=path  write reads/s, bases/s and stage times there (stdout stays the SVG)
  */
 #include <pthread.h>

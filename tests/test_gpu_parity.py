@@ -14,8 +14,9 @@ import qb_testutil as util
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [capi.KERNEL_SIMPLE, capi.KERNEL_FUSED]
-KNAME = {capi.KERNEL_SIMPLE: "simple", capi.KERNEL_FUSED: "fused"}
+KERNELS = [capi.KERNEL_SIMPLE, capi.KERNEL_FUSED, capi.KERNEL_WTILE]
+SMEM_KERNELS = [capi.KERNEL_FUSED, capi.KERNEL_WTILE]
+KNAME = {capi.KERNEL_SIMPLE: "simple", capi.KERNEL_FUSED: "fused", capi.KERNEL_WTILE: "wtile"}
 
 
 @pytest.fixture(scope="module")
@@ -142,11 +143,12 @@ def test_two_mates_many_small_batches(kernel, table, keys):
     assert np.array_equal(r0.rows, rows)
 
 
-def test_u16_flush_path(table, keys, monkeypatch):
+@pytest.mark.parametrize("kernel", SMEM_KERNELS, ids=KNAME.get)
+def test_u16_flush_path(kernel, table, keys, monkeypatch):
     """More than 65535 reads through one CTA forces the mid-launch flush of the packed u16 counters."""
     monkeypatch.setenv("QB_FUSED_GRID", "2")
     batch = util.random_batch(31, 300000, 30, 50, plant=0.05)
-    got = run_gpu(batch, 64, keys, capi.KERNEL_FUSED, resident=True)
+    got = run_gpu(batch, 64, keys, kernel, resident=True)
     util.assert_same(got, po.accumulate_batch(*batch, table), "flush")
 
 
@@ -155,7 +157,7 @@ def test_linearity_and_generator_full_size(keys, table):
     properties (running the batch twice doubles every count; per-position content and score sums equal
     the number of reads that long) and against the oracle on the first 100 k reads."""
     n = 2_000_000
-    with capi.Context(150, adapter_keys=keys, kernel=capi.KERNEL_FUSED) as ctx:
+    with capi.Context(150, adapter_keys=keys, kernel=capi.KERNEL_WTILE) as ctx:
         b = ctx.generate(2, 1, 0, n, 150, 150, 0.1)
         b.run(0)
         r1 = ctx.finish(0)
@@ -242,10 +244,11 @@ def test_auto_kernel_is_planned_per_batch(table, keys):
     assert np.array_equal(res.rows, rows)
 
 
-def test_max_len_promise_is_enforced(keys):
+@pytest.mark.parametrize("kernel", SMEM_KERNELS, ids=KNAME.get)
+def test_max_len_promise_is_enforced(kernel, keys):
     """A batch submitted with a max_len smaller than its longest read is rejected loudly, not mis-counted."""
     batch = util.random_batch(43, 200, 100, 100)
-    with capi.Context(304, adapter_keys=keys, kernel=capi.KERNEL_FUSED) as ctx:
+    with capi.Context(304, adapter_keys=keys, kernel=kernel) as ctx:
         b = ctx.upload(*batch, max_len=50)
         b.run(0)
         with pytest.raises(capi.QbError):
@@ -269,5 +272,6 @@ def test_adapter_dimers_overflow_the_hit_queue(table, keys):
     for kernel in KERNELS:
         util.assert_same(run_gpu(batch, 150, keys, kernel), want, KNAME[kernel])
     uniform = util.pack([(s[:150].ljust(150, b"A"), q[:150].ljust(150, b"I")) for s, q in reads])
-    util.assert_same(run_gpu(uniform, 150, keys, capi.KERNEL_FUSED, resident=True),
-                     po.accumulate_batch(*uniform, table), "uniform dimers")
+    for kernel in SMEM_KERNELS:
+        util.assert_same(run_gpu(uniform, 150, keys, kernel, resident=True),
+                         po.accumulate_batch(*uniform, table), "uniform dimers " + KNAME[kernel])

@@ -12,7 +12,10 @@ from quack_b200 import capi
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import qb_testutil as util
 
-HBM = 6550.1
+HBM = 6545.3
+KN = {capi.KERNEL_SIMPLE: "simple", capi.KERNEL_FUSED: "fused", capi.KERNEL_WTILE: "wtile"}
+# QB_QUICK_KERNELS=3,2 restricts the sweep (default: wtile, fused, simple)
+KSEL = [int(k) for k in os.environ.get("QB_QUICK_KERNELS", "3,2,1").split(",")]
 
 
 def main():
@@ -21,20 +24,21 @@ def main():
     out = []
     for lmin, lmax, cap in ((150, 150, 150), (35, 300, 304)):
         for ad in (None, keys):
-            for kernel in (capi.KERNEL_FUSED, capi.KERNEL_SIMPLE):
-                nn = n if kernel == capi.KERNEL_FUSED else n // 8
+            for kernel in KSEL:
+                nn = n if kernel != capi.KERNEL_SIMPLE else n // 8
                 with capi.Context(cap, adapter_keys=ad, kernel=kernel) as ctx:
                     b = ctx.generate(2, 1, 0, nn, lmin, lmax, 0.1)
                     nr, nb = b.info
                     avg, mn = b.time(0, warmup=2, iters=5, flush_l2=False)
                     alg = 2 * nb + 8 * nr
                     rec = {"len": [lmin, lmax], "adapters": ad is not None,
-                           "kernel": "fused" if kernel == capi.KERNEL_FUSED else "simple", "reads": nr,
+                           "kernel": KN[kernel], "reads": nr,
                            "ms_avg": round(avg, 4), "ms_min": round(mn, 4), "Greads_s": round(nr / avg / 1e6, 3),
                            "Gbases_s": round(nb / avg / 1e6, 2), "GBps": round(alg / avg / 1e6, 1),
                            "frac_hbm": round(alg / avg / 1e6 / HBM, 4)}
-                    if ad is not None:
-                        rec["bloom"] = ctx.adapter_filter_info()
+                    for k in ("QB_LIB", "QB_WT_READS"):
+                        if os.environ.get(k):
+                            rec[k] = os.path.basename(os.environ[k])
                     print(json.dumps(rec), flush=True)
                     out.append(rec)
                     b.free()
