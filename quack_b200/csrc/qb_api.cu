@@ -67,6 +67,7 @@ struct Slot {
   uint32_t *h_off = nullptr, *h_len = nullptr;
   uint8_t *d_seq = nullptr, *d_qual = nullptr;
   uint32_t *d_off = nullptr, *d_len = nullptr;
+  uint2 *d_tiles = nullptr;  // tile descriptors of the warp-tile kernel (one per read at most)
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   bool pending = false;
@@ -115,6 +116,7 @@ struct qb_dbatch {
   int device_index;
   uint8_t *d_seq, *d_qual;
   uint32_t *d_off, *d_len;
+  uint2 *d_tiles;
   uint32_t n_reads;
   uint64_t n_bytes;
   uint32_t max_len;
@@ -343,6 +345,7 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
       QB_CREATE_CUDA(cudaMalloc(&s.d_qual, pad_bytes(cfg.batch_bytes)));
       QB_CREATE_CUDA(cudaMalloc(&s.d_off, pad_reads(cfg.batch_reads) * 4));
       QB_CREATE_CUDA(cudaMalloc(&s.d_len, pad_reads(cfg.batch_reads) * 4));
+      QB_CREATE_CUDA(cudaMalloc(&s.d_tiles, pad_reads(cfg.batch_reads) * sizeof(uint2)));
       QB_CREATE_CUDA(cudaMemset(s.d_seq, 0, pad_bytes(cfg.batch_bytes)));
       QB_CREATE_CUDA(cudaMemset(s.d_qual, 0, pad_bytes(cfg.batch_bytes)));
       QB_CREATE_CUDA(cudaMemset(s.d_off, 0, pad_reads(cfg.batch_reads) * 4));
@@ -387,6 +390,7 @@ void qb_destroy(qb_ctx *ctx) {
       cudaFree(s.d_qual);
       cudaFree(s.d_off);
       cudaFree(s.d_len);
+      cudaFree(s.d_tiles);
       if (s.stream) cudaStreamDestroy(s.stream);
       if (s.done) cudaEventDestroy(s.done);
     }
@@ -463,7 +467,7 @@ static int submit_on(qb_ctx *ctx, int di, int si, int mate, const uint8_t *seq, 
     }
     QB_CUDA(ctx, cudaMemcpyAsync(s.d_off, offset, (size_t)n_reads * 4, cudaMemcpyHostToDevice, s.stream));
     QB_CUDA(ctx, cudaMemcpyAsync(s.d_len, length, (size_t)n_reads * 4, cudaMemcpyHostToDevice, s.stream));
-    qb::BatchView v{s.d_seq, s.d_qual, s.d_off, s.d_len, n_reads, n_bytes, max_len ? max_len : ctx->cfg.len_cap};
+    qb::BatchView v{s.d_seq, s.d_qual, s.d_off, s.d_len, n_reads, n_bytes, max_len ? max_len : ctx->cfg.len_cap, s.d_tiles};
     int rc = launch_batch(ctx, d, v, mate, s.stream);
     if (rc) return rc;
   }
@@ -733,7 +737,8 @@ static int dbatch_alloc(qb_ctx *ctx, int di, uint32_t n_reads, uint64_t n_bytes,
   if ((e = cudaMalloc(&b->d_seq, pad_bytes(n_bytes))) != cudaSuccess ||
       (e = cudaMalloc(&b->d_qual, pad_bytes(n_bytes))) != cudaSuccess ||
       (e = cudaMalloc(&b->d_off, pad_reads(n_reads) * 4)) != cudaSuccess ||
-      (e = cudaMalloc(&b->d_len, pad_reads(n_reads) * 4)) != cudaSuccess) {
+      (e = cudaMalloc(&b->d_len, pad_reads(n_reads) * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&b->d_tiles, pad_reads(n_reads) * sizeof(uint2))) != cudaSuccess) {
     qb_dbatch_free(ctx, b);
     return fail(ctx, QB_ERR_NOMEM, "cudaMalloc for a device batch failed: %s", cudaGetErrorString(e));
   }
@@ -819,6 +824,7 @@ void qb_dbatch_free(qb_ctx *ctx, qb_dbatch *b) {
   cudaFree(b->d_qual);
   cudaFree(b->d_off);
   cudaFree(b->d_len);
+  cudaFree(b->d_tiles);
   delete b;
 }
 
@@ -828,7 +834,7 @@ int qb_dbatch_run(qb_ctx *ctx, qb_dbatch *b, int mate) {
   if (!b) return QB_ERR_ARG;
   Device &d = ctx->dev[b->device_index];
   QB_CUDA(ctx, cudaSetDevice(d.id));
-  qb::BatchView v{b->d_seq, b->d_qual, b->d_off, b->d_len, b->n_reads, b->n_bytes, b->max_len};
+  qb::BatchView v{b->d_seq, b->d_qual, b->d_off, b->d_len, b->n_reads, b->n_bytes, b->max_len, b->d_tiles};
   return launch_batch(ctx, d, v, mate, d.main_stream);
 }
 

@@ -54,6 +54,7 @@ struct BatchView {
   uint32_t n_reads;
   uint64_t n_bytes;
   uint32_t max_len;        // longest read in the batch (upper bound)
+  uint2 *tiles;            // scratch of n_reads entries: tile descriptors written by the warp-tile kernel's first pass
 };
 
 struct Accum {

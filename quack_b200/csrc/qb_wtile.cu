@@ -9,9 +9,12 @@
 //     waits on the mbarrier of tile t+1: no producer warp, no polling, no CTA barrier in the steady state.
 //     Warps drift apart, so the ALU-heavy phase A of one warp overlaps the shared-memory-heavy phase H of
 //     another (the v3 kernel ran them in lock step and left both pipes < 45 % busy);
-//   * per-tile bookkeeping is one lane per read (offsets / lengths loaded straight from global memory one
-//     tile ahead, validated with warp votes), candidate queue positions come from a ballot + popc instead
-//     of shared atomics, queue entries are one per 16-byte unit (4-bit anchor mask);
+//   * a small first pass (tile_desc_kernel, one warp per tile) validates the reads of every tile and writes an
+//     8-byte tile descriptor (first byte, read count, common read length or 0, byte count); the hot kernel
+//     reads one descriptor per tile, one tile ahead, and never touches offsets / lengths of tiles whose reads
+//     all have one length and lie back to back (the normal case);
+//   * candidate queue positions come from a ballot + popc instead of shared atomics, queue entries are one
+//     per 16-byte unit (4-bit anchor mask);
 //   * histogram rows are 256 bytes at a 64 KiB-aligned shared address, so ONE byte permute builds the
 //     address of a base's counter from its key byte (row = key): 2 instructions per base in phase H
 //     (PRMT + RED) instead of 3.
@@ -133,24 +136,58 @@ __device__ __forceinline__ void w_tail(uint32_t L, uint32_t lane, uint32_t (&pin
   if (KIND == 3) t1 = 128u * kSets + 32u + lane < L ? 0x10000u : 0u;
 }
 
-// nr reads of length L back to back from kb: two reads in flight
+// nr reads of length L back to back from kb.  Four reads per iteration: 4 L is a multiple of 4, so the
+// byte alignment of read j of a group (the funnel-shift amount) is loop invariant and its aligned word
+// address just advances by 4 L -- two address instructions per read instead of six.
 template <int kSets, int NF, int KIND>
 __device__ __forceinline__ void w_uniform(WInc c, uint32_t tl, uint32_t kb, uint32_t L, uint32_t nr, uint32_t lane) {
   uint32_t pinc[4], t0, t1;
   w_tail<kSets, NF, KIND>(L, lane, pinc, t0, t1);
+  constexpr int kWords = NF + (KIND == 1 ? 1 : 0);
   uint32_t r = 0;
-  for (; r + 2u <= nr; r += 2u) {
-    WRead<kSets, NF, KIND> x, y;
-    x.load(kb, lane, pinc[0] != 0u);
-    y.load(kb + L, lane, pinc[0] != 0u);
-    x.red(c, pinc, tl, t0, t1);
-    y.red(c, pinc, tl, t0, t1);
-    kb += 2u * L;
+  if (nr >= 4u) {
+    uint32_t al[4], sh[4], kt[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t kw = kb + (uint32_t)j * L + 4u * lane;
+      al[j] = kw & ~3u;
+      sh[j] = kw << 3;
+      kt[j] = kb + (uint32_t)j * L + 128u * kSets + lane;
+    }
+    const uint32_t L4 = 4u * L;
+    for (; r + 4u <= nr; r += 4u) {
+      uint32_t k4[4][kWords > 0 ? kWords : 1], b0[4], b1[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+#pragma unroll
+        for (int s = 0; s < NF; s++)
+          k4[j][s] = __funnelshift_r(lds_u32(al[j] + 128u * s), lds_u32(al[j] + 128u * s + 4u), sh[j]);
+        if constexpr (KIND == 1) {
+          k4[j][NF] = 0;
+          if (pinc[0]) k4[j][NF] = __funnelshift_r(lds_u32(al[j] + 128u * NF), lds_u32(al[j] + 128u * NF + 4u), sh[j]);
+        }
+        if constexpr (KIND >= 2) b0[j] = lds_u8(kt[j]);
+        if constexpr (KIND == 3) b1[j] = lds_u8(kt[j] + 32u);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if constexpr (NF >= 1) w_red_word<0u>(k4[j][0], c, c.lo, c.hi, c.lo, c.hi);
+        if constexpr (NF >= 2) w_red_word<0x10000u>(k4[j][1], c, c.lo, c.hi, c.lo, c.hi);
+        if constexpr (KIND == 1 && NF == 0) w_red_word<0u>(k4[j][0], c, pinc[0], pinc[1], pinc[2], pinc[3]);
+        if constexpr (KIND == 1 && NF == 1) w_red_word<0x10000u>(k4[j][1], c, pinc[0], pinc[1], pinc[2], pinc[3]);
+        if constexpr (KIND >= 2) red_shared_add<0>(b0[j] * kTailRow + tl, t0);
+        if constexpr (KIND == 3) red_shared_add<0>(b1[j] * kTailRow + tl, t1);
+        al[j] += L4;
+        if constexpr (KIND >= 2) kt[j] += L4;
+      }
+    }
+    kb += r * L;
   }
-  if (r < nr) {
+  for (; r < nr; r++) {
     WRead<kSets, NF, KIND> x;
     x.load(kb, lane, pinc[0] != 0u);
     x.red(c, pinc, tl, t0, t1);
+    kb += L;
   }
 }
 template <int kSets, int NF, int KIND>
@@ -162,18 +199,56 @@ __device__ __forceinline__ void w_one(WInc c, uint32_t tl, uint32_t kb, uint32_t
   x.red(c, pinc, tl, t0, t1);
 }
 
-// rare path of phase A: re-key the words of a 16-byte unit whose quality bytes fall outside the window,
-// counting their bases exactly (global atomics)
-__device__ __noinline__ uint32_t w_fix_bad_unit(uint4 sv, uint4 qv, uint4 &K, uint32_t n0, uint32_t n1, uint32_t n2,
-                                                uint32_t n3, uint32_t qsub, uint32_t abs0, uint32_t soff_s, uint32_t nr,
-                                                const Accum a) {
-  const uint32_t *soff = shared_ptr<const uint32_t>(soff_s);
-  const uint32_t *slen = soff + 32;
+// Where absolute byte `abs` of the batch falls: read index inside the tile, position inside the read, read
+// length.  Tiles whose reads all have length ulen and lie back to back from byte lo divide; the others
+// search the staged offsets.  false: the byte belongs to no read of the tile.
+struct WTileMap {
+  uint32_t lo, ulen, nr, soff_s;  // soff_s: shared address of soff[32], slen[32] behind it (ragged tiles only)
+};
+__device__ __forceinline__ bool w_locate(const WTileMap &tm, uint32_t abs, uint32_t &r, uint32_t &pos, uint32_t &len) {
+  if (tm.ulen) {
+    const uint32_t d = abs - tm.lo;
+    if ((int32_t)d < 0) return false;
+    // d < 2^16 and (d + 0.5) / len is never closer than 1/(2 len) to an integer: the float quotient is exact
+    r = (uint32_t)(((float)d + 0.5f) * __frcp_rn((float)tm.ulen));
+    pos = d - r * tm.ulen;
+    len = tm.ulen;
+    return r < tm.nr;
+  }
+  const uint32_t *soff = shared_ptr<const uint32_t>(tm.soff_s);
+  const int rr = find_read(soff, tm.nr, abs);
+  if (rr < 0) return false;
+  r = (uint32_t)rr;
+  pos = abs - soff[r];
+  len = soff[32 + r];
+  return pos < len;
+}
+
+// rare path of phase A: the 4 bases of a word with an out-of-window quality byte, counted one by one
+__device__ __noinline__ uint32_t w_exact_word(uint32_t sw, uint32_t qw, uint32_t abs0, const WTileMap tm, const Accum a) {
   uint32_t n_invalid = 0;
-  if (word_bad(qv.x, qsub)) K.x = key_bytes_bad(n0), n_invalid += exact_word(sv.x, qv.x, abs0, soff, slen, nr, a);
-  if (word_bad(qv.y, qsub)) K.y = key_bytes_bad(n1), n_invalid += exact_word(sv.y, qv.y, abs0 + 4u, soff, slen, nr, a);
-  if (word_bad(qv.z, qsub)) K.z = key_bytes_bad(n2), n_invalid += exact_word(sv.z, qv.z, abs0 + 8u, soff, slen, nr, a);
-  if (word_bad(qv.w, qsub)) K.w = key_bytes_bad(n3), n_invalid += exact_word(sv.w, qv.w, abs0 + 12u, soff, slen, nr, a);
+  for (uint32_t j = 0; j < 4; j++) {
+    uint32_t r, p, len;
+    if (!w_locate(tm, abs0 + j, r, p, len)) continue;  // alignment slack
+    if (len > a.len_cap) continue;                      // a read the launch rejects anyway
+    unsigned long long *row = a.rows + (size_t)p * kRow;
+    atomicAdd(&row[kColContent + base_code((sw >> (8 * j)) & 0xFFu)], 1ull);
+    const int sc = (int)((qw >> (8 * j)) & 0xFFu) - 33;
+    if (sc >= 0 && sc < 91)
+      atomicAdd(&row[sc], 1ull);
+    else
+      n_invalid++;
+  }
+  return n_invalid;
+}
+// ... re-keying the words of a 16-byte unit whose quality bytes fall outside the window
+__device__ __noinline__ uint32_t w_fix_bad_unit(uint4 sv, uint4 qv, uint4 &K, uint32_t n0, uint32_t n1, uint32_t n2,
+                                                uint32_t n3, uint32_t qsub, uint32_t abs0, const WTileMap tm, const Accum a) {
+  uint32_t n_invalid = 0;
+  if (word_bad(qv.x, qsub)) K.x = key_bytes_bad(n0), n_invalid += w_exact_word(sv.x, qv.x, abs0, tm, a);
+  if (word_bad(qv.y, qsub)) K.y = key_bytes_bad(n1), n_invalid += w_exact_word(sv.y, qv.y, abs0 + 4u, tm, a);
+  if (word_bad(qv.z, qsub)) K.z = key_bytes_bad(n2), n_invalid += w_exact_word(sv.z, qv.z, abs0 + 8u, tm, a);
+  if (word_bad(qv.w, qsub)) K.w = key_bytes_bad(n3), n_invalid += w_exact_word(sv.w, qv.w, abs0 + 12u, tm, a);
   return n_invalid;
 }
 
@@ -182,35 +257,60 @@ __device__ __noinline__ uint32_t w_fix_bad_unit(uint4 sv, uint4 qv, uint4 &K, ui
 // found in the exact key set whose 10 bases lie inside one read lowers that read's first-hit position.  A
 // hit that ends on the last base of its read is dropped: it can only be the first hit if there is no
 // other, and then the reference counts nothing (quack.c:215).
-__device__ __forceinline__ void w_confirm(uint32_t lo, uint32_t hi, uint32_t unit, uint32_t w, const AdapterSet ad,
-                                          uint32_t exact_s, uint32_t lo_al, uint32_t soff_s, uint32_t nr, uint32_t ulen,
-                                          uint32_t fhit_s) {
+// Returns true when a hit was recorded and every later window of the unit lies in the same read (so none
+// of them can be that read's first hit).
+__device__ __forceinline__ bool w_confirm(uint32_t lo, uint32_t hi, uint32_t unit, uint32_t w, const AdapterSet ad,
+                                          uint32_t exact_s, uint32_t lo_al, const WTileMap &tm, uint32_t fhit_s) {
   const uint32_t key = __funnelshift_r(lo, hi, 2u * w) & 0xFFFFFu;
   bool member;
   if (ad.exact)
     member = lds_u32(exact_s + exact_off1(key)) == key || lds_u32(exact_s + exact_off2(key)) == key;
   else
     member = (ad.bitmap[key >> 5] >> (key & 31u)) & 1u;
-  if (!member) return;
-  const uint32_t abs = lo_al + unit * 16u + w + 9u;  // byte on which the window ends
+  if (!member) return false;
   uint32_t r, pos, len;
-  if (ulen) {  // reads of one length, back to back: divide instead of searching
-    const uint32_t d = abs - lds_u32(soff_s);
-    if ((int32_t)d < 0) return;
-    // d < 2^16 and (d + 0.5) / len is never closer than 1/(2 len) to an integer: the float quotient is exact
-    r = (uint32_t)(((float)d + 0.5f) * __frcp_rn((float)ulen));
-    pos = d - r * ulen;
-    len = ulen;
-    if (r >= nr) return;
-  } else {
-    const uint32_t *soff = shared_ptr<const uint32_t>(soff_s);
-    const int rr = find_read(soff, nr, abs);
-    if (rr < 0) return;
-    r = (uint32_t)rr;
-    pos = abs - soff[r];
-    len = soff[32 + r];
+  if (!w_locate(tm, lo_al + unit * 16u + w + 9u, r, pos, len)) return false;  // byte on which the window ends
+  if (pos < 9u || pos + 1u >= len) return false;  // the window spans two reads, or ends on the last base
+  atomicMin(shared_ptr<uint32_t>(fhit_s) + r, pos);
+  return pos + 16u < len;
+}
+
+// ------------------------------------------------------------------------------------------
+// first pass: one descriptor per tile of R reads
+//   x = first byte of the tile (offset of its first read)
+//   y = reads (6 bits) | common read length if the reads all have one length and lie back to back, else 0
+//       (10 bits) | bytes from the first byte of the first read to the last byte of the last (16 bits)
+// A tile that breaks the batch contract (offsets not ascending, reads overlapping, span beyond the staged
+// buffer) gets an empty descriptor and raises the error counter: never corrupt silently.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tile_desc_kernel(BatchView b, Accum a, uint32_t R, uint32_t tile_bytes, uint32_t n_tiles) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (tile >= n_tiles) return;
+  constexpr uint32_t kFull = 0xffffffffu;
+  const uint32_t r0 = tile * R;
+  uint32_t nr = min(R, b.n_reads - r0);
+  uint32_t off = 0, len = 0;
+  if (lane < nr) {
+    off = __ldg(b.offset + r0 + lane);
+    len = __ldg(b.length + r0 + lane);
   }
-  if (pos >= 9u && pos + 1u < len) atomicMin(shared_ptr<uint32_t>(fhit_s) + r, pos);  // whole window inside the read
+  const uint32_t end = off + len;
+  const uint32_t lo = __shfl_sync(kFull, off, 0);
+  const uint32_t hi = __shfl_sync(kFull, end, nr - 1u);
+  const uint32_t prev_end = __shfl_up_sync(kFull, end, 1);
+  const uint32_t len0 = __shfl_sync(kFull, len, 0);
+  const bool mine = lane < nr;
+  const bool ok = !mine || (end >= off && (lane == 0 || off >= prev_end) && len <= a.len_cap);
+  const bool back_to_back = !mine || (len == len0 && (lane == 0 || off == prev_end));
+  const uint32_t span = (hi - (lo & ~15u) + 15u) & ~15u;
+  const bool valid = __all_sync(kFull, ok) && hi >= lo && span <= tile_bytes && hi - lo < 65536u;
+  uint32_t ulen = __all_sync(kFull, back_to_back) ? len0 : 0u;
+  if (ulen > 1023u) ulen = 0;
+  if (lane == 0) {
+    if (!valid) atomicAdd(&a.counters[kCntError], 1ull);
+    b.tiles[tile] = valid ? make_uint2(lo, nr | (ulen << 6) | ((hi - lo) << 16)) : make_uint2(0u, 0u);
+  }
 }
 
 template <bool kAdapters, int kSets>
@@ -280,7 +380,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
   __syncthreads();
 
   const uint32_t R = P.reads_per_tile;
-  const uint32_t n_reads = args.b.n_reads, n_tiles = args.n_tiles;
+  const uint32_t n_tiles = args.n_tiles;
   const uint32_t G = gridDim.x * kWW;
   const uint32_t g0 = blockIdx.x * kWW;
   const uint32_t iters = n_tiles > g0 ? (n_tiles - g0 + G - 1u) / G : 0u;  // the same for every warp of the CTA
@@ -301,6 +401,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
   const uint32_t exact_s = P.exact_s;
   const uint32_t fhit_s = wb_s + kWoFhit, q_s = wb_s + kWoQueue;
   const uint32_t lenhist_s = P.lenhist_s, kmerhist_s = P.kmerhist_s;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   unsigned long long n_invalid = 0;
 
   auto flush = [&]() {  // all warps are behind a barrier
@@ -362,51 +463,20 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
     }
   };
 
-  // offsets / lengths of a tile, lane <-> read (zero for lanes without a read)
-  auto load_idx = [&](uint32_t tile, uint32_t &off, uint32_t &len) {
-    off = 0;
-    len = 0;
-    if (tile < n_tiles && lane < R) {
-      const uint32_t r = tile * R + lane;
-      if (r < n_reads) {
-        off = __ldg(args.b.offset + r);
-        len = __ldg(args.b.length + r);
-      }
-    }
-  };
-  // describe tile `tile` (its reads' offsets / lengths in off / len), stash the description in stage s of the
-  // warp block and start the bulk copies of its bytes.  The whole warp calls this; tile < n_tiles.
-  auto issue = [&](uint32_t tile, uint32_t s, uint32_t off, uint32_t len) {
-    uint32_t nr = min(R, n_reads - tile * R);
-    const uint32_t end = off + len;
-    const uint32_t lo = __shfl_sync(kFull, off, 0);
-    const uint32_t hi = __shfl_sync(kFull, end, nr - 1u);
-    const uint32_t prev_end = __shfl_up_sync(kFull, end, 1);
-    const uint32_t len0 = __shfl_sync(kFull, len, 0);
-    const uint32_t lo_al = lo & ~15u;
-    uint32_t span = (hi - lo_al + 15u) & ~15u;
-    // reads in ascending order without overlap (the batch contract): every read lies inside [lo, hi)
-    const bool mine = lane < nr;
-    const bool ok = !mine || (end >= off && (lane == 0 || off >= prev_end));
-    const bool back_to_back = !mine || (len == len0 && (lane == 0 || off == prev_end));
-    const bool valid = __all_sync(kFull, ok) && hi >= lo && span <= P.tile_bytes;
-    const uint32_t ulen = __all_sync(kFull, back_to_back) ? len0 : 0u;
-    if (!valid) {  // capacity / layout violation: never corrupt silently
-      if (lane == 0) atomicAdd(&args.a.counters[kCntError], 1ull);
-      nr = 0;
-      span = 0;
-    }
-    const uint32_t hdr_s = wb_s + kWoStage + s * kWStageHdr;
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(hdr_s + 16u + lane * 4u), "r"(off) : "memory");
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(hdr_s + 144u + lane * 4u), "r"(len) : "memory");
-    if (lane == 0) sts_u128(hdr_s, make_uint4(lo_al, nr, span, ulen));
+  // Start the bulk copies of a tile (descriptor d) into stage s and stash the descriptor in the stage header.
+  // The whole warp calls this once it is done with the stage's previous tile.
+  auto issue = [&](uint32_t s, uint2 d) {
     __syncwarp();  // every lane is done with the stage's old contents
     if (lane == 0) {
+      const uint32_t lo_al = d.x & ~15u;
+      const uint32_t span = ((d.x & 15u) + (d.y >> 16) + 15u) & ~15u;
+      sts_u64(wb_s + kWoStage + s * kWStageHdr, d.x, d.y);
       // the TMA (async proxy) write must be ordered behind the generic-proxy key-byte writes into the buffer
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       uint64_t *bar = reinterpret_cast<uint64_t *>(gen(wb_s + kWoBar + 8u * s));
-      mbar_arrive_expect_tx(bar, 2u * span);
-      if (span) {
+      const bool any = (d.y & 63u) != 0u && span != 0u;
+      mbar_arrive_expect_tx(bar, any ? 2u * span : 0u);
+      if (any) {
         bulk_g2s(gen(stage_s0 + 2u * s * buf), args.b.seq + lo_al, span, bar);
         bulk_g2s(gen(stage_s0 + (2u * s + 1u) * buf), args.b.qual + lo_al, span, bar);
       }
@@ -414,34 +484,46 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
   };
 
   const uint32_t g = g0 + warp;
-  {
-    uint32_t off, len;
-    for (uint32_t k = 0; k < 2u; k++) {
-      const uint32_t tile = g + k * G;
-      if (k < iters && tile < n_tiles) {
-        load_idx(tile, off, len);
-        issue(tile, k, off, len);
-      }
-    }
+  const uint2 *tiles = args.b.tiles;
+  for (uint32_t k = 0; k < 2u; k++) {
+    const uint32_t tile = g + k * G;
+    if (tile < n_tiles) issue(k, __ldg(tiles + tile));
   }
 
-  for (uint32_t it = 0; it < iters; ++it) {
-    const uint32_t tile = g + it * G;
+  uint32_t to_flush = epoch;
+  uint32_t tile = g;
+  for (uint32_t it = 0; it < iters; ++it, tile += G) {
     if (tile < n_tiles) {
       const uint32_t s = it & 1u;
-      // offsets / lengths of the tile after the next one: in flight while this tile is processed
+      // descriptor of the tile after the next one: in flight while this tile is processed
       const bool more = n_tiles - tile > 2u * G;
-      uint32_t off2 = 0, len2 = 0;
-      if (more) load_idx(tile + 2u * G, off2, len2);
+      uint2 d2 = make_uint2(0u, 0u);
+      if (more) d2 = __ldg(tiles + tile + 2u * G);
 
-      mbar_wait(wb_s + kWoBar + 8u * s, (it >> 1) & 1u);
       const uint32_t hdr_s = wb_s + kWoStage + s * kWStageHdr;
-      const uint4 mt = lds_u128(hdr_s);
-      const uint32_t lo_al = mt.x, nr = mt.y, span = mt.z, ulen = mt.w;
+      mbar_wait(wb_s + kWoBar + 8u * s, (it >> 1) & 1u);
+      const uint2 mt = lds_u64(hdr_s);
+      const uint32_t lo = mt.x, nr = mt.y & 63u, ulen = (mt.y >> 6) & 1023u;
+      const uint32_t lo_al = lo & ~15u;
+      const uint32_t n16 = ((lo & 15u) + (mt.y >> 16) + 15u) >> 4;  // 16-byte units of the tile
       const uint32_t soff_s = hdr_s + 16u, slen_s = hdr_s + 144u;
       const uint32_t seq_s = stage_s0 + 2u * s * buf;
       const uint32_t key_s = seq_s + buf;  // phase A overwrites the quality bytes with the key bytes
-      const uint32_t n16 = span >> 4;
+      const WTileMap tm{lo, ulen, nr, soff_s};
+
+      if (!ulen && nr) {  // ragged tile: stage its offsets / lengths, lane <-> read (zero for lanes without a read)
+        uint32_t off = 0, len = 0;
+        if (lane < nr) {
+          off = __ldg(args.b.offset + tile * R + lane);
+          len = __ldg(args.b.length + tile * R + lane);
+        }
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(soff_s + lane * 4u), "r"(off) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(slen_s + lane * 4u), "r"(len) : "memory");
+        if (len) red_shared_add<0>(lenhist_s + (len - 1u) * 4u, 1u);  // quack.c:219 (len <= len_cap: checked by the first pass)
+        __syncwarp();
+      } else if (ulen && lane == 0) {
+        red_shared_add<0>(lenhist_s + (ulen - 1u) * 4u, nr);
+      }
 
       // ---------------- phase A: flat over the tile, key bytes written in place of the quality bytes ----------------
       uint32_t qn = 0;  // queued anchor hits
@@ -456,7 +538,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
           K.z = key_bytes(sv.z, qv.z, kc, n2, bad);
           K.w = key_bytes(sv.w, qv.w, kc, n3, bad);
           if (bad & 0xC0C0C0C0u)  // rare: re-key the offending words to the dummy rows, count them exactly
-            n_invalid += w_fix_bad_unit(sv, qv, K, n0, n1, n2, n3, qsub, lo_al + u * 16u, soff_s, nr, args.a);
+            n_invalid += w_fix_bad_unit(sv, qv, K, n0, n1, n2, n3, qsub, lo_al + u * 16u, tm, args.a);
           sts_u128(a + buf, K);
         }
       } else {
@@ -479,7 +561,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
           const uint32_t nx = __shfl_down_sync(kFull, p, 1);
           if (own) {
             if (bad & 0xC0C0C0C0u)
-              n_invalid += w_fix_bad_unit(sv, qv, K, n0, n1, n2, n3, qsub, lo_al + u * 16u, soff_s, nr, args.a);
+              n_invalid += w_fix_bad_unit(sv, qv, K, n0, n1, n2, n3, qsub, lo_al + u * 16u, tm, args.a);
             sts_u128(a + buf, K);
           }
           // anchor j = the 7-mer starting at base 4j+3: row = its bits 13:5 (32-byte rows), bit = its bits 4:0
@@ -489,14 +571,15 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
           const uint32_t w1 = lds_u32_at(lop3<0xEA>(e1, 0x3FE0u, afilt_copy), afilt_s);
           const uint32_t w2 = lds_u32_at(lop3<0xEA>(e2, 0x3FE0u, afilt_copy), afilt_s);
           const uint32_t w3 = lds_u32_at(lop3<0xEA>(e3, 0x3FE0u, afilt_copy), afilt_s);
-          // bit j of m = anchor j passed
-          uint32_t m = (__funnelshift_r(w0, 0u, e0) & 1u) | ((__funnelshift_r(w1, 0u, e1) & 1u) << 1) |
-                       ((__funnelshift_r(w2, 0u, e2) & 1u) << 2) | ((__funnelshift_r(w3, 0u, e3) & 1u) << 3);
-          if (!own) m = 0;
-          const uint32_t bal = __ballot_sync(kFull, m != 0u);
+          // bit 0 of m_j = anchor j passed (shift amounts wrap at 32)
+          const uint32_t m0 = __funnelshift_r(w0, 0u, e0), m1 = __funnelshift_r(w1, 0u, e1);
+          const uint32_t m2 = __funnelshift_r(w2, 0u, e2), m3 = __funnelshift_r(w3, 0u, e3);
+          const bool hit = own && ((m0 | m1 | m2 | m3) & 1u);
+          const uint32_t bal = __ballot_sync(kFull, hit);
           if (bal) {  // one queue entry per unit with a hit: 25 bases, anchor mask, unit
-            if (m) {
-              const uint32_t idx = qn + __popc(bal & ((1u << lane) - 1u));
+            if (hit) {
+              const uint32_t idx = qn + __popc(bal & lt_mask);
+              const uint32_t m = (m0 & 1u) | ((m1 & 1u) << 1) | ((m2 & 1u) << 2) | ((m3 & 1u) << 3);
               if (idx < kWQueue) sts_u64(q_s + idx * 8u, p, (nx & 0x3FFFFu) | (m << 18) | (u << 22));
             }
             qn += __popc(bal);
@@ -505,37 +588,38 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
       }
       __syncwarp();  // key bytes and the candidate queue of this tile are complete
 
-      // ---------------- per-read counters, one lane per read (quack.c:219) ----------------
-      if (lane < nr) {
-        const uint32_t len = lds_u32(slen_s + lane * 4u);
-        if (len > len_cap)
-          atomicAdd(&args.a.counters[kCntError], 1ull);
-        else if (len)
-          red_shared_add<0>(lenhist_s + (len - 1u) * 4u, 1u);
-      }
-
       // ---------------- phase A2: confirm the queued anchor hits (quack.c:210-217) ----------------
       if (kAdapters && qn) {
         if (qn <= kWQueue) {
-          for (uint32_t i = lane; i < qn * 4u; i += 32u) {  // one (entry, window offset) pair per lane
-            const uint2 c = lds_u64(q_s + (i >> 2) * 8u);
+          // 8 entries per pass: a quad of lanes per entry, lane t of the quad tests the windows 4j + t of the
+          // entry's anchors j in ascending order; the quad stops at the first recorded hit whose read also
+          // holds the rest of the unit (no later window can then be that read's first hit)
+          for (uint32_t e0 = 0; e0 < qn; e0 += 8u) {
+            const uint32_t e = e0 + (lane >> 2);
+            uint2 c = make_uint2(0u, 0u);
+            if (e < qn) c = lds_u64(q_s + e * 8u);
             uint32_t m = (c.y >> 18) & 15u;
-            while (m) {  // anchor j starts at base 4j+3 of its unit; the windows that contain it start at 4j .. 4j+3
-              const uint32_t j = __ffs(m) - 1u;
-              m &= m - 1u;
-              w_confirm(c.x, c.y & 0x3FFFFu, c.y >> 22, 4u * j + (i & 3u), args.ad, exact_s, lo_al, soff_s, nr, ulen, fhit_s);
+            while (__any_sync(kFull, m != 0u)) {
+              bool stop = false;
+              if (m) {  // anchor j starts at base 4j+3 of its unit; the windows that contain it start at 4j .. 4j+3
+                const uint32_t j = __ffs(m) - 1u;
+                m &= m - 1u;
+                stop = w_confirm(c.x, c.y & 0x3FFFFu, c.y >> 22, 4u * j + (lane & 3u), args.ad, exact_s, lo_al, tm, fhit_s);
+              }
+              const uint32_t stops = __ballot_sync(kFull, stop);
+              if ((stops >> (lane & 28u)) & 15u) m = 0;
             }
           }
         } else {  // queue overflow (adapter-dimer-like data): test every window of the tile exactly
           for (uint32_t i = lane; i < n16 * 4u; i += 32u) {
             const uint32_t unit = i >> 2, t = i & 3u;
             const uint4 ka = lds_u128(key_s + unit * 16u), kb = lds_u128(key_s + unit * 16u + 16u);
-            const uint32_t lo = pack16_keys(ka), hi = pack16_keys(kb);
-            for (uint32_t j = 0; j < 4u; j++) w_confirm(lo, hi, unit, 4u * j + t, args.ad, exact_s, lo_al, soff_s, nr, ulen, fhit_s);
+            const uint32_t klo = pack16_keys(ka), khi = pack16_keys(kb);
+            for (uint32_t j = 0; j < 4u; j++) w_confirm(klo, khi, unit, 4u * j + t, args.ad, exact_s, lo_al, tm, fhit_s);
           }
         }
         __syncwarp();
-        // first hit of a read -> adapter histogram (quack.c:215-217: counted at p + 1, only if that is inside the read)
+        // first hit of a read -> adapter histogram (quack.c:215-217: counted at p + 1, which is inside the read)
         const uint32_t fa = fhit_s + lane * 4u;
         const uint32_t pfirst = lds_u32(fa);
         if (pfirst != kNoHit) {
@@ -550,21 +634,18 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
 #define QB_WSHAPES(FN) FN(0, 1) FN(1, 0) FN(1, 1) FN(1, 2) FN(1, 3) FN(2, 0) FN(2, 2) FN(2, 3)
 #define QB_WVALID(nf, kind) ((nf) <= kSets && ((kind) == 0 || ((kind) == 1 ? (nf) < kSets : (nf) == kSets)))
         if (ulen) {
-          if (ulen <= len_cap && nr) {
-            const uint32_t kb = k0_s + lds_u32(soff_s);
-            switch (w_shape<kSets>(ulen)) {
-#define QB_WCASE(nf, kind)                                                                       \
-  case (nf)*4 + (kind):                                                                          \
-    if constexpr (QB_WVALID(nf, kind)) w_uniform<kSets, nf, kind>(hc, tl, kb, ulen, nr, lane);   \
+          switch (w_shape<kSets>(ulen)) {
+#define QB_WCASE(nf, kind)                                                                          \
+  case (nf)*4 + (kind):                                                                             \
+    if constexpr (QB_WVALID(nf, kind)) w_uniform<kSets, nf, kind>(hc, tl, k0_s + lo, ulen, nr, lane); \
     break;
-              QB_WSHAPES(QB_WCASE)
+            QB_WSHAPES(QB_WCASE)
 #undef QB_WCASE
-            }
           }
         } else {
           for (uint32_t r = 0; r < nr; r++) {
             const uint32_t len = lds_u32(slen_s + r * 4u);
-            if (len == 0 || len > len_cap) continue;  // reported in the bookkeeping pass above
+            if (len == 0) continue;
             const uint32_t kb = k0_s + lds_u32(soff_s + r * 4u);
             switch (w_shape<kSets>(len)) {
 #define QB_WCASE(nf, kind)                                                                  \
@@ -581,9 +662,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
       }
 
       // the stage is free: refill it with the tile after the next one
-      if (more) issue(tile + 2u * G, s, off2, len2);
+      if (more) issue(s, d2);
     }
-    if ((it + 1u) % epoch == 0u && it + 1u < iters) {  // u16 counters: flush before any bin can wrap
+    if (--to_flush == 0u && it + 1u < iters) {  // u16 counters: flush before any bin can wrap
+      to_flush = epoch;
       __syncthreads();
       flush();
       __syncthreads();
@@ -695,6 +777,8 @@ cudaError_t launch_wtile(const BatchView &b, const Accum &a, const AdapterSet &a
   args.ad = ad;
   args.plan = plan;
   args.n_tiles = (b.n_reads + plan.reads_per_tile - 1u) / plan.reads_per_tile;
+  if (!b.tiles) return cudaErrorInvalidValue;
+  tile_desc_kernel<<<(args.n_tiles + 7u) / 8u, 256, 0, stream>>>(b, a, plan.reads_per_tile, plan.tile_bytes, args.n_tiles);
   uint32_t grid = (args.n_tiles + (uint32_t)kWW - 1u) / (uint32_t)kWW;
   if (grid > plan.grid) grid = plan.grid;
   if (const char *g = getenv("QB_FUSED_GRID")) {  // test hook: few CTAs exercise the u16 flush path
