@@ -50,10 +50,10 @@ typedef enum {
 } qb_status;
 
 typedef enum {
-  QB_KERNEL_AUTO = 0,      /* warp-tile kernel when the batch's longest read fits its shared-memory histogram */
+  QB_KERNEL_AUTO = 0,      /* warp-tile kernel for batches of reads <= 192 bp, fused kernel up to 320 bp, else simple */
   QB_KERNEL_SIMPLE = 1,    /* one warp per read, global atomics: any len_cap, slow */
   QB_KERNEL_FUSED = 2,     /* CTA-wide TMA-staged tiles, joint (base,score) shared-memory histogram (v3) */
-  QB_KERNEL_WTILE = 3      /* autonomous warps, each with its own TMA-staged tile ring (v4, the default) */
+  QB_KERNEL_WTILE = 3      /* autonomous warps, each with its own TMA-staged tile ring (v4; reads <= 192 bp) */
 } qb_kernel;
 
 typedef struct qb_ctx qb_ctx;       /* one per process; owns devices, streams, accumulators */

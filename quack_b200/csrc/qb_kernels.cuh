@@ -88,7 +88,6 @@ constexpr int kFusedConsumerWarps = QB_CW;  // + 1 producer warp = 512 threads (
 constexpr int kWtileWarps = QB_WW;  // autonomous warps per CTA (one CTA per SM)
 
 struct WtilePlan {
-  uint32_t nsets;            // histogram sets of 128 positions (1: reads <= 192 bp, 2: <= 320 bp), + 64 tail positions
   uint32_t reads_per_tile;   // R <= 32 whole reads per warp tile
   uint32_t tile_bytes;       // capacity of one staged byte buffer (seq or qual), multiple of 16
   uint32_t buf;              // tile_bytes + pad
@@ -96,7 +95,7 @@ struct WtilePlan {
   uint32_t smem_base;        // shared address the dynamic shared memory must start at (checked by the kernel)
   uint32_t smem_bytes;
   uint32_t tail_s, afilt_s, exact_s, lenhist_s, kmerhist_s;  // shared addresses of the CTA-wide arrays
-  uint32_t region_s[3], region_n[3];                         // warp blocks: region_n[i] blocks from region_s[i]
+  uint32_t region_s[2], region_n[2];                         // warp blocks: region_n[i] blocks from region_s[i]
   uint32_t qbase;            // score field s = q - qbase
   uint32_t grid;
   int ok;                    // 0: the batch does not fit -> another kernel

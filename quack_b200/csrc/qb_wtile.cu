@@ -1,9 +1,9 @@
 // qb_wtile.cu -- warp-tile kernel (v4) for quack's per-read statistics accumulation
-// (reference: the while loop of read_fastq(), quack.c:193-221).
+// (reference: the while loop of read_fastq(), quack.c:193-221).  Reads of up to 192 bp.
 //
-// Same arithmetic as fused_kernel (qb_kernels.cu) -- SWAR key bytes, joint (score, code) x position
-// histogram of packed u16 counters in shared memory, 7-mer anchor filter + exact confirmation for -a --
-// but organised around AUTONOMOUS WARPS instead of a CTA-wide pipeline:
+// Same idea as fused_kernel (qb_kernels.cu) -- SWAR key bytes, joint (code, score) x position histogram of
+// packed u16 counters in shared memory, 7-mer anchor filter + exact confirmation for -a -- but organised
+// around AUTONOMOUS WARPS instead of a CTA-wide pipeline:
 //   * every warp owns a private 2-stage ring of small tiles (R whole reads, ~1-4 KB of seq + of qual).
 //     The warp itself issues the 1-D TMA bulk copies of its tile t+2 when it is done with tile t and then
 //     waits on the mbarrier of tile t+1: no producer warp, no polling, no CTA barrier in the steady state.
@@ -13,11 +13,12 @@
 //     8-byte tile descriptor (first byte, read count, common read length or 0, byte count); the hot kernel
 //     reads one descriptor per tile, one tile ahead, and never touches offsets / lengths of tiles whose reads
 //     all have one length and lie back to back (the normal case);
+//   * key byte K = code << 6 | (q - qbase): 256 histogram rows of 256 bytes at a 64 KiB-aligned shared
+//     address, so ONE byte permute builds the address of a base's counter from its key byte (2 instructions
+//     per base in phase H: PRMT + RED), every byte value is a valid row, and a quality byte is inside the
+//     counted window iff bits 7:6 of q - qbase are clear (one OR per word in phase A);
 //   * candidate queue positions come from a ballot + popc instead of shared atomics, queue entries are one
-//     per 16-byte unit (4-bit anchor mask);
-//   * histogram rows are 256 bytes at a 64 KiB-aligned shared address, so ONE byte permute builds the
-//     address of a base's counter from its key byte (row = key): 2 instructions per base in phase H
-//     (PRMT + RED) instead of 3.
+//     per 16-byte unit (4-bit anchor mask), confirmed by quads of lanes that stop at the first hit.
 // The CTA synchronises only in the prologue, at the final flush and every 65535 reads (u16 counters).
 //
 // No tensor cores: the path is an integer histogram.
@@ -33,14 +34,18 @@ constexpr int kWW = kWtileWarps;                 // warps per CTA, one CTA per S
 constexpr int kWThreads = kWW * 32;
 constexpr uint32_t kWQueue = 64;                 // anchor-hit entries per tile (one per 16-byte unit)
 constexpr uint32_t kWPad = 32;                   // readable bytes behind a staged buffer (look-ahead unit + word)
-constexpr uint32_t kMainBase = 0x10000u;         // shared address of histogram set 0 (set s at (s + 1) << 16)
-constexpr uint32_t kMainBytes = kHistRows * 256u;  // 48 KiB: 192 rows of 64 u32 = 128 positions x u16
-constexpr uint32_t kTailRow = 128u;              // tail histogram: 192 rows of 32 u32 = 64 positions x u16
-constexpr uint32_t kTailBytes = kHistRows * kTailRow;
+constexpr uint32_t kWRows = 256;                 // histogram rows: key byte = code << 6 | score
+constexpr uint32_t kWScores = 64;                // score field s = q - qbase in [0, 64)
+constexpr uint32_t kMainBase = 0x10000u;         // shared address of the main histogram (positions 0..127)
+constexpr uint32_t kMainBytes = kWRows * 256u;   // 64 KiB: rows of 64 u32 = 128 positions x u16
+constexpr uint32_t kTail0 = 128u;                // first position of the tail histogram
+constexpr uint32_t kTailRow = 128u;              // tail histogram (positions 128..191): rows of 32 u32 = 64 positions x u16
+constexpr uint32_t kTailBytes = kWRows * kTailRow;
+constexpr uint32_t kWMaxLen = kTail0 + 64u;      // longest read the histograms hold
 
 // offsets inside a warp block (all multiples of 16)
 constexpr uint32_t kWoBar = 0;                   // 2 mbarriers
-constexpr uint32_t kWoStage = 16;                // per stage: meta uint4, soff[32], slen[32]
+constexpr uint32_t kWoStage = 16;                // per stage: descriptor (16 B), soff[32], slen[32]
 constexpr uint32_t kWStageHdr = 16 + 128 + 128;
 constexpr uint32_t kWoFhit = kWoStage + 2 * kWStageHdr;  // first-hit position per read of the tile (-a)
 constexpr uint32_t kWoQueue = kWoFhit + 128;
@@ -54,147 +59,154 @@ struct WArgs {
   uint32_t n_tiles;
 };
 
+// ---- phase A arithmetic ----
+// loop-invariant SWAR constants
+struct WKeyConsts {
+  uint32_t m5b, x43, m1f, x07, x14, a7f, a3f, m80, c0, qsub;
+  __device__ __forceinline__ explicit WKeyConsts(uint32_t qbase)
+      : m5b(0x5B5B5B5Bu), x43(0x43434343u), m1f(0x1F1F1F1Fu), x07(0x07070707u), x14(0x14141414u), a7f(0x7F7F7F7Fu),
+        a3f(0x3F3F3F3Fu), m80(0x80808080u), c0(0xC0C0C0C0u), qsub(qbase * 0x01010101u) {}
+};
+// One aligned word of 4 bases + 4 quality bytes -> 4 key bytes K = code << 6 | s, code = A0 T1 C2 G3
+// (quack.c:150; N and everything else 0), s = q - qbase.  `nc` gets the inverted codes in bits 7:6 of each
+// byte (other bits undefined), `qs` the 4 score bytes: a word whose qs has a bit 7 or 6 set holds a quality
+// byte outside [qbase, qbase + 64) (a borrow can only start at a byte that is itself out of range) and is
+// re-keyed by the caller.
+__device__ __forceinline__ uint32_t w_key_bytes(uint32_t sw, uint32_t qw, const WKeyConsts &c, uint32_t &nc, uint32_t &qs) {
+  // per byte: bit7 of n_cg is 0 iff (b & 0x5B) == 0x43; bit6 of n_g / n_t is 0 iff (b & 0x1F) == 7 / 0x14
+  const uint32_t n_cg = lop3<0x6A>(sw, c.m5b, c.x43) + c.a7f;
+  const uint32_t n_g = lop3<0x6A>(sw, c.m1f, c.x07) + c.a3f;
+  const uint32_t n_t = lop3<0x6A>(sw, c.m1f, c.x14) + c.a3f;
+  nc = lop3<0xE4>(n_cg, n_g & n_t, c.m80);  // bit 7 from n_cg, the rest from n_g & n_t
+  qs = qw - c.qsub;
+  return lop3<0xCE>(nc, qs, c.c0);  // (~nc & 0xC0C0C0C0) | qs
+}
+// key bytes of a word with an out-of-window quality byte: code kept, s = 63 (compensated by w_exact_word)
+__device__ __forceinline__ uint32_t w_key_bytes_bad(uint32_t nc) { return (~nc & 0xC0C0C0C0u) | 0x3F3F3F3Fu; }
+__device__ __forceinline__ bool w_word_bad(uint32_t qw, uint32_t qsub) { return ((qw - qsub) & 0xC0C0C0C0u) != 0u; }
+
 // ---- phase H building blocks ----
-// Position p < 128 * kSets lives in set p >> 7; inside a set, position 4 l + t sits in u32 column
-// l + 32 (t >> 1), half-word t & 1: the t-th atomic of a word step (lane l <-> positions 4 l .. 4 l + 3)
-// touches bank l in every lane.  Positions behind the sets live in the tail histogram, position
-// 128 kSets + q in column q & 31, half-word q >> 5 (byte steps, lane <-> position).
-// per-lane constants of phase H: c = (shared address of set 0) | lane << 2; lo / hi = the increments of the
-// low and the high u16 of a counter word, kept in registers so that the atomics are plain ATOMS.ADD (with
-// immediates the compiler emits the warp-aggregating ATOMS.POPC.INC form instead)
+// Position 4 l + t < 128 sits in u32 column l + 32 (t >> 1), half-word t & 1 of its row: the t-th atomic of
+// a word step (lane l <-> positions 4 l .. 4 l + 3) touches bank l in every lane.  Position 128 + q lives in
+// the tail histogram, column q & 31, half-word q >> 5 (byte steps, lane <-> position).
+//
+// per-lane constants: c = (shared address of the main histogram) | lane << 2; lo / hi = the increments of
+// the low and the high u16 of a counter word, kept in registers so that the atomics are plain ATOMS.ADD
+// (with immediates the compiler emits the warp-aggregating ATOMS.POPC.INC form instead)
 struct WInc {
   uint32_t c, lo, hi;
 };
-template <uint32_t kOff>
 __device__ __forceinline__ void w_red_word(uint32_t k4, WInc c, uint32_t i0, uint32_t i1, uint32_t i2, uint32_t i3) {
-  // address = c with byte 1 replaced by the key byte: (set base) | key << 8 | lane << 2
-  red_shared_add<kOff>(__byte_perm(k4, c.c, 0x7604), i0);
-  red_shared_add<kOff>(__byte_perm(k4, c.c, 0x7614), i1);
-  red_shared_add<kOff + 0x80u>(__byte_perm(k4, c.c, 0x7624), i2);
-  red_shared_add<kOff + 0x80u>(__byte_perm(k4, c.c, 0x7634), i3);
+  // address = c with byte 1 replaced by the key byte: base | key << 8 | lane << 2
+  red_shared_add<0u>(__byte_perm(k4, c.c, 0x7604), i0);
+  red_shared_add<0u>(__byte_perm(k4, c.c, 0x7614), i1);
+  red_shared_add<0x80u>(__byte_perm(k4, c.c, 0x7624), i2);
+  red_shared_add<0x80u>(__byte_perm(k4, c.c, 0x7634), i3);
 }
 // the 4 key bytes of positions 4 lane .. + 3 of a word step whose lane-th word starts at kw (any alignment)
 __device__ __forceinline__ uint32_t w_load_word(uint32_t kw) {
   const uint32_t al = kw & ~3u;
-  const uint32_t w0 = lds_u32(al), w1 = lds_u32(al + 4u);
-  return __funnelshift_r(w0, w1, kw << 3);
+  return __funnelshift_r(lds_u32(al), lds_u32(al + 4u), kw << 3);
 }
 
-// shape of a read of length L for kSets main sets: NF full word steps, then
-//   KIND 0 nothing, 1 a partial word step in set NF (NF < kSets), 2 one tail byte step, 3 two tail byte steps
-template <int kSets>
+// shape of a read of length L: 0 nothing; 1 a partial word step (L < 128); 2 a full word step (L == 128);
+// 3 / 4 a full word step and one / two tail byte steps
 __device__ __forceinline__ uint32_t w_shape(uint32_t L) {
-  const uint32_t nf = min(L >> 7, (uint32_t)kSets);
-  const uint32_t rem = L - 128u * nf;
-  uint32_t kind = 0;
-  if (rem) kind = nf < (uint32_t)kSets ? 1u : (rem <= 32u ? 2u : 3u);
-  return nf * 4u + kind;
+  if (L < 128u) return L ? 1u : 0u;
+  return L == 128u ? 2u : (L <= 160u ? 3u : 4u);
 }
 
-template <int kSets, int NF, int KIND>
+template <int SHAPE>
 struct WRead {
-  static constexpr int kWords = NF + (KIND == 1 ? 1 : 0);
-  uint32_t k4[kWords > 0 ? kWords : 1];
-  uint32_t kb0, kb1;
+  uint32_t k4, b0, b1;
   // `part`: this lane has a position in the partial word step (the others must not load: they would read up
   // to 130 bytes behind the read's end)
   __device__ __forceinline__ void load(uint32_t kb, uint32_t lane, bool part) {
-#pragma unroll
-    for (int s = 0; s < NF; s++) k4[s] = w_load_word(kb + 128u * s + 4u * lane);
-    if constexpr (KIND == 1) {
-      k4[NF] = 0;
-      if (part) k4[NF] = w_load_word(kb + 128u * NF + 4u * lane);
-    }
-    if constexpr (KIND >= 2) kb0 = lds_u8(kb + 128u * kSets + lane);
-    if constexpr (KIND == 3) kb1 = lds_u8(kb + 128u * kSets + 32u + lane);
+    k4 = 0;
+    if (SHAPE >= 2 || part) k4 = w_load_word(kb + 4u * lane);
+    if constexpr (SHAPE >= 3) b0 = lds_u8(kb + kTail0 + lane);
+    if constexpr (SHAPE == 4) b1 = lds_u8(kb + kTail0 + 32u + lane);
   }
-  // pinc: increments of the partial word step; t0 / t1: increments of the tail byte steps; tl: tail column address
+  // pinc: increments of the word step; t0 / t1: increments of the tail byte steps; tl: tail column address
   __device__ __forceinline__ void red(WInc c, const uint32_t (&pinc)[4], uint32_t tl, uint32_t t0, uint32_t t1) const {
-    if constexpr (NF >= 1) w_red_word<0u>(k4[0], c, c.lo, c.hi, c.lo, c.hi);
-    if constexpr (NF >= 2) w_red_word<0x10000u>(k4[1], c, c.lo, c.hi, c.lo, c.hi);
-    if constexpr (KIND == 1 && NF == 0) w_red_word<0u>(k4[0], c, pinc[0], pinc[1], pinc[2], pinc[3]);
-    if constexpr (KIND == 1 && NF == 1) w_red_word<0x10000u>(k4[1], c, pinc[0], pinc[1], pinc[2], pinc[3]);
-    if constexpr (KIND >= 2) red_shared_add<0>(kb0 * kTailRow + tl, t0);
-    if constexpr (KIND == 3) red_shared_add<0>(kb1 * kTailRow + tl, t1);
+    if constexpr (SHAPE == 1) w_red_word(k4, c, pinc[0], pinc[1], pinc[2], pinc[3]);
+    if constexpr (SHAPE >= 2) w_red_word(k4, c, c.lo, c.hi, c.lo, c.hi);
+    if constexpr (SHAPE >= 3) red_shared_add<0>(b0 * kTailRow + tl, t0);
+    if constexpr (SHAPE == 4) red_shared_add<0>(b1 * kTailRow + tl, t1);
   }
 };
 
-// increments of the last step(s) of a read of length L (lanes behind the read's end add 0 to whatever bin the
-// stray key byte selects: stage buffers only ever hold key bytes < kHistRows or zeroes behind a tile)
-template <int kSets, int NF, int KIND>
+// increments of the last step(s) of a read of length L (lanes behind the read's end add 0 to whatever row the
+// stray key byte selects: every byte value is a row of the histogram)
+template <int SHAPE>
 __device__ __forceinline__ void w_tail(uint32_t L, uint32_t lane, uint32_t (&pinc)[4], uint32_t &t0, uint32_t &t1) {
   pinc[0] = pinc[1] = pinc[2] = pinc[3] = 0;
   t0 = t1 = 0;
-  if (KIND == 1) {
-    const uint32_t p = 128u * NF + 4u * lane;
+  if (SHAPE == 1) {
+    const uint32_t p = 4u * lane;
     pinc[0] = p < L ? 1u : 0u;
     pinc[1] = p + 1u < L ? 0x10000u : 0u;
     pinc[2] = p + 2u < L ? 1u : 0u;
     pinc[3] = p + 3u < L ? 0x10000u : 0u;
   }
-  if (KIND >= 2) t0 = 128u * kSets + lane < L ? 1u : 0u;
-  if (KIND == 3) t1 = 128u * kSets + 32u + lane < L ? 0x10000u : 0u;
+  if (SHAPE >= 3) t0 = kTail0 + lane < L ? 1u : 0u;
+  if (SHAPE == 4) t1 = kTail0 + 32u + lane < L ? 0x10000u : 0u;
 }
 
 // nr reads of length L back to back from kb.  Four reads per iteration: 4 L is a multiple of 4, so the
 // byte alignment of read j of a group (the funnel-shift amount) is loop invariant and its aligned word
 // address just advances by 4 L -- two address instructions per read instead of six.
-template <int kSets, int NF, int KIND>
+template <int SHAPE>
 __device__ __forceinline__ void w_uniform(WInc c, uint32_t tl, uint32_t kb, uint32_t L, uint32_t nr, uint32_t lane) {
   uint32_t pinc[4], t0, t1;
-  w_tail<kSets, NF, KIND>(L, lane, pinc, t0, t1);
-  constexpr int kWords = NF + (KIND == 1 ? 1 : 0);
+  w_tail<SHAPE>(L, lane, pinc, t0, t1);
   uint32_t r = 0;
   if (nr >= 4u) {
     uint32_t al[4], sh[4], kt[4];
+    uint32_t kw = kb + 4u * lane, kq = kb + kTail0 + lane;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const uint32_t kw = kb + (uint32_t)j * L + 4u * lane;
       al[j] = kw & ~3u;
       sh[j] = kw << 3;
-      kt[j] = kb + (uint32_t)j * L + 128u * kSets + lane;
+      kt[j] = kq;
+      kw += L;
+      kq += L;
     }
     const uint32_t L4 = 4u * L;
+#pragma unroll 1
     for (; r + 4u <= nr; r += 4u) {
-      uint32_t k4[4][kWords > 0 ? kWords : 1], b0[4], b1[4];
+      uint32_t k4[4], b0[4], b1[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-#pragma unroll
-        for (int s = 0; s < NF; s++)
-          k4[j][s] = __funnelshift_r(lds_u32(al[j] + 128u * s), lds_u32(al[j] + 128u * s + 4u), sh[j]);
-        if constexpr (KIND == 1) {
-          k4[j][NF] = 0;
-          if (pinc[0]) k4[j][NF] = __funnelshift_r(lds_u32(al[j] + 128u * NF), lds_u32(al[j] + 128u * NF + 4u), sh[j]);
-        }
-        if constexpr (KIND >= 2) b0[j] = lds_u8(kt[j]);
-        if constexpr (KIND == 3) b1[j] = lds_u8(kt[j] + 32u);
+        k4[j] = 0;
+        if (SHAPE >= 2 || pinc[0]) k4[j] = __funnelshift_r(lds_u32(al[j]), lds_u32(al[j] + 4u), sh[j]);
+        if constexpr (SHAPE >= 3) b0[j] = lds_u8(kt[j]);
+        if constexpr (SHAPE == 4) b1[j] = lds_u8(kt[j] + 32u);
       }
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        if constexpr (NF >= 1) w_red_word<0u>(k4[j][0], c, c.lo, c.hi, c.lo, c.hi);
-        if constexpr (NF >= 2) w_red_word<0x10000u>(k4[j][1], c, c.lo, c.hi, c.lo, c.hi);
-        if constexpr (KIND == 1 && NF == 0) w_red_word<0u>(k4[j][0], c, pinc[0], pinc[1], pinc[2], pinc[3]);
-        if constexpr (KIND == 1 && NF == 1) w_red_word<0x10000u>(k4[j][1], c, pinc[0], pinc[1], pinc[2], pinc[3]);
-        if constexpr (KIND >= 2) red_shared_add<0>(b0[j] * kTailRow + tl, t0);
-        if constexpr (KIND == 3) red_shared_add<0>(b1[j] * kTailRow + tl, t1);
+        if constexpr (SHAPE == 1) w_red_word(k4[j], c, pinc[0], pinc[1], pinc[2], pinc[3]);
+        if constexpr (SHAPE >= 2) w_red_word(k4[j], c, c.lo, c.hi, c.lo, c.hi);
+        if constexpr (SHAPE >= 3) red_shared_add<0>(b0[j] * kTailRow + tl, t0);
+        if constexpr (SHAPE == 4) red_shared_add<0>(b1[j] * kTailRow + tl, t1);
         al[j] += L4;
-        if constexpr (KIND >= 2) kt[j] += L4;
+        if constexpr (SHAPE >= 3) kt[j] += L4;
       }
     }
     kb += r * L;
   }
   for (; r < nr; r++) {
-    WRead<kSets, NF, KIND> x;
+    WRead<SHAPE> x;
     x.load(kb, lane, pinc[0] != 0u);
     x.red(c, pinc, tl, t0, t1);
     kb += L;
   }
 }
-template <int kSets, int NF, int KIND>
+template <int SHAPE>
 __device__ __forceinline__ void w_one(WInc c, uint32_t tl, uint32_t kb, uint32_t L, uint32_t lane) {
   uint32_t pinc[4], t0, t1;
-  w_tail<kSets, NF, KIND>(L, lane, pinc, t0, t1);
-  WRead<kSets, NF, KIND> x;
+  w_tail<SHAPE>(L, lane, pinc, t0, t1);
+  WRead<SHAPE> x;
   x.load(kb, lane, pinc[0] != 0u);
   x.red(c, pinc, tl, t0, t1);
 }
@@ -224,32 +236,39 @@ __device__ __forceinline__ bool w_locate(const WTileMap &tm, uint32_t abs, uint3
   return pos < len;
 }
 
-// rare path of phase A: the 4 bases of a word with an out-of-window quality byte, counted one by one
-__device__ __noinline__ uint32_t w_exact_word(uint32_t sw, uint32_t qw, uint32_t abs0, const WTileMap tm, const Accum a) {
-  uint32_t n_invalid = 0;
+// Rare path of phase A: the 4 bases of a word with a quality byte outside the counted window.  The word is
+// re-keyed to s = 63, so phase H counts its bases (content is right) in score row 63; here every base that
+// lies inside a read gets its true score counted in the global accumulator and the row-63 count taken back
+// (u64 arithmetic wraps: the sums are exact once the CTA's flush has added its part).  Returns the change of
+// the invalid-quality count.
+__device__ __noinline__ int w_exact_word(uint32_t qw, uint32_t abs0, const WTileMap tm, const Accum a, uint32_t qbase) {
+  int d_invalid = 0;
+  const int sc63 = (int)(63u + qbase) - 33;
   for (uint32_t j = 0; j < 4; j++) {
     uint32_t r, p, len;
-    if (!w_locate(tm, abs0 + j, r, p, len)) continue;  // alignment slack
-    if (len > a.len_cap) continue;                      // a read the launch rejects anyway
+    if (!w_locate(tm, abs0 + j, r, p, len)) continue;  // alignment slack: phase H does not count it either
     unsigned long long *row = a.rows + (size_t)p * kRow;
-    atomicAdd(&row[kColContent + base_code((sw >> (8 * j)) & 0xFFu)], 1ull);
     const int sc = (int)((qw >> (8 * j)) & 0xFFu) - 33;
     if (sc >= 0 && sc < 91)
       atomicAdd(&row[sc], 1ull);
     else
-      n_invalid++;
+      d_invalid++;
+    if (sc63 >= 0 && sc63 < 91)
+      atomicAdd(&row[sc63], ~0ull);  // - 1
+    else
+      d_invalid--;
   }
-  return n_invalid;
+  return d_invalid;
 }
-// ... re-keying the words of a 16-byte unit whose quality bytes fall outside the window
-__device__ __noinline__ uint32_t w_fix_bad_unit(uint4 sv, uint4 qv, uint4 &K, uint32_t n0, uint32_t n1, uint32_t n2,
-                                                uint32_t n3, uint32_t qsub, uint32_t abs0, const WTileMap tm, const Accum a) {
-  uint32_t n_invalid = 0;
-  if (word_bad(qv.x, qsub)) K.x = key_bytes_bad(n0), n_invalid += w_exact_word(sv.x, qv.x, abs0, tm, a);
-  if (word_bad(qv.y, qsub)) K.y = key_bytes_bad(n1), n_invalid += w_exact_word(sv.y, qv.y, abs0 + 4u, tm, a);
-  if (word_bad(qv.z, qsub)) K.z = key_bytes_bad(n2), n_invalid += w_exact_word(sv.z, qv.z, abs0 + 8u, tm, a);
-  if (word_bad(qv.w, qsub)) K.w = key_bytes_bad(n3), n_invalid += w_exact_word(sv.w, qv.w, abs0 + 12u, tm, a);
-  return n_invalid;
+// ... re-keying the words of a 16-byte unit that hold such a byte
+__device__ __noinline__ int w_fix_bad_unit(uint4 qv, uint4 &K, uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3,
+                                           uint32_t qsub, uint32_t abs0, const WTileMap tm, const Accum a, uint32_t qbase) {
+  int d = 0;
+  if (w_word_bad(qv.x, qsub)) K.x = w_key_bytes_bad(n0), d += w_exact_word(qv.x, abs0, tm, a, qbase);
+  if (w_word_bad(qv.y, qsub)) K.y = w_key_bytes_bad(n1), d += w_exact_word(qv.y, abs0 + 4u, tm, a, qbase);
+  if (w_word_bad(qv.z, qsub)) K.z = w_key_bytes_bad(n2), d += w_exact_word(qv.z, abs0 + 8u, tm, a, qbase);
+  if (w_word_bad(qv.w, qsub)) K.w = w_key_bytes_bad(n3), d += w_exact_word(qv.w, abs0 + 12u, tm, a, qbase);
+  return d;
 }
 
 // One window of an anchor hit.  `lo`/`hi` hold the 25 bases from the start of 16-byte unit `unit` (2 bits
@@ -280,8 +299,9 @@ __device__ __forceinline__ bool w_confirm(uint32_t lo, uint32_t hi, uint32_t uni
 //   x = first byte of the tile (offset of its first read)
 //   y = reads (6 bits) | common read length if the reads all have one length and lie back to back, else 0
 //       (10 bits) | bytes from the first byte of the first read to the last byte of the last (16 bits)
-// A tile that breaks the batch contract (offsets not ascending, reads overlapping, span beyond the staged
-// buffer) gets an empty descriptor and raises the error counter: never corrupt silently.
+// A tile that breaks the batch contract (offsets not ascending, reads overlapping or longer than len_cap,
+// span beyond the staged buffer) gets an empty descriptor and raises the error counter: never corrupt
+// silently.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tile_desc_kernel(BatchView b, Accum a, uint32_t R, uint32_t tile_bytes, uint32_t n_tiles) {
   const uint32_t lane = threadIdx.x & 31u;
@@ -289,7 +309,7 @@ __global__ void __launch_bounds__(256) tile_desc_kernel(BatchView b, Accum a, ui
   if (tile >= n_tiles) return;
   constexpr uint32_t kFull = 0xffffffffu;
   const uint32_t r0 = tile * R;
-  uint32_t nr = min(R, b.n_reads - r0);
+  const uint32_t nr = min(R, b.n_reads - r0);
   uint32_t off = 0, len = 0;
   if (lane < nr) {
     off = __ldg(b.offset + r0 + lane);
@@ -313,7 +333,10 @@ __global__ void __launch_bounds__(256) tile_desc_kernel(BatchView b, Accum a, ui
   }
 }
 
-template <bool kAdapters, int kSets>
+// ------------------------------------------------------------------------------------------
+// the hot kernel
+// ------------------------------------------------------------------------------------------
+template <bool kAdapters>
 __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
   extern __shared__ __align__(128) uint8_t smem[];
   const WtilePlan &P = args.plan;
@@ -321,7 +344,6 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
   const uint32_t smem_s = smem_u32(smem);
   const uint32_t len_cap = args.a.len_cap;
   constexpr uint32_t kFull = 0xffffffffu;
-  constexpr uint32_t kTail0 = 128u * kSets;  // first position of the tail histogram
 
   if (smem_s != P.smem_base) {  // the histogram must sit at its fixed shared address: fail loudly, count nothing
     if (tid == 0) atomicAdd(&args.a.counters[kCntError], 1ull);
@@ -330,26 +352,15 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
   auto gen = [&](uint32_t shared_addr) -> uint8_t * { return smem + (shared_addr - smem_s); };
 
   // ---- this warp's block ----
-  uint32_t wb_s;
-  {
-    uint32_t w = warp;
-    if (w < P.region_n[0])
-      wb_s = P.region_s[0] + w * P.wblock;
-    else if ((w -= P.region_n[0]) < P.region_n[1])
-      wb_s = P.region_s[1] + w * P.wblock;
-    else
-      wb_s = P.region_s[2] + (w - P.region_n[1]) * P.wblock;
-  }
+  const uint32_t wb_s = warp < P.region_n[0] ? P.region_s[0] + warp * P.wblock : P.region_s[1] + (warp - P.region_n[0]) * P.wblock;
   const uint32_t buf = P.buf;
   const uint32_t stage_s0 = wb_s + wblock_hdr(kAdapters);  // stage s: seq at + 2 s buf, qual / keys at + (2 s + 1) buf
 
-  // ---- prologue: zero histograms and stage buffers, load the adapter tables, init barriers ----
-  {
+  // ---- prologue: zero the histograms, load the adapter tables, init barriers ----
+  auto clear_counters = [&]() {
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int s = 0; s < kSets; s++) {
-      uint4 *h4 = reinterpret_cast<uint4 *>(gen(kMainBase * (uint32_t)(s + 1)));
-      for (uint32_t i = tid; i < kMainBytes / 16u; i += kWThreads) h4[i] = z;
-    }
+    uint4 *h4 = reinterpret_cast<uint4 *>(gen(kMainBase));
+    for (uint32_t i = tid; i < kMainBytes / 16u; i += kWThreads) h4[i] = z;
     uint4 *t4 = reinterpret_cast<uint4 *>(gen(P.tail_s));
     for (uint32_t i = tid; i < kTailBytes / 16u; i += kWThreads) t4[i] = z;
     uint32_t *lenhist = reinterpret_cast<uint32_t *>(gen(P.lenhist_s));
@@ -358,25 +369,22 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
       lenhist[i] = 0;
       if (kAdapters) kmerhist[i] = 0;
     }
-    if (kAdapters) {
-      uint32_t *af = reinterpret_cast<uint32_t *>(gen(P.afilt_s));
-      for (uint32_t i = tid; i < kAnchorWords * kAnchorCopies; i += kWThreads) af[i] = args.ad.anchor[i / kAnchorCopies];
-      uint32_t *ex = reinterpret_cast<uint32_t *>(gen(P.exact_s));
-      if (args.ad.exact)
-        for (uint32_t i = tid; i < kExactSlots; i += kWThreads) ex[i] = args.ad.exact[i];
-    }
-    // the warp's own block: zeroed stage buffers (stray key bytes behind a tile then select valid rows)
-    uint4 *b4 = reinterpret_cast<uint4 *>(gen(wb_s));
-    for (uint32_t i = lane; i < P.wblock / 16u; i += 32u) b4[i] = z;
-    __syncwarp();
-    if (kAdapters) reinterpret_cast<uint32_t *>(gen(wb_s + kWoFhit))[lane] = kNoHit;
-    if (lane == 0) {
-      mbar_init(reinterpret_cast<uint64_t *>(gen(wb_s + kWoBar)), 1);
-      mbar_init(reinterpret_cast<uint64_t *>(gen(wb_s + kWoBar + 8u)), 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(&args.a.counters[kCntReads], (unsigned long long)args.b.n_reads);
+  };
+  clear_counters();
+  if (kAdapters) {
+    uint32_t *af = reinterpret_cast<uint32_t *>(gen(P.afilt_s));
+    for (uint32_t i = tid; i < kAnchorWords * kAnchorCopies; i += kWThreads) af[i] = args.ad.anchor[i / kAnchorCopies];
+    uint32_t *ex = reinterpret_cast<uint32_t *>(gen(P.exact_s));
+    if (args.ad.exact)
+      for (uint32_t i = tid; i < kExactSlots; i += kWThreads) ex[i] = args.ad.exact[i];
+    reinterpret_cast<uint32_t *>(gen(wb_s + kWoFhit))[lane] = kNoHit;
   }
+  if (lane == 0) {
+    mbar_init(reinterpret_cast<uint64_t *>(gen(wb_s + kWoBar)), 1);
+    mbar_init(reinterpret_cast<uint64_t *>(gen(wb_s + kWoBar + 8u)), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&args.a.counters[kCntReads], (unsigned long long)args.b.n_reads);
   __syncthreads();
 
   const uint32_t R = P.reads_per_tile;
@@ -387,31 +395,27 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
   uint32_t epoch = 65535u / ((uint32_t)kWW * R);  // iterations between two flushes of the u16 counters
   if (epoch == 0) epoch = 1;
 
-  const uint32_t qsub = P.qbase * 0x01010101u;
-  const KeyConsts kc(P.qbase);
-  WInc hc;                                            // this lane's column in histogram set 0, counter units
+  const uint32_t qbase = P.qbase;
+  const WKeyConsts kc(qbase);
+  WInc hc;  // this lane's column in the main histogram, counter units
   hc.c = kMainBase | (lane << 2);
-#ifdef QB_WT_CONST_INC
-  hc.lo = 1u, hc.hi = 0x10000u;
-#else
   hc.lo = pin(1u), hc.hi = pin(0x10000u);
-#endif
-  const uint32_t tl = P.tail_s + (lane << 2);         // ... and in the tail histogram
-  const uint32_t afilt_s = P.afilt_s, afilt_copy = (lane >> 2) * 4u;
+  const uint32_t tl = P.tail_s + (lane << 2);  // ... and in the tail histogram
+  // this lane's copy of the anchor map (8 copies, 32-byte rows); the table is 16 KiB-aligned, so its base ORs in
+  const uint32_t afilt_or = P.afilt_s | ((lane >> 2) * 4u);
   const uint32_t exact_s = P.exact_s;
   const uint32_t fhit_s = wb_s + kWoFhit, q_s = wb_s + kWoQueue;
   const uint32_t lenhist_s = P.lenhist_s, kmerhist_s = P.kmerhist_s;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  unsigned long long n_invalid = 0;
+  long long n_invalid = 0;
 
   auto flush = [&]() {  // all warps are behind a barrier
-    const uint32_t npos = min(kTail0 + 64u, len_cap);
+    const uint32_t npos = min(kWMaxLen, len_cap);
     for (uint32_t pos = tid; pos < npos; pos += kWThreads) {
       uint32_t base, rstride, sh;
       if (pos < kTail0) {
-        const uint32_t q = pos & 127u;
-        base = kMainBase * ((pos >> 7) + 1u) + 4u * ((q >> 2) + 32u * ((q & 3u) >> 1));
-        sh = (q & 1u) * 16u;
+        base = kMainBase + 4u * ((pos >> 2) + 32u * ((pos & 3u) >> 1));
+        sh = (pos & 1u) * 16u;
         rstride = 256u;
       } else {
         const uint32_t q = pos - kTail0;
@@ -420,46 +424,32 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
         rstride = kTailRow;
       }
       unsigned long long *row = args.a.rows + (size_t)pos * kRow;
-      uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-      for (uint32_t sp = 0; sp < kScoreBins; sp++) {  // the rows of s = kScoreBins are the dummies
-        const uint32_t a = base + 4u * sp * rstride;
-        const uint32_t v0 = (lds_u32(a) >> sh) & 0xFFFFu, v1 = (lds_u32(a + rstride) >> sh) & 0xFFFFu;
-        const uint32_t v2 = (lds_u32(a + 2u * rstride) >> sh) & 0xFFFFu, v3 = (lds_u32(a + 3u * rstride) >> sh) & 0xFFFFu;
-        const uint32_t tot = v0 + v1 + v2 + v3;
-        c0 += v0, c1 += v1, c2 += v2, c3 += v3;
+      uint32_t cc[4] = {0, 0, 0, 0};
+      for (uint32_t sp = 0; sp < kWScores; sp++) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (uint32_t c = 0; c < 4u; c++) {  // row = code << 6 | score
+          const uint32_t v = (lds_u32(base + (c * kWScores + sp) * rstride) >> sh) & 0xFFFFu;
+          cc[c] += v;
+          tot += v;
+        }
         if (tot) {
-          const int sc = (int)(sp + P.qbase) - 33;
+          const int sc = (int)(sp + qbase) - 33;
           if (sc >= 0 && sc < 91)
             atomicAdd(&row[sc], (unsigned long long)tot);
           else
             n_invalid += tot;
         }
       }
-      if (c0) atomicAdd(&row[kColContent + 0], (unsigned long long)c0);
-      if (c1) atomicAdd(&row[kColContent + 1], (unsigned long long)c1);
-      if (c2) atomicAdd(&row[kColContent + 2], (unsigned long long)c2);
-      if (c3) atomicAdd(&row[kColContent + 3], (unsigned long long)c3);
+#pragma unroll
+      for (uint32_t c = 0; c < 4u; c++)
+        if (cc[c]) atomicAdd(&row[kColContent + c], (unsigned long long)cc[c]);
       const uint32_t lc = lds_u32(lenhist_s + pos * 4u);
       if (lc) atomicAdd(&row[kColLength], (unsigned long long)lc);
       if (kAdapters) {
         const uint32_t kcnt = lds_u32(kmerhist_s + pos * 4u);
         if (kcnt) atomicAdd(&row[kColKmer], (unsigned long long)kcnt);
       }
-    }
-  };
-  auto clear_counters = [&]() {  // between two epochs
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int s = 0; s < kSets; s++) {
-      uint4 *h4 = reinterpret_cast<uint4 *>(gen(kMainBase * (uint32_t)(s + 1)));
-      for (uint32_t i = tid; i < kMainBytes / 16u; i += kWThreads) h4[i] = z;
-    }
-    uint4 *t4 = reinterpret_cast<uint4 *>(gen(P.tail_s));
-    for (uint32_t i = tid; i < kTailBytes / 16u; i += kWThreads) t4[i] = z;
-    uint32_t *lenhist = reinterpret_cast<uint32_t *>(gen(P.lenhist_s));
-    uint32_t *kmerhist = reinterpret_cast<uint32_t *>(gen(P.kmerhist_s));
-    for (uint32_t i = tid; i < len_cap; i += kWThreads) {
-      lenhist[i] = 0;
-      if (kAdapters) kmerhist[i] = 0;
     }
   };
 
@@ -470,15 +460,17 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
     if (lane == 0) {
       const uint32_t lo_al = d.x & ~15u;
       const uint32_t span = ((d.x & 15u) + (d.y >> 16) + 15u) & ~15u;
+      const uint32_t bar_s = wb_s + kWoBar + 8u * s;
+      const uint32_t dst_s = stage_s0 + 2u * s * buf;
       sts_u64(wb_s + kWoStage + s * kWStageHdr, d.x, d.y);
       // the TMA (async proxy) write must be ordered behind the generic-proxy key-byte writes into the buffer
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      uint64_t *bar = reinterpret_cast<uint64_t *>(gen(wb_s + kWoBar + 8u * s));
-      const bool any = (d.y & 63u) != 0u && span != 0u;
-      mbar_arrive_expect_tx(bar, any ? 2u * span : 0u);
-      if (any) {
-        bulk_g2s(gen(stage_s0 + 2u * s * buf), args.b.seq + lo_al, span, bar);
-        bulk_g2s(gen(stage_s0 + (2u * s + 1u) * buf), args.b.qual + lo_al, span, bar);
+      if ((d.y & 63u) != 0u && span != 0u) {
+        mbar_arrive_expect_tx_s(bar_s, 2u * span);
+        bulk_g2s_s(dst_s, args.b.seq + lo_al, span, bar_s);
+        bulk_g2s_s(dst_s + buf, args.b.qual + lo_al, span, bar_s);
+      } else {
+        mbar_arrive(bar_s);
       }
     }
   };
@@ -496,9 +488,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
     if (tile < n_tiles) {
       const uint32_t s = it & 1u;
       // descriptor of the tile after the next one: in flight while this tile is processed
-      const bool more = n_tiles - tile > 2u * G;
+      const uint32_t tile2 = tile + 2u * G;
+      const bool more = tile2 < n_tiles;
       uint2 d2 = make_uint2(0u, 0u);
-      if (more) d2 = __ldg(tiles + tile + 2u * G);
+      if (more) d2 = __ldg(tiles + tile2);
 
       const uint32_t hdr_s = wb_s + kWoStage + s * kWStageHdr;
       mbar_wait(wb_s + kWoBar + 8u * s, (it >> 1) & 1u);
@@ -511,7 +504,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
       const uint32_t key_s = seq_s + buf;  // phase A overwrites the quality bytes with the key bytes
       const WTileMap tm{lo, ulen, nr, soff_s};
 
-      if (!ulen && nr) {  // ragged tile: stage its offsets / lengths, lane <-> read (zero for lanes without a read)
+      // ---------------- per-read counters (quack.c:219) ----------------
+      if (ulen) {
+        if (lane == 0) red_shared_add<0>(lenhist_s + (ulen - 1u) * 4u, nr);
+      } else if (nr) {  // ragged tile: stage its offsets / lengths, lane <-> read (zero for lanes without a read)
         uint32_t off = 0, len = 0;
         if (lane < nr) {
           off = __ldg(args.b.offset + tile * R + lane);
@@ -519,10 +515,8 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
         }
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(soff_s + lane * 4u), "r"(off) : "memory");
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(slen_s + lane * 4u), "r"(len) : "memory");
-        if (len) red_shared_add<0>(lenhist_s + (len - 1u) * 4u, 1u);  // quack.c:219 (len <= len_cap: checked by the first pass)
+        if (len) red_shared_add<0>(lenhist_s + (len - 1u) * 4u, 1u);  // len <= len_cap: checked by the first pass
         __syncwarp();
-      } else if (ulen && lane == 0) {
-        red_shared_add<0>(lenhist_s + (ulen - 1u) * 4u, nr);
       }
 
       // ---------------- phase A: flat over the tile, key bytes written in place of the quality bytes ----------------
@@ -531,14 +525,14 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
         for (uint32_t u = lane; u < n16; u += 32u) {
           const uint32_t a = seq_s + u * 16u;
           const uint4 sv = lds_u128(a), qv = lds_u128(a + buf);
-          uint32_t n0, n1, n2, n3, bad = 0;
+          uint32_t n0, n1, n2, n3, q0, q1, q2, q3;
           uint4 K;
-          K.x = key_bytes(sv.x, qv.x, kc, n0, bad);
-          K.y = key_bytes(sv.y, qv.y, kc, n1, bad);
-          K.z = key_bytes(sv.z, qv.z, kc, n2, bad);
-          K.w = key_bytes(sv.w, qv.w, kc, n3, bad);
-          if (bad & 0xC0C0C0C0u)  // rare: re-key the offending words to the dummy rows, count them exactly
-            n_invalid += w_fix_bad_unit(sv, qv, K, n0, n1, n2, n3, qsub, lo_al + u * 16u, tm, args.a);
+          K.x = w_key_bytes(sv.x, qv.x, kc, n0, q0);
+          K.y = w_key_bytes(sv.y, qv.y, kc, n1, q1);
+          K.z = w_key_bytes(sv.z, qv.z, kc, n2, q2);
+          K.w = w_key_bytes(sv.w, qv.w, kc, n3, q3);
+          if ((lop3<0xFE>(q0, q1, q2) | q3) & 0xC0C0C0C0u)  // rare: a quality byte outside the counted window
+            n_invalid += w_fix_bad_unit(qv, K, n0, n1, n2, n3, kc.qsub, lo_al + u * 16u, tm, args.a, qbase);
           sts_u128(a + buf, K);
         }
       } else {
@@ -549,32 +543,30 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
           const uint32_t u = u0 + lane;
           const uint32_t a = seq_s + min(u, n16) * 16u;  // at most the 16 bytes behind the span are read
           const uint4 sv = lds_u128(a), qv = lds_u128(a + buf);
-          uint32_t n0, n1, n2, n3, bad = 0;
+          uint32_t n0, n1, n2, n3, q0, q1, q2, q3;
           uint4 K;
-          K.x = key_bytes(sv.x, qv.x, kc, n0, bad);
-          K.y = key_bytes(sv.y, qv.y, kc, n1, bad);
-          K.z = key_bytes(sv.z, qv.z, kc, n2, bad);
-          K.w = key_bytes(sv.w, qv.w, kc, n3, bad);
+          K.x = w_key_bytes(sv.x, qv.x, kc, n0, q0);
+          K.y = w_key_bytes(sv.y, qv.y, kc, n1, q1);
+          K.z = w_key_bytes(sv.z, qv.z, kc, n2, q2);
+          K.w = w_key_bytes(sv.w, qv.w, kc, n3, q3);
           const bool own = lane < 31u && u < n16;
           // 16 bases -> 32 bits.  The codes come from the base bytes alone (~n), not from the key bytes.
           const uint32_t p = pack16(~n0, ~n1, ~n2, ~n3);
           const uint32_t nx = __shfl_down_sync(kFull, p, 1);
           if (own) {
-            if (bad & 0xC0C0C0C0u)
-              n_invalid += w_fix_bad_unit(sv, qv, K, n0, n1, n2, n3, qsub, lo_al + u * 16u, tm, args.a);
+            if ((lop3<0xFE>(q0, q1, q2) | q3) & 0xC0C0C0C0u)
+              n_invalid += w_fix_bad_unit(qv, K, n0, n1, n2, n3, kc.qsub, lo_al + u * 16u, tm, args.a, qbase);
             sts_u128(a + buf, K);
           }
           // anchor j = the 7-mer starting at base 4j+3: row = its bits 13:5 (32-byte rows), bit = its bits 4:0
           const uint32_t e0 = __funnelshift_r(p, nx, 6), e1 = __funnelshift_r(p, nx, 14);
           const uint32_t e2 = __funnelshift_r(p, nx, 22), e3 = __funnelshift_r(p, nx, 30);
-          const uint32_t w0 = lds_u32_at(lop3<0xEA>(e0, 0x3FE0u, afilt_copy), afilt_s);
-          const uint32_t w1 = lds_u32_at(lop3<0xEA>(e1, 0x3FE0u, afilt_copy), afilt_s);
-          const uint32_t w2 = lds_u32_at(lop3<0xEA>(e2, 0x3FE0u, afilt_copy), afilt_s);
-          const uint32_t w3 = lds_u32_at(lop3<0xEA>(e3, 0x3FE0u, afilt_copy), afilt_s);
-          // bit 0 of m_j = anchor j passed (shift amounts wrap at 32)
+          const uint32_t w0 = lds_u32(lop3<0xEA>(e0, 0x3FE0u, afilt_or)), w1 = lds_u32(lop3<0xEA>(e1, 0x3FE0u, afilt_or));
+          const uint32_t w2 = lds_u32(lop3<0xEA>(e2, 0x3FE0u, afilt_or)), w3 = lds_u32(lop3<0xEA>(e3, 0x3FE0u, afilt_or));
+          // bit 0 of m_j = anchor j passed (funnel shifts wrap at 32)
           const uint32_t m0 = __funnelshift_r(w0, 0u, e0), m1 = __funnelshift_r(w1, 0u, e1);
           const uint32_t m2 = __funnelshift_r(w2, 0u, e2), m3 = __funnelshift_r(w3, 0u, e3);
-          const bool hit = own && ((m0 | m1 | m2 | m3) & 1u);
+          const bool hit = own && ((lop3<0xFE>(m0, m1, m2) | m3) & 1u);
           const uint32_t bal = __ballot_sync(kFull, hit);
           if (bal) {  // one queue entry per unit with a hit: 25 bases, anchor mask, unit
             if (hit) {
@@ -614,7 +606,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
           for (uint32_t i = lane; i < n16 * 4u; i += 32u) {
             const uint32_t unit = i >> 2, t = i & 3u;
             const uint4 ka = lds_u128(key_s + unit * 16u), kb = lds_u128(key_s + unit * 16u + 16u);
-            const uint32_t klo = pack16_keys(ka), khi = pack16_keys(kb);
+            const uint32_t klo = pack16(ka.x, ka.y, ka.z, ka.w), khi = pack16(kb.x, kb.y, kb.z, kb.w);  // codes = bits 7:6
             for (uint32_t j = 0; j < 4u; j++) w_confirm(klo, khi, unit, 4u * j + t, args.ad, exact_s, lo_al, tm, fhit_s);
           }
         }
@@ -631,34 +623,26 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
       // ---------------- phase H: one shared atomic per base ----------------
       {
         const uint32_t k0_s = key_s - lo_al;  // + absolute offset of a read = shared address of its first key byte
-#define QB_WSHAPES(FN) FN(0, 1) FN(1, 0) FN(1, 1) FN(1, 2) FN(1, 3) FN(2, 0) FN(2, 2) FN(2, 3)
-#define QB_WVALID(nf, kind) ((nf) <= kSets && ((kind) == 0 || ((kind) == 1 ? (nf) < kSets : (nf) == kSets)))
         if (ulen) {
-          switch (w_shape<kSets>(ulen)) {
-#define QB_WCASE(nf, kind)                                                                          \
-  case (nf)*4 + (kind):                                                                             \
-    if constexpr (QB_WVALID(nf, kind)) w_uniform<kSets, nf, kind>(hc, tl, k0_s + lo, ulen, nr, lane); \
-    break;
-            QB_WSHAPES(QB_WCASE)
-#undef QB_WCASE
+          const uint32_t kb = k0_s + lo;
+          switch (w_shape(ulen)) {
+            case 1: w_uniform<1>(hc, tl, kb, ulen, nr, lane); break;
+            case 2: w_uniform<2>(hc, tl, kb, ulen, nr, lane); break;
+            case 3: w_uniform<3>(hc, tl, kb, ulen, nr, lane); break;
+            case 4: w_uniform<4>(hc, tl, kb, ulen, nr, lane); break;
           }
         } else {
           for (uint32_t r = 0; r < nr; r++) {
             const uint32_t len = lds_u32(slen_s + r * 4u);
-            if (len == 0) continue;
             const uint32_t kb = k0_s + lds_u32(soff_s + r * 4u);
-            switch (w_shape<kSets>(len)) {
-#define QB_WCASE(nf, kind)                                                                  \
-  case (nf)*4 + (kind):                                                                     \
-    if constexpr (QB_WVALID(nf, kind)) w_one<kSets, nf, kind>(hc, tl, kb, len, lane);        \
-    break;
-              QB_WSHAPES(QB_WCASE)
-#undef QB_WCASE
+            switch (w_shape(len)) {
+              case 1: w_one<1>(hc, tl, kb, len, lane); break;
+              case 2: w_one<2>(hc, tl, kb, len, lane); break;
+              case 3: w_one<3>(hc, tl, kb, len, lane); break;
+              case 4: w_one<4>(hc, tl, kb, len, lane); break;
             }
           }
         }
-#undef QB_WVALID
-#undef QB_WSHAPES
       }
 
       // the stage is free: refill it with the tile after the next one
@@ -675,8 +659,9 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
   }
   __syncthreads();
   flush();
-  n_invalid = warp_sum(n_invalid);
-  if (lane == 0 && n_invalid) atomicAdd(&args.a.counters[kCntInvalidQual], n_invalid);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_invalid += __shfl_xor_sync(kFull, n_invalid, o);
+  if (lane == 0 && n_invalid) atomicAdd(&args.a.counters[kCntInvalidQual], (unsigned long long)n_invalid);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -687,21 +672,16 @@ WtilePlan wtile_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int
                      uint32_t smem_reserved, uint32_t qbase) {
   WtilePlan p;
   memset(&p, 0, sizeof p);
-  if (len_cap == 0 || len_cap > 320u) return p;  // beyond the shared-memory histogram
+  if (len_cap == 0 || len_cap > kWMaxLen) return p;  // beyond the shared-memory histogram
   if (batch_max_len == 0 || batch_max_len > len_cap) batch_max_len = len_cap;
-  p.nsets = len_cap <= 192u ? 1u : 2u;
   p.qbase = qbase;
   p.smem_base = smem_reserved;  // dynamic shared memory starts right behind the driver's reserved bytes
   const uint32_t end = smem_reserved + smem_optin;
-  // free address ranges around the histogram sets
+  // free address ranges below and above the main histogram
   struct Gap {
     uint32_t a, b;
-  } gap[3] = {{smem_reserved, kMainBase}, {kMainBase + kMainBytes, 2u * kMainBase}, {0, 0}};
-  if (p.nsets == 1)
-    gap[2] = Gap{2u * kMainBase, end};
-  else
-    gap[2] = Gap{2u * kMainBase + kMainBytes, end};
-  if (gap[0].a > gap[0].b || gap[2].a > gap[2].b) return p;
+  } gap[2] = {{smem_reserved, kMainBase}, {kMainBase + kMainBytes, end}};
+  if (gap[0].a > gap[0].b || gap[1].a > gap[1].b) return p;
   auto take = [&](int g, uint32_t bytes) -> uint32_t {  // 0: does not fit
     bytes = (bytes + 15u) & ~15u;
     if (gap[g].b - gap[g].a < bytes) return 0;
@@ -710,17 +690,18 @@ WtilePlan wtile_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int
     return at;
   };
   if (adapters) {
-    if (!(p.afilt_s = take(1, kAnchorSmemBytes))) return p;  // exactly the 16 KiB between set 0 and 0x20000
-    if (!(p.exact_s = take(2, kExactSlots * 4u))) return p;
+    if (!(p.afilt_s = take(1, kAnchorSmemBytes)) || (p.afilt_s & (kAnchorSmemBytes - 1u))) return p;  // 16 KiB-aligned
+    if (!(p.exact_s = take(1, kExactSlots * 4u))) return p;
   }
-  if (!(p.tail_s = take(2, kTailBytes))) return p;
-  if (!(p.lenhist_s = take(2, len_cap * 4u))) return p;
-  if (adapters && !(p.kmerhist_s = take(2, len_cap * 4u))) return p;
+  if (!(p.tail_s = take(1, kTailBytes))) return p;
+  if (!(p.lenhist_s = take(1, len_cap * 4u))) return p;
+  if (adapters && !(p.kmerhist_s = take(1, len_cap * 4u))) return p;
 
-  // reads per tile: the largest-throughput R whose kWW warp blocks fit the remaining gaps
+  // reads per tile: the R with the fewest warp instructions per base whose kWW warp blocks fit the gaps
   const uint32_t hdr = wblock_hdr(adapters);
-  const uint32_t U = adapters ? 31u : 32u;                 // units per phase-A step
-  const double c_step = adapters ? 115.0 : 72.0, c_tile = 75.0;  // warp instructions per step / per tile (measured)
+  const uint32_t U = adapters ? 31u : 32u;                       // units per phase-A step
+  const double c_step = adapters ? 100.0 : 62.0, c_tile = 70.0;  // warp instructions per step / per tile (ncu)
+  const double c_group = 17.0 * 4.0 + 3.0, c_single = 24.0;      // phase H: 4 reads unrolled / one read
   uint32_t forced = 0;
   if (const char *e = getenv("QB_WT_READS")) forced = (uint32_t)atoi(e);  // tuning hook (tools/sweep_wtile.py)
   double best_score = 0;
@@ -729,12 +710,11 @@ WtilePlan wtile_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int
     const uint32_t tb = (r * batch_max_len + 15u + 15u) & ~15u;
     if (tb > 1023u * 16u) continue;  // queue entries address 1024 units
     const uint32_t wblock = hdr + 4u * (tb + kWPad);
-    uint32_t fit = 0;
-    for (int g = 0; g < 3; g++) fit += (gap[g].b - gap[g].a) / wblock;
-    if (fit < (uint32_t)kWW) continue;
+    if ((gap[0].b - gap[0].a) / wblock + (gap[1].b - gap[1].a) / wblock < (uint32_t)kWW) continue;
     const uint32_t units = (r * batch_max_len + 15u + 15u) / 16u;
     const double steps = (double)((units + U - 1u) / U);
-    const double score = (double)(r * batch_max_len) / (steps * c_step + c_tile);
+    const double cost = steps * c_step + c_tile + (double)(r / 4u) * c_group + (double)(r % 4u) * c_single;
+    const double score = (double)(r * batch_max_len) / cost;
     if (forced ? r == forced : score > best_score) {
       best_score = score;
       best_r = r;
@@ -747,7 +727,7 @@ WtilePlan wtile_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int
   p.buf = p.tile_bytes + kWPad;
   p.wblock = hdr + 4u * p.buf;
   uint32_t left = (uint32_t)kWW;
-  for (int g = 0; g < 3; g++) {
+  for (int g = 0; g < 2; g++) {
     uint32_t n = (gap[g].b - gap[g].a) / p.wblock;
     if (n > left) n = left;
     p.region_s[g] = gap[g].a;
@@ -762,22 +742,20 @@ WtilePlan wtile_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int
 
 cudaError_t wtile_configure() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(wtile_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
-  if ((e = cudaFuncSetAttribute(wtile_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
-  if ((e = cudaFuncSetAttribute(wtile_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
-  return cudaFuncSetAttribute(wtile_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if ((e = cudaFuncSetAttribute(wtile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+  return cudaFuncSetAttribute(wtile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
 }
 
 cudaError_t launch_wtile(const BatchView &b, const Accum &a, const AdapterSet &ad, const WtilePlan &plan,
                          cudaStream_t stream) {
   if (b.n_reads == 0) return cudaSuccess;
+  if (!b.tiles) return cudaErrorInvalidValue;
   WArgs args;
   args.b = b;
   args.a = a;
   args.ad = ad;
   args.plan = plan;
   args.n_tiles = (b.n_reads + plan.reads_per_tile - 1u) / plan.reads_per_tile;
-  if (!b.tiles) return cudaErrorInvalidValue;
   tile_desc_kernel<<<(args.n_tiles + 7u) / 8u, 256, 0, stream>>>(b, a, plan.reads_per_tile, plan.tile_bytes, args.n_tiles);
   uint32_t grid = (args.n_tiles + (uint32_t)kWW - 1u) / (uint32_t)kWW;
   if (grid > plan.grid) grid = plan.grid;
@@ -785,17 +763,10 @@ cudaError_t launch_wtile(const BatchView &b, const Accum &a, const AdapterSet &a
     const uint32_t v = (uint32_t)atoi(g);
     if (v >= 1 && v < grid) grid = v;
   }
-  if (plan.nsets == 1u) {
-    if (ad.enabled)
-      wtile_kernel<true, 1><<<grid, kWThreads, plan.smem_bytes, stream>>>(args);
-    else
-      wtile_kernel<false, 1><<<grid, kWThreads, plan.smem_bytes, stream>>>(args);
-  } else {
-    if (ad.enabled)
-      wtile_kernel<true, 2><<<grid, kWThreads, plan.smem_bytes, stream>>>(args);
-    else
-      wtile_kernel<false, 2><<<grid, kWThreads, plan.smem_bytes, stream>>>(args);
-  }
+  if (ad.enabled)
+    wtile_kernel<true><<<grid, kWThreads, plan.smem_bytes, stream>>>(args);
+  else
+    wtile_kernel<false><<<grid, kWThreads, plan.smem_bytes, stream>>>(args);
   return cudaGetLastError();
 }
 

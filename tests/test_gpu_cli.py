@@ -46,10 +46,10 @@ def _golden(golden_dir, name):
 
 
 @pytest.mark.parametrize("name", sorted(COMBOS))
-@pytest.mark.parametrize("kernel", ["1", "2", "3"], ids=["simple", "fused", "wtile"])
+@pytest.mark.parametrize("kernel", ["1", "2", "0"], ids=["simple", "fused", "auto"])
 def test_cli_svg_matches_reference_golden(name, kernel, golden_dir):
     args = [os.path.join(golden_dir, a) if os.path.exists(os.path.join(golden_dir, a)) else a for a in COMBOS[name]]
-    r = _run(args, {"QB_KERNEL": kernel, "QB_LEN_CAP": "65536" if kernel == "1" else "320"})
+    r = _run(args, {"QB_KERNEL": kernel, "QB_LEN_CAP": "320" if kernel == "2" else "65536"})
     assert r.returncode == 0, r.stderr
     assert r.stdout == _golden(golden_dir, name)
 

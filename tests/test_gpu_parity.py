@@ -29,8 +29,13 @@ def keys(table):
     return table.keys()
 
 
+WTILE_MAX_LEN = 192   # the warp-tile kernel's shared-memory histogram; longer batches take the fused kernel
+
+
 def run_gpu(batch, len_cap, keys, kernel, resident=False, **kw):
     seq, qual, off, lens = batch
+    if kernel == capi.KERNEL_WTILE and len(lens) and min(int(lens.max()), len_cap) > WTILE_MAX_LEN:
+        pytest.skip("batch beyond the warp-tile kernel's 192-bp histogram (AUTO picks the fused kernel)")
     with capi.Context(len_cap, adapter_keys=keys, kernel=kernel, **kw) as ctx:
         if resident:
             b = ctx.upload(seq, qual, off, lens, max_len=int(lens.max()) if len(lens) else 0)
