@@ -83,7 +83,7 @@ constexpr int kFusedConsumerWarps = QB_CW;  // + 1 producer warp = 512 threads (
 
 // ---- warp-tile kernel geometry (qb_wtile.cu; computed on the host, see wtile_plan) --------
 #ifndef QB_WW
-#define QB_WW 24
+#define QB_WW 16
 #endif
 constexpr int kWtileWarps = QB_WW;  // autonomous warps per CTA (one CTA per SM)
 

@@ -4,9 +4,11 @@
 // Same idea as fused_kernel (qb_kernels.cu) -- SWAR key bytes, joint (code, score) x position histogram of
 // packed u16 counters in shared memory, 7-mer anchor filter + exact confirmation for -a -- but organised
 // around AUTONOMOUS WARPS instead of a CTA-wide pipeline:
-//   * every warp owns a private 2-stage ring of small tiles (R whole reads, ~1-4 KB of seq + of qual).
-//     The warp itself issues the 1-D TMA bulk copies of its tile t+2 when it is done with tile t and then
-//     waits on the mbarrier of tile t+1: no producer warp, no polling, no CTA barrier in the steady state.
+//   * every warp owns a private ring of small tiles (R whole reads, ~1-4 KB of seq + of qual): two quality /
+//     key-byte buffers and ONE base buffer (the bases are dead once phase A has turned them into key bytes).
+//     The warp itself issues the 1-D TMA bulk copies -- the bases of tile t+1 right after phase A of tile t,
+//     the quality bytes of tile t+2 when it is done with tile t -- and then waits on the mbarrier of tile
+//     t+1: no producer warp, no polling, no CTA barrier in the steady state.
 //     Warps drift apart, so the ALU-heavy phase A of one warp overlaps the shared-memory-heavy phase H of
 //     another (the v3 kernel ran them in lock step and left both pipes < 45 % busy);
 //   * a small first pass (tile_desc_kernel, one warp per tile) validates the reads of every tile and writes an
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
   // ---- this warp's block ----
   const uint32_t wb_s = warp < P.region_n[0] ? P.region_s[0] + warp * P.wblock : P.region_s[1] + (warp - P.region_n[0]) * P.wblock;
   const uint32_t buf = P.buf;
-  const uint32_t stage_s0 = wb_s + wblock_hdr(kAdapters);  // stage s: seq at + 2 s buf, qual / keys at + (2 s + 1) buf
+  const uint32_t seqbuf_s = wb_s + wblock_hdr(kAdapters);  // bases of the current tile; quality / key bytes of stage s at + (1 + s) buf
 
   // ---- prologue: zero the histograms, load the adapter tables, init barriers ----
   auto clear_counters = [&]() {
@@ -380,8 +382,8 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
     reinterpret_cast<uint32_t *>(gen(wb_s + kWoFhit))[lane] = kNoHit;
   }
   if (lane == 0) {
-    mbar_init(reinterpret_cast<uint64_t *>(gen(wb_s + kWoBar)), 1);
-    mbar_init(reinterpret_cast<uint64_t *>(gen(wb_s + kWoBar + 8u)), 1);
+    mbar_init(reinterpret_cast<uint64_t *>(gen(wb_s + kWoBar)), 2);  // one arrival for the bases, one for the quality bytes
+    mbar_init(reinterpret_cast<uint64_t *>(gen(wb_s + kWoBar + 8u)), 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (blockIdx.x == 0 && tid == 0) atomicAdd(&args.a.counters[kCntReads], (unsigned long long)args.b.n_reads);
@@ -453,22 +455,24 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
     }
   };
 
-  // Start the bulk copies of a tile (descriptor d) into stage s and stash the descriptor in the stage header.
-  // The whole warp calls this once it is done with the stage's previous tile.
-  auto issue = [&](uint32_t s, uint2 d) {
-    __syncwarp();  // every lane is done with the stage's old contents
+  // Start the bulk copy of one half of a tile (descriptor d): its quality bytes into stage s (the descriptor is
+  // stashed in the stage header), or its bases into the base buffer.  Both arrive on the mbarrier of stage s.
+  // The whole warp calls this once it is done with the buffer's previous contents.
+  auto issue = [&](uint32_t s, uint2 d, bool bases) {
+    __syncwarp();  // every lane is done with the buffer's old contents
     if (lane == 0) {
       const uint32_t lo_al = d.x & ~15u;
       const uint32_t span = ((d.x & 15u) + (d.y >> 16) + 15u) & ~15u;
       const uint32_t bar_s = wb_s + kWoBar + 8u * s;
-      const uint32_t dst_s = stage_s0 + 2u * s * buf;
-      sts_u64(wb_s + kWoStage + s * kWStageHdr, d.x, d.y);
-      // the TMA (async proxy) write must be ordered behind the generic-proxy key-byte writes into the buffer
+      if (!bases) sts_u64(wb_s + kWoStage + s * kWStageHdr, d.x, d.y);
+      // the TMA (async proxy) write must be ordered behind the generic-proxy accesses to the buffer
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       if ((d.y & 63u) != 0u && span != 0u) {
-        mbar_arrive_expect_tx_s(bar_s, 2u * span);
-        bulk_g2s_s(dst_s, args.b.seq + lo_al, span, bar_s);
-        bulk_g2s_s(dst_s + buf, args.b.qual + lo_al, span, bar_s);
+        mbar_arrive_expect_tx_s(bar_s, span);
+        if (bases)
+          bulk_g2s_s(seqbuf_s, args.b.seq + lo_al, span, bar_s);
+        else
+          bulk_g2s_s(seqbuf_s + (1u + s) * buf, args.b.qual + lo_al, span, bar_s);
       } else {
         mbar_arrive(bar_s);
       }
@@ -477,9 +481,11 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
 
   const uint32_t g = g0 + warp;
   const uint2 *tiles = args.b.tiles;
-  for (uint32_t k = 0; k < 2u; k++) {
-    const uint32_t tile = g + k * G;
-    if (tile < n_tiles) issue(k, __ldg(tiles + tile));
+  if (g < n_tiles) {
+    const uint2 d = __ldg(tiles + g);
+    issue(0, d, false);
+    issue(0, d, true);
+    if (g + G < n_tiles) issue(1, __ldg(tiles + g + G), false);
   }
 
   uint32_t to_flush = epoch;
@@ -500,8 +506,9 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
       const uint32_t lo_al = lo & ~15u;
       const uint32_t n16 = ((lo & 15u) + (mt.y >> 16) + 15u) >> 4;  // 16-byte units of the tile
       const uint32_t soff_s = hdr_s + 16u, slen_s = hdr_s + 144u;
-      const uint32_t seq_s = stage_s0 + 2u * s * buf;
-      const uint32_t key_s = seq_s + buf;  // phase A overwrites the quality bytes with the key bytes
+      const uint32_t seq_s = seqbuf_s;
+      const uint32_t key_s = seqbuf_s + (1u + s) * buf;  // phase A overwrites the quality bytes with the key bytes
+      const uint32_t kd = key_s - seq_s;                 // quality / key byte of a base = its address + kd
       const WTileMap tm{lo, ulen, nr, soff_s};
 
       // ---------------- per-read counters (quack.c:219) ----------------
@@ -524,7 +531,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
       if (!kAdapters) {
         for (uint32_t u = lane; u < n16; u += 32u) {
           const uint32_t a = seq_s + u * 16u;
-          const uint4 sv = lds_u128(a), qv = lds_u128(a + buf);
+          const uint4 sv = lds_u128(a), qv = lds_u128(a + kd);
           uint32_t n0, n1, n2, n3, q0, q1, q2, q3;
           uint4 K;
           K.x = w_key_bytes(sv.x, qv.x, kc, n0, q0);
@@ -533,7 +540,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
           K.w = w_key_bytes(sv.w, qv.w, kc, n3, q3);
           if ((lop3<0xFE>(q0, q1, q2) | q3) & 0xC0C0C0C0u)  // rare: a quality byte outside the counted window
             n_invalid += w_fix_bad_unit(qv, K, n0, n1, n2, n3, kc.qsub, lo_al + u * 16u, tm, args.a, qbase);
-          sts_u128(a + buf, K);
+          sts_u128(a + kd, K);
         }
       } else {
         // One 16-byte unit per lane.  A step covers 31 new units; lane 31 re-reads the unit behind them so
@@ -542,7 +549,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
         for (uint32_t u0 = 0; u0 < n16; u0 += 31u) {
           const uint32_t u = u0 + lane;
           const uint32_t a = seq_s + min(u, n16) * 16u;  // at most the 16 bytes behind the span are read
-          const uint4 sv = lds_u128(a), qv = lds_u128(a + buf);
+          const uint4 sv = lds_u128(a), qv = lds_u128(a + kd);
           uint32_t n0, n1, n2, n3, q0, q1, q2, q3;
           uint4 K;
           K.x = w_key_bytes(sv.x, qv.x, kc, n0, q0);
@@ -556,7 +563,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
           if (own) {
             if ((lop3<0xFE>(q0, q1, q2) | q3) & 0xC0C0C0C0u)
               n_invalid += w_fix_bad_unit(qv, K, n0, n1, n2, n3, kc.qsub, lo_al + u * 16u, tm, args.a, qbase);
-            sts_u128(a + buf, K);
+            sts_u128(a + kd, K);
           }
           // anchor j = the 7-mer starting at base 4j+3: row = its bits 13:5 (32-byte rows), bit = its bits 4:0
           const uint32_t e0 = __funnelshift_r(p, nx, 6), e1 = __funnelshift_r(p, nx, 14);
@@ -578,7 +585,14 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
           }
         }
       }
-      __syncwarp();  // key bytes and the candidate queue of this tile are complete
+      // key bytes and the candidate queue of this tile are complete and its bases are dead: fetch the next tile's
+      // (its descriptor sits in the other stage's header since its quality bytes were requested)
+      if (tile + G < n_tiles) {
+        const uint2 d1 = lds_u64(wb_s + kWoStage + (s ^ 1u) * kWStageHdr);
+        issue(s ^ 1u, d1, true);
+      } else {
+        __syncwarp();
+      }
 
       // ---------------- phase A2: confirm the queued anchor hits (quack.c:210-217) ----------------
       if (kAdapters && qn) {
@@ -646,7 +660,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wtile_kernel(const WArgs args) {
       }
 
       // the stage is free: refill it with the tile after the next one
-      if (more) issue(s, d2);
+      if (more) issue(s, d2, false);
     }
     if (--to_flush == 0u && it + 1u < iters) {  // u16 counters: flush before any bin can wrap
       to_flush = epoch;
@@ -700,7 +714,7 @@ WtilePlan wtile_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int
   // reads per tile: the R with the fewest warp instructions per base whose kWW warp blocks fit the gaps
   const uint32_t hdr = wblock_hdr(adapters);
   const uint32_t U = adapters ? 31u : 32u;                       // units per phase-A step
-  const double c_step = adapters ? 100.0 : 62.0, c_tile = 70.0;  // warp instructions per step / per tile (ncu)
+  const double c_step = adapters ? 100.0 : 62.0, c_tile = 140.0;  // warp instructions per step / per tile (ncu)
   const double c_group = 17.0 * 4.0 + 3.0, c_single = 24.0;      // phase H: 4 reads unrolled / one read
   uint32_t forced = 0;
   if (const char *e = getenv("QB_WT_READS")) forced = (uint32_t)atoi(e);  // tuning hook (tools/sweep_wtile.py)
@@ -709,7 +723,7 @@ WtilePlan wtile_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int
   for (uint32_t r = 32; r >= 1; r--) {
     const uint32_t tb = (r * batch_max_len + 15u + 15u) & ~15u;
     if (tb > 1023u * 16u) continue;  // queue entries address 1024 units
-    const uint32_t wblock = hdr + 4u * (tb + kWPad);
+    const uint32_t wblock = hdr + 3u * (tb + kWPad);
     if ((gap[0].b - gap[0].a) / wblock + (gap[1].b - gap[1].a) / wblock < (uint32_t)kWW) continue;
     const uint32_t units = (r * batch_max_len + 15u + 15u) / 16u;
     const double steps = (double)((units + U - 1u) / U);
@@ -725,7 +739,7 @@ WtilePlan wtile_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int
   p.reads_per_tile = best_r;
   p.tile_bytes = (best_r * batch_max_len + 15u + 15u) & ~15u;
   p.buf = p.tile_bytes + kWPad;
-  p.wblock = hdr + 4u * p.buf;
+  p.wblock = hdr + 3u * p.buf;
   uint32_t left = (uint32_t)kWW;
   for (int g = 0; g < 2; g++) {
     uint32_t n = (gap[g].b - gap[g].a) / p.wblock;
