@@ -50,10 +50,14 @@ typedef enum {
 } qb_status;
 
 typedef enum {
-  QB_KERNEL_AUTO = 0,      /* warp-tile kernel for batches of reads <= 192 bp, fused kernel up to 320 bp, else simple */
+  QB_KERNEL_AUTO = 0,      /* period kernel for batches of back-to-back reads of one even length in [32, 256]; else the
+                              fused kernel up to 320 bp, the warp-tile kernel, or simple */
   QB_KERNEL_SIMPLE = 1,    /* one warp per read, global atomics: any len_cap, slow */
   QB_KERNEL_FUSED = 2,     /* CTA-wide TMA-staged tiles, joint (base,score) shared-memory histogram (v3) */
-  QB_KERNEL_WTILE = 3      /* autonomous warps, each with its own TMA-staged tile ring (v4; reads <= 192 bp) */
+  QB_KERNEL_WTILE = 3,     /* autonomous warps, each with its own TMA-staged tile ring (v4; reads <= 192 bp) */
+  QB_KERNEL_PERIOD = 4     /* v5: lanes own fixed positions of a k-read period, one aligned load + PRMT + RED per base;
+                              uniform-length batches only (an error otherwise), the reads that do not fill a tile
+                              go to the AUTO choice among the others */
 } qb_kernel;
 
 typedef struct qb_ctx qb_ctx;       /* one per process; owns devices, streams, accumulators */
@@ -165,6 +169,11 @@ int qb_timer_start(qb_ctx *ctx, int device_index);
 int qb_timer_stop(qb_ctx *ctx, int device_index, float *ms);
 /* Measured pinned H2D bandwidth of device_index in GB/s (best of `iters` copies of `bytes`). */
 int qb_measure_h2d(qb_ctx *ctx, int device_index, uint64_t bytes, int iters, double *gbs);
+/* Geometry and shared-memory counter layout of the period kernel (QB_KERNEL_PERIOD) for reads of one length.
+ * Needs no GPU.  0 if the kernel takes such batches, -1 otherwise.  info = reads per period, words per period,
+ * warp steps per period, periods per tile, reads per tile, stages; slot[p] = histogram block << 7 | 32-bit
+ * column of position p (its bank is the column modulo 32). */
+int qb_period_layout(uint32_t read_len, int adapters, uint32_t info[6], uint8_t slot[256]);
 
 /* ---- host helpers that define the kernel's inputs ---- */
 /* lookup[(c-65)&~32] of quack.c:150,201 extended to all byte values. */

@@ -13,7 +13,7 @@ from .build import lib_path
 
 ROW = 97
 COL_CONTENT, COL_LENGTH, COL_KMER = 91, 95, 96
-KERNEL_AUTO, KERNEL_SIMPLE, KERNEL_FUSED, KERNEL_WTILE = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_SIMPLE, KERNEL_FUSED, KERNEL_WTILE, KERNEL_PERIOD = 0, 1, 2, 3, 4
 NCCL_ID_BYTES = 128
 
 _u8p = C.POINTER(C.c_uint8)

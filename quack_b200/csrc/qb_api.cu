@@ -97,7 +97,7 @@ struct qb_ctx {
   std::mutex mu;
   uint64_t next_slot = 0;
   std::string err;
-  uint64_t launches = 0, launches_fused = 0, launches_simple = 0;
+  uint64_t launches = 0, launches_fused = 0, launches_simple = 0, launches_period = 0;
   size_t acc_u64 = 0;  // len_cap*97 + counters
   qb::AdapterSet ad_host_template{};
   uint32_t n_anchors = 0;     // distinct 7-mer anchors of the adapter set
@@ -120,6 +120,7 @@ struct qb_dbatch {
   uint32_t n_reads;
   uint64_t n_bytes;
   uint32_t max_len;
+  uint32_t uniform_len, first_offset;  // see qb::BatchView
 };
 
 namespace {
@@ -171,12 +172,20 @@ qb::Accum accum(const qb_ctx *ctx, const Device &d, int mate) {
   return a;
 }
 
-// chooses and launches the statistics kernel for one device-resident batch
-int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaStream_t stream) {
-  if (v.n_reads == 0) return QB_OK;
-  const qb::AdapterSet ad = adapter_set(ctx, d);
-  qb::Accum ac = accum(ctx, d, mate);
-  int kernel = ctx->cfg.kernel;
+// Host-side check of the batch shape the period kernel needs: every read has the same length and the reads
+// lie back to back.  Returns that length (0: ragged) -- one vectorisable pass over the two u32 arrays.
+uint32_t detect_uniform(const uint32_t *offset, const uint32_t *length, uint32_t n_reads, uint32_t *first_offset) {
+  if (n_reads == 0) return 0;
+  const uint32_t l = length[0], o0 = offset[0];
+  uint32_t diff = 0;
+  for (uint32_t r = 0; r < n_reads; r++) diff |= (length[r] ^ l) | (offset[r] ^ (o0 + r * l));
+  *first_offset = o0;
+  return diff ? 0u : l;
+}
+
+// one launch of the v4 / v3 / simple kernel on a batch view
+int launch_other(qb_ctx *ctx, Device &d, const qb::BatchView &v, qb::Accum ac, const qb::AdapterSet &ad, int kernel,
+                 cudaStream_t stream) {
   qb::FusedPlan plan{};
   qb::WtilePlan wplan{};
   if (kernel != QB_KERNEL_SIMPLE) {
@@ -185,16 +194,17 @@ int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaS
     // opened for 65536-bp reads still runs short-read batches on the shared-memory kernels.
     uint32_t eff_cap = ctx->cfg.len_cap;
     if (v.max_len && v.max_len < eff_cap) eff_cap = v.max_len < 11u ? 11u : v.max_len;
-    if (kernel != QB_KERNEL_FUSED)
+    // AUTO: the v3 kernel measured faster than v4 wherever both fit (profiles/r01c)
+    if (kernel != QB_KERNEL_WTILE)
+      plan = qb::fused_plan(eff_cap, v.max_len, ad.enabled, d.sm_count, (uint32_t)d.smem_optin, ctx->qbase);
+    if (kernel != QB_KERNEL_FUSED && !plan.ok)
       wplan = qb::wtile_plan(eff_cap, v.max_len, ad.enabled, d.sm_count, (uint32_t)d.smem_optin,
                              (uint32_t)d.smem_reserved, ctx->qbase);
-    if (kernel != QB_KERNEL_WTILE && !wplan.ok)
-      plan = qb::fused_plan(eff_cap, v.max_len, ad.enabled, d.sm_count, (uint32_t)d.smem_optin, ctx->qbase);
-    if (wplan.ok) {
-      kernel = QB_KERNEL_WTILE;
-      ac.len_cap = eff_cap;
-    } else if (plan.ok) {
+    if (plan.ok) {
       kernel = QB_KERNEL_FUSED;
+      ac.len_cap = eff_cap;
+    } else if (wplan.ok) {
+      kernel = QB_KERNEL_WTILE;
       ac.len_cap = eff_cap;
     } else {
       if (kernel != QB_KERNEL_AUTO)
@@ -203,11 +213,38 @@ int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaS
       kernel = QB_KERNEL_SIMPLE;
     }
   }
-  qb_ctx::ProfRec *rec = nullptr;
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->launches++;
     (kernel == QB_KERNEL_SIMPLE ? ctx->launches_simple : ctx->launches_fused)++;
+  }
+  cudaError_t e = kernel == QB_KERNEL_WTILE   ? qb::launch_wtile(v, ac, ad, wplan, stream)
+                  : kernel == QB_KERNEL_FUSED ? qb::launch_fused(v, ac, ad, plan, stream)
+                                              : qb::launch_simple(v, ac, ad, d.sm_count, stream);
+  if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  return QB_OK;
+}
+
+// chooses and launches the statistics kernel(s) for one device-resident batch
+int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaStream_t stream) {
+  if (v.n_reads == 0) return QB_OK;
+  const qb::AdapterSet ad = adapter_set(ctx, d);
+  qb::Accum ac = accum(ctx, d, mate);
+  int kernel = ctx->cfg.kernel;
+  qb::PeriodPlan pplan{};
+  if ((kernel == QB_KERNEL_AUTO || kernel == QB_KERNEL_PERIOD) && v.uniform_len && v.uniform_len <= ctx->cfg.len_cap &&
+      (!v.max_len || v.uniform_len <= v.max_len))
+    pplan = qb::period_plan(v.uniform_len, v.first_offset, ad.enabled, d.sm_count, (uint32_t)d.smem_optin,
+                            (uint32_t)d.smem_reserved, ctx->qbase);
+  if (kernel == QB_KERNEL_PERIOD) {
+    if (!pplan.ok)
+      return fail(ctx, QB_ERR_CAPACITY, "the period kernel needs a batch of back-to-back reads of one even length in [32, %u]",
+                  qb::kPeriodMaxLen);
+    kernel = QB_KERNEL_AUTO;  // for the reads that do not fill a tile
+  }
+  qb_ctx::ProfRec *rec = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
     if ((int)ctx->prof.size() < ctx->prof_cap) {
       qb_ctx::ProfRec r{};
       if (cudaEventCreate(&r.e0) == cudaSuccess && cudaEventCreate(&r.e1) == cudaSuccess) {
@@ -220,12 +257,27 @@ int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaS
   }
   cudaEvent_t e0 = rec ? rec->e0 : nullptr, e1 = rec ? rec->e1 : nullptr;
   if (e0) cudaEventRecord(e0, stream);
-  cudaError_t e = kernel == QB_KERNEL_WTILE   ? qb::launch_wtile(v, ac, ad, wplan, stream)
-                  : kernel == QB_KERNEL_FUSED ? qb::launch_fused(v, ac, ad, plan, stream)
-                                              : qb::launch_simple(v, ac, ad, d.sm_count, stream);
+  uint32_t n_main = 0;
+  int rc = QB_OK;
+  if (pplan.ok) {
+    const cudaError_t e = qb::launch_period(v, ac, ad, pplan, stream, &n_main);
+    if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    if (n_main) {
+      std::lock_guard<std::mutex> lk(ctx->mu);
+      ctx->launches++;
+      ctx->launches_fused++;
+      ctx->launches_period++;
+    }
+  }
+  if (n_main < v.n_reads) {  // everything, or the reads that do not fill a tile of the period kernel
+    qb::BatchView rest = v;
+    rest.offset += n_main;
+    rest.length += n_main;
+    rest.n_reads -= n_main;
+    rc = launch_other(ctx, d, rest, ac, ad, kernel, stream);
+  }
   if (e1) cudaEventRecord(e1, stream);
-  if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
-  return QB_OK;
+  return rc;
 }
 
 int check_mate(qb_ctx *ctx, int mate) {
@@ -318,6 +370,7 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
     QB_CREATE_CUDA(cudaDeviceGetAttribute(&d.smem_reserved, cudaDevAttrReservedSharedMemoryPerBlock, d.id));
     QB_CREATE_CUDA(qb::fused_configure());
     QB_CREATE_CUDA(qb::wtile_configure());
+    QB_CREATE_CUDA(qb::period_configure());
     QB_CREATE_CUDA(cudaStreamCreateWithFlags(&d.main_stream, cudaStreamNonBlocking));
     d.acc.resize(cfg.n_mates);
     for (int m = 0; m < cfg.n_mates; m++) {
@@ -468,6 +521,8 @@ static int submit_on(qb_ctx *ctx, int di, int si, int mate, const uint8_t *seq, 
     QB_CUDA(ctx, cudaMemcpyAsync(s.d_off, offset, (size_t)n_reads * 4, cudaMemcpyHostToDevice, s.stream));
     QB_CUDA(ctx, cudaMemcpyAsync(s.d_len, length, (size_t)n_reads * 4, cudaMemcpyHostToDevice, s.stream));
     qb::BatchView v{s.d_seq, s.d_qual, s.d_off, s.d_len, n_reads, n_bytes, max_len ? max_len : ctx->cfg.len_cap, s.d_tiles};
+    if (ctx->cfg.kernel == QB_KERNEL_AUTO || ctx->cfg.kernel == QB_KERNEL_PERIOD)
+      v.uniform_len = detect_uniform(offset, length, n_reads, &v.first_offset);
     int rc = launch_batch(ctx, d, v, mate, s.stream);
     if (rc) return rc;
   }
@@ -764,6 +819,7 @@ int qb_dbatch_upload(qb_ctx *ctx, int device_index, const uint8_t *seq, const ui
   if (n_reads) {
     QB_CUDA(ctx, cudaMemcpy(b->d_off, offset, (size_t)n_reads * 4, cudaMemcpyHostToDevice));
     QB_CUDA(ctx, cudaMemcpy(b->d_len, length, (size_t)n_reads * 4, cudaMemcpyHostToDevice));
+    b->uniform_len = detect_uniform(offset, length, n_reads, &b->first_offset);
   }
   *out = b;
   return QB_OK;
@@ -788,12 +844,15 @@ int qb_dbatch_generate(qb_ctx *ctx, int device_index, uint64_t seed, int mate, u
     return fail(ctx, QB_ERR_NOMEM, "pinned staging allocation failed");
   }
   uint64_t base = 0;
+  bool uniform = len_min == len_max;  // the generator packs reads back to back
   for (uint32_t r0 = 0; r0 < n_reads && rc == QB_OK; r0 += chunk) {
     const uint32_t n = n_reads - r0 < chunk ? n_reads - r0 : chunk;
     uint64_t nb = 0;
     rc = qb_gen_reads(seed, mate, first_read + r0, n, len_min, len_max, adapter_rate, hs, hq, ho, hl, &nb);
     if (rc) break;
     for (uint32_t i = 0; i < n; i++) ho[i] += (uint32_t)base;
+    uint32_t fo = 0;
+    if (uniform && (detect_uniform(ho, hl, n, &fo) != len_min || fo != (uint32_t)base)) uniform = false;
     if (cudaMemcpy(b->d_seq + base, hs, nb, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(b->d_qual + base, hq, nb, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(b->d_off + r0, ho, (size_t)n * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -806,6 +865,8 @@ int qb_dbatch_generate(qb_ctx *ctx, int device_index, uint64_t seed, int mate, u
     qb_dbatch_free(ctx, b);
     return rc;
   }
+  b->uniform_len = uniform && n_reads ? len_min : 0u;
+  b->first_offset = 0;
   *out = b;
   return QB_OK;
 }
@@ -834,7 +895,8 @@ int qb_dbatch_run(qb_ctx *ctx, qb_dbatch *b, int mate) {
   if (!b) return QB_ERR_ARG;
   Device &d = ctx->dev[b->device_index];
   QB_CUDA(ctx, cudaSetDevice(d.id));
-  qb::BatchView v{b->d_seq, b->d_qual, b->d_off, b->d_len, b->n_reads, b->n_bytes, b->max_len, b->d_tiles};
+  qb::BatchView v{b->d_seq, b->d_qual, b->d_off, b->d_len, b->n_reads, b->n_bytes, b->max_len, b->d_tiles,
+                  b->uniform_len, b->first_offset};
   return launch_batch(ctx, d, v, mate, d.main_stream);
 }
 

@@ -55,6 +55,9 @@ struct BatchView {
   uint64_t n_bytes;
   uint32_t max_len;        // longest read in the batch (upper bound)
   uint2 *tiles;            // scratch of n_reads entries: tile descriptors written by the warp-tile kernel's first pass
+  uint32_t uniform_len;    // != 0: the HOST verified that every read has this length and that the reads lie back to
+                           // back (offset[r] = offset[0] + r * uniform_len); 0: unknown / ragged
+  uint32_t first_offset;   // offset[0] of a uniform batch
 };
 
 struct Accum {
@@ -106,6 +109,41 @@ WtilePlan wtile_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int
 cudaError_t launch_wtile(const BatchView &b, const Accum &a, const AdapterSet &ad, const WtilePlan &plan,
                          cudaStream_t stream);
 cudaError_t wtile_configure();  // opt in to the large dynamic shared memory once per device
+
+// ---- period kernel geometry (qb_period.cu; computed on the host, see period_plan) --------
+#ifndef QB_PW
+#define QB_PW 16
+#endif
+constexpr int kPeriodWarps = QB_PW;   // autonomous warps per CTA (one CTA per SM)
+constexpr uint32_t kPeriodMaxLen = 256;  // two histogram blocks of 128 positions
+
+struct PeriodPlan {
+  uint32_t len;              // the common read length l (even, 32..256)
+  uint32_t k;                // reads per period: k * l is a multiple of 4
+  uint32_t wp;               // 32-bit words per period = k * l / 4
+  uint32_t steps;            // warp steps per period = ceil(wp / 32): 3, 4 or 5 (template parameter)
+  uint32_t ppt;              // periods per tile: tile_bytes = ppt * k * l is a multiple of 16
+  uint32_t tile_bytes;
+  uint32_t reads_per_tile;   // ppt * k, a multiple of 4
+  uint32_t stages;           // staged tiles per warp (2..4)
+  uint32_t nblocks;          // histogram blocks (128 positions each)
+  uint32_t wblock;           // bytes of one warp block (barriers, first hits, queue, stages x (seq + qual))
+  uint32_t smem_base;        // shared address the dynamic shared memory must start at (checked by the kernel)
+  uint32_t smem_bytes;
+  uint32_t afilt_s, exact_s, kmerhist_s;  // shared addresses of the CTA-wide arrays
+  uint32_t region_s[3], region_n[3];      // warp blocks: region_n[i] blocks from region_s[i]
+  uint32_t qbase;
+  uint32_t grid;
+  int ok;                    // 0: not a batch for this kernel
+};
+
+PeriodPlan period_plan(uint32_t uniform_len, uint32_t first_offset, int adapters, int sm_count, uint32_t smem_optin,
+                       uint32_t smem_reserved, uint32_t qbase);
+// counts the first n_main = floor(n_reads / reads_per_tile) * reads_per_tile reads of a uniform batch; the caller
+// hands the rest to another kernel.  *n_main_out = 0: nothing launched.
+cudaError_t launch_period(const BatchView &b, const Accum &a, const AdapterSet &ad, const PeriodPlan &plan,
+                          cudaStream_t stream, uint32_t *n_main_out);
+cudaError_t period_configure();
 
 FusedPlan fused_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int sm_count,
                      uint32_t smem_optin, uint32_t qbase);

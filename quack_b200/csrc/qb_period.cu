@@ -1,0 +1,690 @@
+// qb_period.cu -- period kernel (v5) for quack's per-read statistics accumulation
+// (reference: the while loop of read_fastq(), quack.c:193-221), for batches whose reads all have ONE length
+// l (even, 32..256 bp) and lie back to back -- the shape of untrimmed Illumina data (configs 1-3, 5).
+//
+// The v3 / v4 kernels are bound by the shared-memory pipe (ncu: 84 % busy once the 1.4-cycle cost of a shared
+// atomic is counted): they touch every base three times there (TMA fill, flat pass that writes key bytes,
+// per-read pass that re-reads them through two unaligned loads + a byte step).  This kernel touches a base
+// twice (TMA fill, ONE aligned 32-bit load) and spends 2 instructions per base on the histogram update:
+//   * k reads form a PERIOD of k*l bytes that is a whole number of 32-bit words (k = 1, 2 or a multiple that
+//     fills the last warp step: 4 x 150 bp = 150 words = 4.7 warp steps).  A warp walks a period in `steps`
+//     steps of 32 aligned words, lane <-> word.  Word 32 s + lane of EVERY period holds the same four
+//     positions, so the shared address of each counter column is a per-lane constant kept in a register
+//     (steps x 4 of them); there is no per-read work at all, no offsets / lengths are read (the host verified
+//     the batch shape), no alignment fix-ups, no tail steps;
+//   * key byte K = score << 2 | code as in the v3 kernel; the joint (score, code) x position histogram has
+//     256-byte rows at a 64 KiB-aligned shared address, so ONE byte permute builds a counter's address from the
+//     key byte and the lane's column register (PRMT + RED per base).  Positions 0..127 live in block 0,
+//     128..255 in block 1 (+64 KiB); only 192 of a block's 256 rows exist, the 16 KiB behind them hold the
+//     anchor filter.  Which u16 slot of a row a position uses is a TABLE (PArgs::slot) chosen on the host so
+//     that the 32 lanes of a warp step fall into different banks as far as the geometry allows;
+//   * -a: the 7-mer anchor probe of the v3 / v4 kernels runs in the same loop on the key bytes just computed
+//     (codes gathered by one multiply, the neighbour lane's by one shuffle); hits queue the word index and are
+//     confirmed per tile against the exact key set from the staged bases, 4 lanes per hit;
+//   * autonomous warps with private TMA rings as in v4 (no producer warp, no CTA barrier in steady state).
+// Reads that do not fill a tile (< reads_per_tile at the end of a batch) are left to the v4 / v3 kernel.
+//
+// No tensor cores: the path is an integer histogram.
+#include "qb_dev.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace qb {
+
+constexpr int kPW = kPeriodWarps;
+constexpr int kPThreads = kPW * 32;
+constexpr uint32_t kPHist0 = 0x10000u;             // shared address of histogram block 0
+constexpr uint32_t kPBlockStride = 0x10000u;       // block b at kPHist0 + b * 64 KiB (its address has byte 1 == 0)
+constexpr uint32_t kPBlockBytes = kHistRows * 256u;  // 192 rows x 256 B = 48 KiB
+constexpr uint32_t kPQueue = 256;                  // anchor-hit entries per warp (u16 word indices)
+constexpr uint32_t kPPad = 16;                     // readable bytes behind a staged buffer (confirmation loads)
+constexpr uint32_t kPMaxStages = 4;
+constexpr uint32_t kPMaxRpt = 64;                  // reads per tile
+// offsets inside a warp block (multiples of 16)
+constexpr uint32_t kPoBar = 0;                     // kPMaxStages mbarriers
+constexpr uint32_t kPoFhit = 32;                   // first-hit position per read of the tile (-a)
+constexpr uint32_t kPoQueue = kPoFhit + kPMaxRpt * 4u;
+__host__ __device__ inline uint32_t pblock_hdr(int adapters) { return adapters ? kPoQueue + kPQueue * 2u : kPoFhit; }
+
+struct PArgs {
+  const uint8_t *seq, *qual;  // first byte of the first read (16-byte aligned)
+  Accum a;
+  AdapterSet ad;
+  PeriodPlan plan;
+  uint32_t n_tiles;
+  uint32_t inc_lo, inc_hi;      // 1 and 65536, passed as arguments so that the atomics stay plain ATOMS.ADD (with
+                                // a known 1 the compiler emits the warp-aggregating ATOMS.POPC.INC form)
+  uint8_t slot[kPeriodMaxLen];  // position -> block << 7 | u32 column of its row (0..63); u16 half = position & 1
+};
+
+__device__ __forceinline__ uint32_t p_slot_addr(uint32_t e) {
+  return kPHist0 + (e >> 7) * kPBlockStride + ((e & 63u) << 2);
+}
+
+// inverted 2-bit codes of 4 bases in bits 7:6 of each byte (see key_bytes, qb_dev.cuh)
+__device__ __forceinline__ uint32_t p_ncodes(uint32_t sw, const KeyConsts &c) {
+  const uint32_t n_cg = lop3<0x6A>(sw, c.m5b, c.x43) + c.a7f;
+  const uint32_t n_g = lop3<0x6A>(sw, c.m1f, c.x07) + c.a3f;
+  const uint32_t n_t = lop3<0x6A>(sw, c.m1f, c.x14) + c.a3f;
+  return lop3<0xE4>(n_cg, n_g & n_t, c.m80);
+}
+
+// rare path: the 4 bases of a word with an out-of-window quality byte, counted one by one in global memory
+// (their key bytes were moved to the dummy row).  b0 = byte of the word inside its period.
+static __device__ __noinline__ uint32_t p_exact_word(uint32_t sw, uint32_t qw, uint32_t b0, uint32_t len, const Accum a) {
+  uint32_t n_invalid = 0;
+  for (uint32_t j = 0; j < 4; j++) {
+    const uint32_t p = (b0 + j) % len;
+    unsigned long long *row = a.rows + (size_t)p * kRow;
+    atomicAdd(&row[kColContent + base_code((sw >> (8 * j)) & 0xFFu)], 1ull);
+    const int sc = (int)((qw >> (8 * j)) & 0xFFu) - 33;
+    if (sc >= 0 && sc < 91)
+      atomicAdd(&row[sc], 1ull);
+    else
+      n_invalid++;
+  }
+  return n_invalid;
+}
+
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+
+template <bool kAd, int kS>
+__global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_constant__ PArgs args) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const PeriodPlan &P = args.plan;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t smem_s = smem_u32(smem);
+  constexpr uint32_t kFull = 0xffffffffu;
+
+  if (smem_s != P.smem_base) {  // the histogram must sit at its fixed shared address: fail loudly, count nothing
+    if (tid == 0) atomicAdd(&args.a.counters[kCntError], 1ull);
+    return;
+  }
+  auto gen = [&](uint32_t shared_addr) -> uint8_t * { return smem + (shared_addr - smem_s); };
+
+  const uint32_t len = P.len, wp = P.wp, pbytes = P.wp * 4u, ppt = P.ppt, rpt = P.reads_per_tile;
+  const uint32_t tb = P.tile_bytes, buf = P.tile_bytes + kPPad, stages = P.stages, nblocks = P.nblocks;
+  const uint32_t last = wp - 32u * (uint32_t)(kS - 1);  // active lanes of the last step (1..32)
+
+  // ---- this warp's block ----
+  uint32_t wb_s;
+  {
+    uint32_t w = warp;
+    if (w < P.region_n[0])
+      wb_s = P.region_s[0] + w * P.wblock;
+    else if ((w -= P.region_n[0]) < P.region_n[1])
+      wb_s = P.region_s[1] + w * P.wblock;
+    else
+      wb_s = P.region_s[2] + (w - P.region_n[1]) * P.wblock;
+  }
+  const uint32_t ring_s = wb_s + pblock_hdr(kAd);  // stage s: bases at ring_s + 2 s buf, quality bytes + buf
+  const uint32_t fhit_s = wb_s + kPoFhit, q_s = wb_s + kPoQueue;
+  const uint32_t kmerhist_s = P.kmerhist_s, exact_s = P.exact_s;
+
+  // ---- prologue: zero the histograms, load the adapter tables, init barriers ----
+  auto clear_counters = [&]() {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint32_t b = 0; b < nblocks; b++) {
+      uint4 *h4 = reinterpret_cast<uint4 *>(gen(kPHist0 + b * kPBlockStride));
+      for (uint32_t i = tid; i < kPBlockBytes / 16u; i += kPThreads) h4[i] = z;
+    }
+    if (kAd) {
+      uint32_t *kh = reinterpret_cast<uint32_t *>(gen(kmerhist_s));
+      for (uint32_t i = tid; i <= len; i += kPThreads) kh[i] = 0;
+    }
+  };
+  clear_counters();
+  if (kAd) {
+    uint32_t *af = reinterpret_cast<uint32_t *>(gen(P.afilt_s));
+    for (uint32_t i = tid; i < kAnchorWords * kAnchorCopies; i += kPThreads) af[i] = args.ad.anchor[i / kAnchorCopies];
+    uint32_t *ex = reinterpret_cast<uint32_t *>(gen(exact_s));
+    if (args.ad.exact)
+      for (uint32_t i = tid; i < kExactSlots; i += kPThreads) ex[i] = args.ad.exact[i];
+    uint32_t *fh = reinterpret_cast<uint32_t *>(gen(fhit_s));
+    for (uint32_t i = lane; i < kPMaxRpt; i += 32u) fh[i] = kNoHit;
+  }
+  if (lane == 0) {
+    for (uint32_t s = 0; s < stages; s++) mbar_init(reinterpret_cast<uint64_t *>(gen(wb_s + kPoBar + 8u * s)), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const uint32_t n_tiles = args.n_tiles;
+  if (blockIdx.x == 0 && tid == 0) {  // quack.c:219-220: every read has length l
+    const unsigned long long n = (unsigned long long)n_tiles * rpt;
+    atomicAdd(&args.a.counters[kCntReads], n);
+    atomicAdd(&args.a.rows[(size_t)(len - 1u) * kRow + kColLength], n);
+  }
+  __syncthreads();
+
+  const uint32_t G = gridDim.x * kPW;
+  const uint32_t g0 = blockIdx.x * kPW;
+  const uint32_t iters = n_tiles > g0 ? (n_tiles - g0 + G - 1u) / G : 0u;  // the same for every warp of the CTA
+  uint32_t epoch = 65535u / ((uint32_t)kPW * rpt);  // iterations between two flushes of the u16 counters
+  if (epoch == 0) epoch = 1;
+
+  const KeyConsts kc(P.qbase);
+  const uint32_t inc_lo = args.inc_lo, inc_hi = args.inc_hi;
+  // this lane's counter columns: word 32 s + lane of a period holds positions (4 (32 s + lane) + j) mod l
+  uint32_t col[kS][4];
+#pragma unroll
+  for (int s = 0; s < kS; s++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) col[s][j] = p_slot_addr(args.slot[(4u * (32u * s + lane) + j) % len]);
+  const uint32_t afilt_or = P.afilt_s | ((lane >> 2) * 4u);  // this lane's copy of the anchor map (8 copies, 32-byte rows)
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t nxt = (lane + 1u) & 31u;
+  const uint32_t len_magic = 0xFFFFFFFFu / len + 1u;  // floor(b / len) = umulhi(b, len_magic) for b < 2^24
+  long long n_invalid = 0;
+
+  auto flush = [&]() {  // all warps are behind a barrier
+    for (uint32_t pos = tid; pos < len; pos += kPThreads) {
+      const uint32_t base = p_slot_addr(args.slot[pos]);
+      const uint32_t sh = (pos & 1u) * 16u;
+      unsigned long long *row = args.a.rows + (size_t)pos * kRow;
+      uint32_t cc[4] = {0, 0, 0, 0};
+      for (uint32_t sp = 0; sp < kScoreBins; sp++) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (uint32_t c = 0; c < 4u; c++) {  // row = score << 2 | code
+          const uint32_t v = (lds_u32(base + ((sp << 2 | c) << 8)) >> sh) & 0xFFFFu;
+          cc[c] += v;
+          tot += v;
+        }
+        if (tot) {
+          const int sc = (int)(sp + P.qbase) - 33;
+          if (sc >= 0 && sc < 91)
+            atomicAdd(&row[sc], (unsigned long long)tot);
+          else
+            n_invalid += tot;
+        }
+      }
+#pragma unroll
+      for (uint32_t c = 0; c < 4u; c++)
+        if (cc[c]) atomicAdd(&row[kColContent + c], (unsigned long long)cc[c]);
+      if (kAd) {
+        const uint32_t kcnt = lds_u32(kmerhist_s + pos * 4u);
+        if (kcnt) atomicAdd(&row[kColKmer], (unsigned long long)kcnt);
+      }
+    }
+  };
+
+  // Start the bulk copies of tile t into stage s.  The whole warp calls this once it is done with the stage.
+  auto issue = [&](uint32_t s, uint32_t t) {
+    __syncwarp();  // every lane is done with the buffer's old contents
+    if (lane == 0) {
+      const uint32_t bar_s = wb_s + kPoBar + 8u * s;
+      const uint32_t dst = ring_s + 2u * s * buf;
+      const size_t off = (size_t)t * tb;
+      // the TMA (async proxy) write must be ordered behind the generic-proxy accesses to the buffer
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive_expect_tx_s(bar_s, 2u * tb);
+      bulk_g2s_s(dst, args.seq + off, tb, bar_s);
+      bulk_g2s_s(dst + buf, args.qual + off, tb, bar_s);
+    }
+  };
+
+  // ---- -a: confirm the queued anchor hits of this tile (quack.c:210-217) ----
+  // Entry = word index w in the tile: the 7-mer starting at base 4 w passed the filter.  The windows that
+  // contain it start at 4 w - 3 .. 4 w.  One lane per entry: it decodes the 16 bases of words w - 1 .. w + 2
+  // once (aligned loads, the SWAR code of phase A) and tests the four 10-mers against the exact key set.  A
+  // window whose 10 bases lie inside one read lowers that read's first-hit position; a hit that ends on the
+  // last base of its read is dropped (it can only be the first hit if there is no other, and then the
+  // reference counts nothing).
+  auto confirm = [&](uint32_t seq_s, uint32_t qn) {
+    __syncwarp();
+    for (uint32_t e0 = 0; e0 < qn; e0 += 32u) {
+      const uint32_t e = e0 + lane;
+      if (e < qn) {
+        const uint32_t b0 = lds_u16(q_s + 2u * e) * 4u;  // tile byte of the anchor's first base
+        const uint32_t n = __umulhi(b0, len_magic), p0 = b0 - n * len;  // its read in the tile, its position
+        // windows start at p0 - o, o = 0..3: inside the read iff p0 >= o and p0 - o + 10 < len
+        if (p0 + 10u < len + 3u && p0 + 6u < lds_u32(fhit_s + 4u * n)) {
+          const uint32_t A = seq_s + b0;
+          const uint32_t cm = gather_codes(~p_ncodes(lds_u32(A - 4u), kc)) >> 24;  // bases -4..-1 (first word of a tile: unused)
+          const uint32_t c0 = gather_codes(~p_ncodes(lds_u32(A), kc)) >> 24;
+          const uint32_t c1 = gather_codes(~p_ncodes(lds_u32(A + 4u), kc)) >> 24;
+          const uint32_t c2 = gather_codes(~p_ncodes(lds_u32(A + 8u), kc)) >> 24;
+          // bases -3 .. 12, 2 bits each, first base least significant
+          const uint32_t ctx = (cm >> 2) | (c0 << 6) | (c1 << 14) | (c2 << 22);
+#pragma unroll
+          for (uint32_t o = 0; o < 4u; o++) {  // ascending window start: o = 3 first
+            const uint32_t oo = 3u - o;        // window starts oo bases before the anchor
+            if (p0 >= oo && p0 - oo + 10u < len) {
+              const uint32_t key = (ctx >> (2u * o)) & 0xFFFFFu;
+              bool member;
+              if (args.ad.exact)
+                member = lds_u32(exact_s + exact_off1(key)) == key || lds_u32(exact_s + exact_off2(key)) == key;
+              else
+                member = (args.ad.bitmap[key >> 5] >> (key & 31u)) & 1u;
+              if (member) atomicMin(shared_ptr<uint32_t>(fhit_s) + n, p0 - oo + 9u);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  };
+
+  const uint32_t g = g0 + warp;
+  for (uint32_t s = 0; s + 1u < stages; s++)
+    if (g + s * G < n_tiles) issue(s, g + s * G);
+
+  uint32_t to_flush = epoch;
+  uint32_t tile = g;
+  uint32_t st = 0, phase = 0;  // stage of this iteration, its mbarrier phase parity
+  for (uint32_t it = 0; it < iters; ++it, tile += G) {
+    if (tile < n_tiles) {
+      {  // keep stages - 1 tiles in flight: the stage freed by the previous iteration takes tile + (stages - 1) G
+        const uint32_t t2 = tile + (stages - 1u) * G;
+        const uint32_t s2 = st == 0 ? stages - 1u : st - 1u;
+        if (t2 < n_tiles) issue(s2, t2);
+      }
+      mbar_wait(wb_s + kPoBar + 8u * st, phase);
+      const uint32_t seq_s = ring_s + 2u * st * buf;
+      uint32_t qn = 0;  // queued anchor hits
+
+      for (uint32_t pp = 0; pp < ppt; pp++) {
+        const uint32_t a0 = seq_s + pp * pbytes + lane * 4u;
+        uint32_t sw[kS], qw[kS], K[kS], nc[kS];
+        uint32_t bad = 0;
+#pragma unroll
+        for (int s = 0; s < kS; s++) {
+          const bool act = s < kS - 1 || lane < last;
+          sw[s] = 0x41414141u;  // lanes without a word: 'A' with the lowest score, not counted
+          qw[s] = kc.qsub;
+          if (act) {
+            sw[s] = lds_u32(a0 + 128u * s);
+            qw[s] = lds_u32(a0 + buf + 128u * s);
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < kS; s++) K[s] = key_bytes(sw[s], qw[s], kc, nc[s], bad);
+        if (bad & 0xC0C0C0C0u) {  // a quality byte outside the counted window: exact path for those words
+#pragma unroll
+          for (int s = 0; s < kS; s++)
+            if (word_bad(qw[s], kc.qsub)) {
+              K[s] = key_bytes_bad(nc[s]);
+              n_invalid += p_exact_word(sw[s], qw[s], 4u * (32u * s + lane), len, args.a);
+            }
+        }
+        if (kAd) {
+          if (qn + 32u * kS > kPQueue) {  // keep room for this period's hits
+            confirm(seq_s, qn);
+            qn = 0;
+          }
+          uint32_t gc[kS], r[kS];
+#pragma unroll
+          for (int s = 0; s < kS; s++) gc[s] = (K[s] & 0x03030303u) * 0x01041040u;  // top byte: the word's 4 codes
+#pragma unroll
+          for (int s = 0; s < kS; s++) r[s] = __shfl_sync(kFull, gc[s], nxt);
+#pragma unroll
+          for (int s = 0; s < kS; s++) {
+            const bool act = s < kS - 1 || lane < last;
+            const uint32_t nx = lane < 31u ? r[s] : (s + 1 < kS ? r[s + 1] : 0u);  // codes of the next word
+            const uint32_t an = __byte_perm(gc[s], nx, 0x7773);  // bits 13:0 = the 7-mer starting at this word
+            const uint32_t fw = lds_u32((an & 0x3FE0u) | afilt_or);
+            const bool hit = act && (__funnelshift_r(fw, 0u, an) & 1u);
+            const uint32_t bal = __ballot_sync(kFull, hit);
+            if (bal) {
+              if (hit) sts_u16(q_s + 2u * (qn + __popc(bal & lt_mask)), pp * wp + 32u * s + lane);
+              qn += __popc(bal);
+            }
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < kS; s++) {
+          const bool act = s < kS - 1 || lane < last;
+          if (act) {
+            red_shared_add<0u>(__byte_perm(K[s], col[s][0], 0x7604), inc_lo);
+            red_shared_add<0u>(__byte_perm(K[s], col[s][1], 0x7614), inc_hi);
+            red_shared_add<0u>(__byte_perm(K[s], col[s][2], 0x7624), inc_lo);
+            red_shared_add<0u>(__byte_perm(K[s], col[s][3], 0x7634), inc_hi);
+          }
+        }
+      }
+
+      if (kAd) {
+        if (qn) confirm(seq_s, qn);
+        // settle the first hits of the tile's reads: kmer_count[p + 1]++ (quack.c:215-216)
+        for (uint32_t n = lane; n < rpt; n += 32u) {
+          const uint32_t f = lds_u32(fhit_s + 4u * n);
+          if (f != kNoHit) {
+            red_shared_add<0u>(kmerhist_s + (f + 1u) * 4u, 1u);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(fhit_s + 4u * n), "r"(kNoHit) : "memory");
+          }
+        }
+      }
+      if (++st == stages) st = 0, phase ^= 1u;
+    }
+    if (--to_flush == 0u && it + 1u < iters) {  // u16 counters: flush before any bin can wrap
+      to_flush = epoch;
+      __syncthreads();
+      flush();
+      __syncthreads();
+      clear_counters();
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  flush();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_invalid += __shfl_xor_sync(kFull, n_invalid, o);
+  if (lane == 0 && n_invalid) atomicAdd(&args.a.counters[kCntInvalidQual], (unsigned long long)n_invalid);
+}
+
+// ------------------------------------------------------------------------------------------
+// plan: period / tile geometry and shared-memory map
+// ------------------------------------------------------------------------------------------
+
+static uint32_t gcd_u32(uint32_t a, uint32_t b) {
+  while (b) {
+    const uint32_t t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+PeriodPlan period_plan(uint32_t l, uint32_t first_offset, int adapters, int sm_count, uint32_t smem_optin,
+                       uint32_t smem_reserved, uint32_t qbase) {
+  PeriodPlan p;
+  memset(&p, 0, sizeof p);
+  if (l < 32u || l > kPeriodMaxLen || (l & 1u) || (first_offset & 15u)) return p;
+  p.len = l;
+  p.qbase = qbase;
+  p.nblocks = l > 128u ? 2u : 1u;
+  p.smem_base = smem_reserved;
+  const uint32_t end = smem_reserved + smem_optin;
+  // free address ranges around the histogram blocks (only 192 of a block's 256 rows exist)
+  struct Gap {
+    uint32_t a, b;
+  } gap[3];
+  gap[0] = {smem_reserved, kPHist0};
+  if (p.nblocks == 2u) {
+    gap[1] = {kPHist0 + kPBlockBytes, kPHist0 + kPBlockStride};
+    gap[2] = {kPHist0 + kPBlockStride + kPBlockBytes, end};
+  } else {
+    gap[1] = {kPHist0 + kPBlockBytes, kPHist0 + kPBlockBytes + kAnchorSmemBytes};
+    gap[2] = {kPHist0 + kPBlockBytes + kAnchorSmemBytes, end};
+  }
+  for (int g = 0; g < 3; g++)
+    if (gap[g].a > gap[g].b || gap[g].b > end) return p;
+  auto take = [&](int g, uint32_t bytes) -> uint32_t {  // 0: does not fit
+    bytes = (bytes + 15u) & ~15u;
+    if (gap[g].b - gap[g].a < bytes) return 0;
+    const uint32_t at = gap[g].a;
+    gap[g].a += bytes;
+    return at;
+  };
+  if (adapters) {
+    if (!(p.afilt_s = take(1, kAnchorSmemBytes)) || (p.afilt_s & (kAnchorSmemBytes - 1u))) return p;  // 16 KiB-aligned
+    if (!(p.exact_s = take(2, kExactSlots * 4u))) return p;
+    if (!(p.kmerhist_s = take(2, (l + 1u) * 4u))) return p;
+  }
+  const uint32_t hdr = pblock_hdr(adapters);
+  uint32_t want = 3, target = 1024u;
+  if (const char *e = getenv("QB_PT_STAGES")) want = (uint32_t)atoi(e);  // tuning hooks
+  if (const char *e = getenv("QB_PT_BYTES")) target = (uint32_t)atoi(e);
+  if (want < 2u) want = 2u;
+  if (want > kPMaxStages) want = kPMaxStages;
+
+  // Reads per period: a multiple of k0 (so that the period is a whole number of words) with 3..5 warp steps;
+  // candidates in order of how well they fill the last step.  Periods per tile: tile bytes a multiple of 16,
+  // reads per tile a multiple of 4 (the rest of the batch goes to a kernel that loads 4 offsets at a time),
+  // about `target` bytes.  The first candidate whose kPW warp blocks fit the gaps wins.
+  const uint32_t k0 = (l & 3u) ? 2u : 1u;
+  bool used[64] = {false};
+  for (;;) {
+    uint32_t bk = 0;
+    double best = 0;
+    for (uint32_t k = k0; k * l / 4u <= 160u && k < 64u; k += k0) {
+      const uint32_t wp = k * l / 4u, steps = (wp + 31u) / 32u;
+      if (used[k] || steps < 3u || steps > 5u) continue;
+      const double eff = (double)wp / (32.0 * steps);
+      if (eff > best + 1e-9) best = eff, bk = k;
+    }
+    if (!bk) return p;
+    used[bk] = true;
+    const uint32_t wp = bk * l / 4u, pb = wp * 4u;
+    uint32_t ppt0 = 16u / gcd_u32(pb, 16u);
+    while ((ppt0 * bk) & 3u) ppt0 *= 2u;
+    if (ppt0 * bk > kPMaxRpt) continue;
+    uint32_t ppt = ppt0;
+    while (ppt * pb < target && (ppt + ppt0) * bk <= kPMaxRpt) ppt += ppt0;
+    for (; ppt >= ppt0 && !p.ok; ppt -= ppt0) {
+      if (ppt * wp > 65535u) continue;
+      for (uint32_t stages = want; stages >= 2u && !p.ok; stages--) {
+        const uint32_t wblock = hdr + stages * 2u * (ppt * pb + kPPad);
+        uint32_t fit = 0;
+        for (int g = 0; g < 3; g++) fit += (gap[g].b - gap[g].a) / wblock;
+        if (fit < (uint32_t)kPW) continue;
+        p.k = bk, p.wp = wp, p.steps = (wp + 31u) / 32u;
+        p.ppt = ppt, p.tile_bytes = ppt * pb, p.reads_per_tile = ppt * bk;
+        p.stages = stages, p.wblock = wblock;
+        p.ok = 1;
+      }
+    }
+    if (p.ok) break;
+  }
+  uint32_t left = (uint32_t)kPW;
+  for (int g = 0; g < 3; g++) {
+    uint32_t n = (gap[g].b - gap[g].a) / p.wblock;
+    if (n > left) n = left;
+    p.region_s[g] = gap[g].a;
+    p.region_n[g] = n;
+    left -= n;
+  }
+  p.smem_bytes = smem_optin;
+  p.grid = (uint32_t)sm_count;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// Position -> u16 slot of a histogram row.
+// The half-word is position & 1 (l is even, so the j-th byte of a word always holds positions of one parity
+// and the increments are compile-time constants); odd position p shares the u32 column of p - 1.  The column
+// of an even position is free, and it decides the BANK its 188 counters live in.  The 32 lanes of warp step
+// (s, j) update positions (4 (32 s + lane) + j) mod l: a conflict-free step needs 32 different banks.  All
+// steps cannot be conflict-free (a bank holds at most 2 * nblocks even positions, and a position occurs in k
+// steps), so the solver looks for the smallest set of steps to give up and colours the conflict graph of the
+// others (DSATUR with a capacity per bank).  For 4 x 150 bp: 3 of 10 steps cost two wavefronts instead of
+// all 10 with the natural layout (column = position / 4).
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct SlotSolver {
+  uint32_t E = 0, cap = 0, nsets = 0;
+  uint8_t set[16][32];
+  uint32_t set_n[16];
+  uint64_t rng = 0x9E3779B97F4A7C15ull;
+  uint32_t rnd() {
+    rng ^= rng << 13, rng ^= rng >> 7, rng ^= rng << 17;
+    return (uint32_t)(rng >> 32);
+  }
+  // colours E positions with 32 banks so that the sets in `hard` have no repeated bank
+  bool colour(uint32_t hard, uint8_t *bank) {
+    static thread_local uint8_t adj[128][128];
+    for (uint32_t a = 0; a < E; a++) memset(adj[a], 0, E);
+    for (uint32_t si = 0; si < nsets; si++)
+      if (hard >> si & 1u)
+        for (uint32_t a = 0; a < set_n[si]; a++)
+          for (uint32_t b = 0; b < set_n[si]; b++)
+            if (set[si][a] != set[si][b]) adj[set[si][a]][set[si][b]] = 1;
+    uint32_t cnt[32] = {0};
+    uint32_t usedmask[128];
+    bool done[128];
+    for (uint32_t a = 0; a < E; a++) usedmask[a] = 0, done[a] = false;
+    for (uint32_t step = 0; step < E; step++) {
+      int bp = -1;
+      uint64_t bkey = 0;
+      for (uint32_t a = 0; a < E; a++) {
+        if (done[a]) continue;
+        const uint64_t key = ((uint64_t)__builtin_popcount(usedmask[a]) << 40) | (uint64_t)(rnd() & 0xFFFFFFu);
+        if (bp < 0 || key > bkey) bp = (int)a, bkey = key;
+      }
+      int bc = -1;
+      uint32_t bcnt = 0;
+      for (uint32_t c = 0; c < 32; c++) {
+        if ((usedmask[bp] >> c & 1u) || cnt[c] >= cap) continue;
+        if (bc < 0 || cnt[c] < bcnt || (cnt[c] == bcnt && (rnd() & 1u))) bc = (int)c, bcnt = cnt[c];
+      }
+      if (bc < 0) return false;
+      bank[bp] = (uint8_t)bc;
+      cnt[bc]++;
+      done[bp] = true;
+      for (uint32_t a = 0; a < E; a++)
+        if (adj[bp][a]) usedmask[a] |= 1u << bc;
+    }
+    return true;
+  }
+  uint32_t cost(const uint8_t *bank) const {
+    uint32_t tot = 0;
+    for (uint32_t si = 0; si < nsets; si++) {
+      uint32_t c[32] = {0}, m = 0;
+      for (uint32_t a = 0; a < set_n[si]; a++) m = ++c[bank[set[si][a]]] > m ? c[bank[set[si][a]]] : m;
+      tot += m;
+    }
+    return tot;
+  }
+};
+
+struct SlotCache {  // the last table solved for each read length
+  std::mutex mu;
+  uint8_t slot[kPeriodMaxLen + 1][kPeriodMaxLen];
+  uint8_t k[kPeriodMaxLen + 1] = {};  // reads per period the table was solved for (0: none)
+};
+
+}  // namespace
+
+static void period_slots(const PeriodPlan &p, uint8_t *slot) {
+  const uint32_t l = p.len, E = l / 2u, cap = 2u * p.nblocks;
+  // natural layout (also the fallback): positions 4 c .. 4 c + 3 of a block in bank c
+  for (uint32_t pos = 0; pos < kPeriodMaxLen; pos++) {
+    const uint32_t blk = pos >> 7, q = pos & 127u;
+    slot[pos] = (uint8_t)(blk << 7 | ((q >> 2) + 32u * ((q >> 1) & 1u)));
+  }
+  if (getenv("QB_PT_NATURAL")) return;  // tuning hook
+  static SlotCache *cache = new SlotCache();
+  std::lock_guard<std::mutex> lk(cache->mu);
+  if (cache->k[l] == p.k) {
+    memcpy(slot, cache->slot[l], kPeriodMaxLen);
+    return;
+  }
+  SlotSolver sv;
+  sv.E = E, sv.cap = cap;
+  for (uint32_t s = 0; s < p.steps; s++)
+    for (uint32_t j = 0; j < 4u; j += 2u) {
+      uint32_t n = 0;
+      for (uint32_t i = 0; i < 32u && 32u * s + i < p.wp; i++) sv.set[sv.nsets][n++] = (uint8_t)(((4u * (32u * s + i) + j) % l) / 2u);
+      sv.set_n[sv.nsets++] = n;
+    }
+  uint8_t bank[128], best_bank[128];
+  for (uint32_t e = 0; e < E; e++) best_bank[e] = (uint8_t)(slot[2u * e] & 31u);
+  uint32_t best = sv.cost(best_bank);
+  uint32_t lower = 0;
+  for (uint32_t si = 0; si < sv.nsets; si++) {  // a position that occurs twice in a step costs a wavefront anyway
+    uint32_t c[128] = {0}, m = 1;
+    for (uint32_t a = 0; a < sv.set_n[si]; a++) m = ++c[sv.set[si][a]] > m ? c[sv.set[si][a]] : m;
+    lower += m;
+  }
+  const uint32_t all = (1u << sv.nsets) - 1u;
+  for (uint32_t nsac = 0; nsac <= 4u && best > lower + nsac; nsac++) {
+    for (uint32_t sac = 0; sac <= all && best > lower + nsac; sac++) {
+      if ((uint32_t)__builtin_popcount(sac) != nsac) continue;
+      for (int t = 0; t < 4; t++)
+        if (sv.colour(all & ~sac, bank)) {
+          const uint32_t c = sv.cost(bank);
+          if (c < best) best = c, memcpy(best_bank, bank, E);
+          break;
+        }
+    }
+  }
+  // banks -> columns: the i-th even position of bank b takes column b (i = 0), b + 32 (1), then block 1
+  uint32_t cnt[32] = {0};
+  bool ok = true;
+  for (uint32_t e = 0; e < E && ok; e++) {
+    const uint32_t b = best_bank[e], i = cnt[b]++;
+    if (i >= cap) ok = false;
+    const uint8_t v = (uint8_t)((i >> 1) << 7 | (b + 32u * (i & 1u)));
+    slot[2u * e] = v, slot[2u * e + 1u] = v;
+  }
+  if (!ok)  // cannot happen (the natural layout respects the capacity); keep the natural layout
+    for (uint32_t pos = 0; pos < kPeriodMaxLen; pos++) {
+      const uint32_t blk = pos >> 7, q = pos & 127u;
+      slot[pos] = (uint8_t)(blk << 7 | ((q >> 2) + 32u * ((q >> 1) & 1u)));
+    }
+  memcpy(cache->slot[l], slot, kPeriodMaxLen);
+  cache->k[l] = (uint8_t)p.k;
+}
+
+template <bool kAd>
+static cudaError_t period_launch_steps(const PArgs &args, uint32_t grid, cudaStream_t stream) {
+  const uint32_t smem = args.plan.smem_bytes;
+  switch (args.plan.steps) {
+    case 3: period_kernel<kAd, 3><<<grid, kPThreads, smem, stream>>>(args); break;
+    case 4: period_kernel<kAd, 4><<<grid, kPThreads, smem, stream>>>(args); break;
+    case 5: period_kernel<kAd, 5><<<grid, kPThreads, smem, stream>>>(args); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t period_configure() {
+  cudaError_t e;
+#define QB_PCFG(A, S)                                                                                               \
+  if ((e = cudaFuncSetAttribute(period_kernel<A, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+  QB_PCFG(false, 3) QB_PCFG(false, 4) QB_PCFG(false, 5) QB_PCFG(true, 3) QB_PCFG(true, 4) QB_PCFG(true, 5)
+#undef QB_PCFG
+  return cudaSuccess;
+}
+
+cudaError_t launch_period(const BatchView &b, const Accum &a, const AdapterSet &ad, const PeriodPlan &plan,
+                          cudaStream_t stream, uint32_t *n_main_out) {
+  *n_main_out = 0;
+  if (!plan.ok || b.uniform_len != plan.len) return cudaErrorInvalidValue;
+  const uint32_t n_tiles = b.n_reads / plan.reads_per_tile;
+  if (n_tiles == 0) return cudaSuccess;
+  PArgs args;
+  memset(&args, 0, sizeof args);
+  args.seq = b.seq + b.first_offset;
+  args.qual = b.qual + b.first_offset;
+  args.a = a;
+  args.ad = ad;
+  args.plan = plan;
+  args.n_tiles = n_tiles;
+  args.inc_lo = 1u, args.inc_hi = 0x10000u;
+  period_slots(plan, args.slot);
+  uint32_t grid = (n_tiles + (uint32_t)kPW - 1u) / (uint32_t)kPW;
+  if (grid > plan.grid) grid = plan.grid;
+  if (const char *g = getenv("QB_FUSED_GRID")) {  // test hook: few CTAs exercise the u16 flush path
+    const uint32_t v = (uint32_t)atoi(g);
+    if (v >= 1 && v < grid) grid = v;
+  }
+  const cudaError_t e = ad.enabled ? period_launch_steps<true>(args, grid, stream) : period_launch_steps<false>(args, grid, stream);
+  if (e == cudaSuccess) *n_main_out = n_tiles * plan.reads_per_tile;
+  return e;
+}
+
+}  // namespace qb
+
+// tools / tests: the geometry and the counter layout the period kernel would use for reads of one length on a
+// B200 (227 KiB of shared memory per block, 1 KiB reserved).  Needs no GPU.  Returns 0 if the kernel takes
+// such batches, -1 otherwise.  info[0..5] = reads per period, words per period, steps, periods per tile,
+// reads per tile, stages; slot[p] = block << 7 | u32 column of position p.
+extern "C" int qb_period_layout(uint32_t read_len, int adapters, uint32_t info[6], uint8_t slot[256]) {
+  const qb::PeriodPlan p = qb::period_plan(read_len, 0, adapters, 148, 232448u - 1024u, 1024u, 33u);
+  if (!p.ok) return -1;
+  if (info) info[0] = p.k, info[1] = p.wp, info[2] = p.steps, info[3] = p.ppt, info[4] = p.reads_per_tile, info[5] = p.stages;
+  if (slot) qb::period_slots(p, slot);
+  return 0;
+}
+

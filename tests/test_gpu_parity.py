@@ -29,6 +29,81 @@ def keys(table):
     return table.keys()
 
 
+# ---- period kernel (v5): uniform-length batches only ----
+PERIOD_LENS = [32, 36, 50, 64, 76, 100, 126, 128, 130, 150, 200, 248, 256]
+
+
+@pytest.mark.parametrize("l", PERIOD_LENS)
+@pytest.mark.parametrize("ad", [False, True], ids=["noad", "ad"])
+@pytest.mark.parametrize("resident", [False, True], ids=["stream", "resident"])
+def test_period_uniform(l, ad, resident, table, keys):
+    """Every supported period geometry (3..5 steps, 1 and 2 histogram blocks), a read count that leaves a
+    remainder for the other kernels, planted adapters, N bases."""
+    batch = util.random_batch(1000 + l, 20011, l, l, plant=0.3)
+    got = run_gpu(batch, 256, keys if ad else None, capi.KERNEL_PERIOD, resident=resident)
+    util.assert_same(got, po.accumulate_batch(*batch, table if ad else None), f"period {l}")
+
+
+@pytest.mark.parametrize("l", [100, 150])
+def test_period_all_byte_values(l, table, keys):
+    rng = np.random.default_rng(l)
+    n = 6000
+    seq = rng.integers(0, 256, size=n * l).astype(np.uint8)
+    qual = rng.integers(0, 256, size=n * l).astype(np.uint8)
+    off = (np.arange(n) * l).astype(np.uint32)
+    lens = np.full(n, l, dtype=np.uint32)
+    want = po.accumulate_batch(seq, qual, off, lens, table)
+    got = run_gpu((seq, qual, off, lens), 256, keys, capi.KERNEL_PERIOD)
+    util.assert_same(got, want, "period all bytes")
+    assert got.invalid == want.n_invalid_qual > 0
+
+
+@pytest.mark.parametrize("qlo,qhi", [(0, 90), (31, 71), (44, 49)], ids=["full", "phred64", "edge"])
+def test_period_score_ranges(qlo, qhi, table, keys):
+    batch = util.random_batch(78, 9000, 150, 150, qlo=qlo, qhi=qhi, plant=0.2)
+    got = run_gpu(batch, 150, keys, capi.KERNEL_PERIOD)
+    util.assert_same(got, po.accumulate_batch(*batch, table), f"period scores {qlo}-{qhi}")
+
+
+def test_period_adapter_every_position(table, keys):
+    """First-hit semantics with the hit planted at every position of a 150-bp read, a second adapter behind
+    it, hits ending on the last base, poly-A tails (many anchor hits per read: the queue overflows)."""
+    ad = b"AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT"
+    reads = []
+    l = 150
+    for rep in range(3):
+        for at in range(0, l):
+            s = bytearray((b"C" if rep != 1 else b"A") * l)
+            m = min(len(ad), l - at)
+            s[at: at + m] = ad[:m]
+            if at + 51 <= l:
+                s[at + 40: at + 40 + 11] = ad[:11]
+            reads.append((bytes(s), b"I" * l))
+    batch = util.pack(reads * 5)
+    got = run_gpu(batch, 150, keys, capi.KERNEL_PERIOD)
+    util.assert_same(got, po.accumulate_batch(*batch, table), "period adapter positions")
+
+
+def test_period_u16_flush(monkeypatch, table, keys):
+    """One CTA, > 65535 reads: the u16 counters are flushed in time."""
+    monkeypatch.setenv("QB_FUSED_GRID", "1")
+    l = 150
+    n = 150000
+    rng = np.random.default_rng(9)
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n * l)]
+    qual = np.full(n * l, 33 + 37, dtype=np.uint8)   # one score bin: every read hits the same counters
+    off = (np.arange(n) * l).astype(np.uint32)
+    lens = np.full(n, l, dtype=np.uint32)
+    got = run_gpu((seq, qual, off, lens), 150, keys, capi.KERNEL_PERIOD, resident=True)
+    util.assert_same(got, po.accumulate_batch(seq, qual, off, lens, table), "period flush")
+
+
+def test_period_rejects_ragged(keys):
+    batch = util.random_batch(3, 100, 100, 150)
+    with pytest.raises(capi.QbError):
+        run_gpu(batch, 150, keys, capi.KERNEL_PERIOD)
+
+
 WTILE_MAX_LEN = 192   # the warp-tile kernel's shared-memory histogram; longer batches take the fused kernel
 
 

@@ -13,7 +13,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import qb_testutil as util
 
 HBM = 6545.3
-KN = {capi.KERNEL_SIMPLE: "simple", capi.KERNEL_FUSED: "fused", capi.KERNEL_WTILE: "wtile"}
+KN = {capi.KERNEL_SIMPLE: "simple", capi.KERNEL_FUSED: "fused", capi.KERNEL_WTILE: "wtile", capi.KERNEL_PERIOD: "period",
+      capi.KERNEL_AUTO: "auto"}
 # QB_QUICK_KERNELS=3,2 restricts the sweep (default: wtile, fused, simple)
 KSEL = [int(k) for k in os.environ.get("QB_QUICK_KERNELS", "3,2,1").split(",")]
 
@@ -22,9 +23,14 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
     keys = np.concatenate([capi.adapter_record_keys(r) for r in util.adapter_records()])
     out = []
-    for lmin, lmax, cap in ((150, 150, 150), (35, 300, 304)):
+    shapes = ((150, 150, 150),) if os.environ.get("QB_QUICK_ONLY150") else ((150, 150, 150), (35, 300, 304))
+    if os.environ.get("QB_QUICK_LENS"):  # fixed-length shapes, e.g. 50,76,100
+        shapes = tuple((int(x), int(x), int(x)) for x in os.environ["QB_QUICK_LENS"].split(","))
+    for lmin, lmax, cap in shapes:
         for ad in (None, keys):
             for kernel in KSEL:
+                if kernel == capi.KERNEL_PERIOD and lmin != lmax:
+                    continue
                 nn = n if kernel != capi.KERNEL_SIMPLE else n // 8
                 with capi.Context(cap, adapter_keys=ad, kernel=kernel) as ctx:
                     b = ctx.generate(2, 1, 0, nn, lmin, lmax, 0.1)
@@ -36,12 +42,14 @@ def main():
                            "ms_avg": round(avg, 4), "ms_min": round(mn, 4), "Greads_s": round(nr / avg / 1e6, 3),
                            "Gbases_s": round(nb / avg / 1e6, 2), "GBps": round(alg / avg / 1e6, 1),
                            "frac_hbm": round(alg / avg / 1e6 / HBM, 4)}
-                    for k in ("QB_LIB", "QB_WT_READS"):
+                    for k in ("QB_LIB", "QB_WT_READS", "QB_PT_STAGES", "QB_PT_BYTES"):
                         if os.environ.get(k):
                             rec[k] = os.path.basename(os.environ[k])
                     print(json.dumps(rec), flush=True)
                     out.append(rec)
                     b.free()
+    if os.environ.get("QB_QUICK_ONLY150") or os.environ.get("QB_QUICK_LENS"):
+        return
     with capi.Context(150) as ctx:
         print(json.dumps({"h2d_GBps": round(ctx.measure_h2d(256 << 20, 5), 2)}), flush=True)
 
