@@ -39,15 +39,19 @@ constexpr int kPThreads = kPW * 32;
 constexpr uint32_t kPHist0 = 0x10000u;             // shared address of histogram block 0
 constexpr uint32_t kPBlockStride = 0x10000u;       // block b at kPHist0 + b * 64 KiB (its address has byte 1 == 0)
 constexpr uint32_t kPBlockBytes = kHistRows * 256u;  // 192 rows x 256 B = 48 KiB
-constexpr uint32_t kPQueue = 256;                  // anchor-hit entries per warp (u16 word indices)
+constexpr uint32_t kPBloomBits = 1u << 14;          // -a: one-hash Bloom filter of the 10-mer keys in front of the exact set
+constexpr uint32_t kPBloomMul = 0x9E3779B1u;
 constexpr uint32_t kPPad = 16;                     // readable bytes behind a staged buffer (confirmation loads)
 constexpr uint32_t kPMaxStages = 4;
 constexpr uint32_t kPMaxRpt = 64;                  // reads per tile
 // offsets inside a warp block (multiples of 16)
 constexpr uint32_t kPoBar = 0;                     // kPMaxStages mbarriers
-constexpr uint32_t kPoFhit = 32;                   // first-hit position per read of the tile (-a)
-constexpr uint32_t kPoQueue = kPoFhit + kPMaxRpt * 4u;
-__host__ __device__ inline uint32_t pblock_hdr(int adapters) { return adapters ? kPoQueue + kPQueue * 2u : kPoFhit; }
+constexpr uint32_t kPoCount = 32;                  // -a: number of queued anchor hits of the tile
+constexpr uint32_t kPoFhit = 48;                   // -a: first-hit position per read of the tile
+constexpr uint32_t kPoQueue = kPoFhit + kPMaxRpt * 4u;  // -a: one u16 word index per anchor hit, room for every word of a tile
+__host__ __device__ inline uint32_t pblock_hdr(int adapters, uint32_t tile_bytes) {
+  return adapters ? kPoQueue + ((tile_bytes / 2u + 15u) & ~15u) : kPoCount;
+}
 
 struct PArgs {
   const uint8_t *seq, *qual;  // first byte of the first read (16-byte aligned)
@@ -127,8 +131,9 @@ __global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_const
     else
       wb_s = P.region_s[2] + (w - P.region_n[1]) * P.wblock;
   }
-  const uint32_t ring_s = wb_s + pblock_hdr(kAd);  // stage s: bases at ring_s + 2 s buf, quality bytes + buf
-  const uint32_t fhit_s = wb_s + kPoFhit, q_s = wb_s + kPoQueue;
+  const uint32_t ring_s = wb_s + pblock_hdr(kAd, tb);  // stage s: bases at ring_s + 2 s buf, quality bytes + buf
+  const uint32_t fhit_s = wb_s + kPoFhit, q_s = wb_s + kPoQueue, qcount_s = wb_s + kPoCount;
+  const uint32_t bloom_s = P.bloom_s;
   const uint32_t kmerhist_s = P.kmerhist_s, exact_s = P.exact_s;
 
   // ---- prologue: zero the histograms, load the adapter tables, init barriers ----
@@ -152,6 +157,18 @@ __global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_const
       for (uint32_t i = tid; i < kExactSlots; i += kPThreads) ex[i] = args.ad.exact[i];
     uint32_t *fh = reinterpret_cast<uint32_t *>(gen(fhit_s));
     for (uint32_t i = lane; i < kPMaxRpt; i += 32u) fh[i] = kNoHit;
+    if (lane == 0) *reinterpret_cast<uint32_t *>(gen(qcount_s)) = 0;
+    uint32_t *bl = reinterpret_cast<uint32_t *>(gen(bloom_s));
+    for (uint32_t i = tid; i < kPBloomBits / 32u; i += kPThreads) bl[i] = args.ad.exact ? 0u : 0xFFFFFFFFu;
+    __syncthreads();
+    if (args.ad.exact)
+      for (uint32_t i = tid; i < kExactSlots; i += kPThreads) {
+        const uint32_t k = args.ad.exact[i];
+        if (k != kExactEmpty) {
+          const uint32_t h = (k * kPBloomMul) >> 18;
+          atomicOr(&bl[h >> 5], 1u << (h & 31u));
+        }
+      }
   }
   if (lane == 0) {
     for (uint32_t s = 0; s < stages; s++) mbar_init(reinterpret_cast<uint64_t *>(gen(wb_s + kPoBar + 8u * s)), 1);
@@ -180,7 +197,6 @@ __global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_const
 #pragma unroll
     for (int j = 0; j < 4; j++) col[s][j] = p_slot_addr(args.slot[(4u * (32u * s + lane) + j) % len]);
   const uint32_t afilt_or = P.afilt_s | ((lane >> 2) * 4u);  // this lane's copy of the anchor map (8 copies, 32-byte rows)
-  const uint32_t lt_mask = (1u << lane) - 1u;
   const uint32_t nxt = (lane + 1u) & 31u;
   const uint32_t len_magic = 0xFFFFFFFFu / len + 1u;  // floor(b / len) = umulhi(b, len_magic) for b < 2^24
   long long n_invalid = 0;
@@ -260,12 +276,15 @@ __global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_const
             const uint32_t oo = 3u - o;        // window starts oo bases before the anchor
             if (p0 >= oo && p0 - oo + 10u < len) {
               const uint32_t key = (ctx >> (2u * o)) & 0xFFFFFu;
-              bool member;
-              if (args.ad.exact)
-                member = lds_u32(exact_s + exact_off1(key)) == key || lds_u32(exact_s + exact_off2(key)) == key;
-              else
-                member = (args.ad.bitmap[key >> 5] >> (key & 31u)) & 1u;
-              if (member) atomicMin(shared_ptr<uint32_t>(fhit_s) + n, p0 - oo + 9u);
+              const uint32_t h = (key * kPBloomMul) >> 18;
+              if (__funnelshift_r(lds_u32(bloom_s + ((h >> 5) << 2)), 0u, h) & 1u) {  // 98 % of the non-members stop here
+                bool member;
+                if (args.ad.exact)
+                  member = lds_u32(exact_s + exact_off1(key)) == key || lds_u32(exact_s + exact_off2(key)) == key;
+                else
+                  member = (args.ad.bitmap[key >> 5] >> (key & 31u)) & 1u;
+                if (member) atomicMin(shared_ptr<uint32_t>(fhit_s) + n, p0 - oo + 9u);
+              }
             }
           }
         }
@@ -290,7 +309,7 @@ __global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_const
       }
       mbar_wait(wb_s + kPoBar + 8u * st, phase);
       const uint32_t seq_s = ring_s + 2u * st * buf;
-      uint32_t qn = 0;  // queued anchor hits
+      uint32_t hm = 0;  // -a: this lane's anchor hits of the tile, one bit per (period, step)
 
       for (uint32_t pp = 0; pp < ppt; pp++) {
         const uint32_t a0 = seq_s + pp * pbytes + lane * 4u;
@@ -317,11 +336,8 @@ __global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_const
             }
         }
         if (kAd) {
-          if (qn + 32u * kS > kPQueue) {  // keep room for this period's hits
-            confirm(seq_s, qn);
-            qn = 0;
-          }
           uint32_t gc[kS], r[kS];
+          hm <<= kS;
 #pragma unroll
           for (int s = 0; s < kS; s++) gc[s] = (K[s] & 0x03030303u) * 0x01041040u;  // top byte: the word's 4 codes
 #pragma unroll
@@ -332,12 +348,9 @@ __global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_const
             const uint32_t nx = lane < 31u ? r[s] : (s + 1 < kS ? r[s + 1] : 0u);  // codes of the next word
             const uint32_t an = __byte_perm(gc[s], nx, 0x7773);  // bits 13:0 = the 7-mer starting at this word
             const uint32_t fw = lds_u32((an & 0x3FE0u) | afilt_or);
-            const bool hit = act && (__funnelshift_r(fw, 0u, an) & 1u);
-            const uint32_t bal = __ballot_sync(kFull, hit);
-            if (bal) {
-              if (hit) sts_u16(q_s + 2u * (qn + __popc(bal & lt_mask)), pp * wp + 32u * s + lane);
-              qn += __popc(bal);
-            }
+            uint32_t hit = __funnelshift_r(fw, 0u, an) & 1u;
+            if (s == kS - 1 && !act) hit = 0;
+            hm |= hit << s;
           }
         }
 #pragma unroll
@@ -353,14 +366,28 @@ __global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_const
       }
 
       if (kAd) {
-        if (qn) confirm(seq_s, qn);
-        // settle the first hits of the tile's reads: kmer_count[p + 1]++ (quack.c:215-216)
-        for (uint32_t n = lane; n < rpt; n += 32u) {
-          const uint32_t f = lds_u32(fhit_s + 4u * n);
-          if (f != kNoHit) {
-            red_shared_add<0u>(kmerhist_s + (f + 1u) * 4u, 1u);
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(fhit_s + 4u * n), "r"(kNoHit) : "memory");
+        // queue this lane's anchor hits: bit (ppt - 1 - pp) kS + s <-> word pp wp + 32 s + lane of the tile
+        while (hm) {
+          const uint32_t b = (uint32_t)__ffs((int)hm) - 1u;
+          hm &= hm - 1u;
+          const uint32_t pr = b / (uint32_t)kS, s = b - pr * (uint32_t)kS;
+          const uint32_t idx = atomicAdd(shared_ptr<uint32_t>(qcount_s), 1u);
+          sts_u16(q_s + 2u * idx, (ppt - 1u - pr) * wp + 32u * s + lane);
+        }
+        __syncwarp();
+        const uint32_t qn = lds_u32(qcount_s);
+        if (qn) {
+          confirm(seq_s, qn);
+          if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(qcount_s), "r"(0u) : "memory");
+          // settle the first hits of the tile's reads: kmer_count[p + 1]++ (quack.c:215-216)
+          for (uint32_t n = lane; n < rpt; n += 32u) {
+            const uint32_t f = lds_u32(fhit_s + 4u * n);
+            if (f != kNoHit) {
+              red_shared_add<0u>(kmerhist_s + (f + 1u) * 4u, 1u);
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(fhit_s + 4u * n), "r"(kNoHit) : "memory");
+            }
           }
+          __syncwarp();
         }
       }
       if (++st == stages) st = 0, phase ^= 1u;
@@ -429,8 +456,8 @@ PeriodPlan period_plan(uint32_t l, uint32_t first_offset, int adapters, int sm_c
     if (!(p.afilt_s = take(1, kAnchorSmemBytes)) || (p.afilt_s & (kAnchorSmemBytes - 1u))) return p;  // 16 KiB-aligned
     if (!(p.exact_s = take(2, kExactSlots * 4u))) return p;
     if (!(p.kmerhist_s = take(2, (l + 1u) * 4u))) return p;
+    if (!(p.bloom_s = take(2, kPBloomBits / 8u))) return p;
   }
-  const uint32_t hdr = pblock_hdr(adapters);
   uint32_t want = 3, target = 1024u;
   if (const char *e = getenv("QB_PT_STAGES")) want = (uint32_t)atoi(e);  // tuning hooks
   if (const char *e = getenv("QB_PT_BYTES")) target = (uint32_t)atoi(e);
@@ -461,9 +488,9 @@ PeriodPlan period_plan(uint32_t l, uint32_t first_offset, int adapters, int sm_c
     uint32_t ppt = ppt0;
     while (ppt * pb < target && (ppt + ppt0) * bk <= kPMaxRpt) ppt += ppt0;
     for (; ppt >= ppt0 && !p.ok; ppt -= ppt0) {
-      if (ppt * wp > 65535u) continue;
+      if (ppt * wp > 65535u || ppt * ((wp + 31u) / 32u) > 32u) continue;  // u16 queue entries, one hit bit per (period, step)
       for (uint32_t stages = want; stages >= 2u && !p.ok; stages--) {
-        const uint32_t wblock = hdr + stages * 2u * (ppt * pb + kPPad);
+        const uint32_t wblock = pblock_hdr(adapters, ppt * pb) + stages * 2u * (ppt * pb + kPPad);
         uint32_t fit = 0;
         for (int g = 0; g < 3; g++) fit += (gap[g].b - gap[g].a) / wblock;
         if (fit < (uint32_t)kPW) continue;
