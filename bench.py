@@ -316,16 +316,19 @@ def bench_ours(args):
     ker_mean = sum(ker_ms) / len(ker_ms) if ker_ms else float("nan")
     peak, peak_src = load_peaks()
     achieved = alg_bytes_launch / (ker_mean * 1e-3) / 1e9
+    # which kernel the timed launches took, and its measured DRAM traffic (one `ncu --set full` capture of the same
+    # kernel on the same read shape, dram__bytes_read.sum + dram__bytes_write.sum, scaled per read)
+    kname = "qb::period_kernel<adapters,5 steps,20 warps>" if ctx.period_launch_count else "qb::fused_kernel<true,96>"
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "bench_traffic.json")) as f:
             tj = json.load(f)
-            if tj.get("pairs") == pairs:
-                traffic = tj.get("dram_bytes_per_launch")
+            if tj.get("kernel_family") == ("period" if ctx.period_launch_count else "fused"):
+                traffic = tj["dram_bytes_per_read"] * db[0].info[0]
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "qb::fused_kernel<true,96>",
+                "traffic": traffic, "peak_source": peak_src, "kernel": kname,
                 "algorithmic_bytes_per_launch": alg_bytes_launch, "kernel_ms_mean": ker_mean,
                 "kernel_ms_min": min(ker_ms) if ker_ms else None, "launches_timed": len(ker_ms),
                 "kernel_share_of_step": 2 * ker_mean / (ms_dev / args.steps)}

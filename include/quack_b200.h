@@ -157,6 +157,8 @@ uint64_t qb_launch_count(const qb_ctx *ctx);
  * fused; chosen per batch whenever the batch's longest read fits the shared-memory histogram,
  * whatever len_cap is). */
 int qb_kernel_counts(const qb_ctx *ctx, uint64_t *n_simple, uint64_t *n_fused);
+/* How many launches took the period kernel (they are also counted in n_fused above). */
+uint64_t qb_period_launch_count(const qb_ctx *ctx);
 /* Live kernel timing: after qb_profile_enable(ctx, n) every statistics-kernel launch is bracketed by
  * a CUDA event pair on the stream it is launched on (up to n launches, then recording stops).
  * qb_profile_collect() synchronises and returns the per-launch durations in ms and the algorithmic
@@ -171,9 +173,9 @@ int qb_timer_stop(qb_ctx *ctx, int device_index, float *ms);
 int qb_measure_h2d(qb_ctx *ctx, int device_index, uint64_t bytes, int iters, double *gbs);
 /* Geometry and shared-memory counter layout of the period kernel (QB_KERNEL_PERIOD) for reads of one length.
  * Needs no GPU.  0 if the kernel takes such batches, -1 otherwise.  info = reads per period, words per period,
- * warp steps per period, periods per tile, reads per tile, stages; slot[p] = histogram block << 7 | 32-bit
+ * warp steps per period, periods per tile, reads per tile, stages, warps per CTA; slot[p] = histogram block << 7 | 32-bit
  * column of position p (its bank is the column modulo 32). */
-int qb_period_layout(uint32_t read_len, int adapters, uint32_t info[6], uint8_t slot[256]);
+int qb_period_layout(uint32_t read_len, int adapters, uint32_t info[7], uint8_t slot[256]);
 
 /* ---- host helpers that define the kernel's inputs ---- */
 /* lookup[(c-65)&~32] of quack.c:150,201 extended to all byte values. */

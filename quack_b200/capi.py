@@ -83,6 +83,8 @@ def lib() -> C.CDLL:
     L.qb_launch_count.argtypes = [vp]
     L.qb_launch_count.restype = C.c_uint64
     L.qb_kernel_counts.argtypes = [vp, _u64p, _u64p]
+    L.qb_period_launch_count.argtypes = [vp]
+    L.qb_period_launch_count.restype = C.c_uint64
     L.qb_profile_enable.argtypes = [vp, C.c_int]
     L.qb_profile_collect.argtypes = [vp, C.POINTER(C.c_float), _u64p, C.c_int]
     L.qb_timer_start.argtypes = [vp, C.c_int]
@@ -298,6 +300,11 @@ class Context:
         return int(lib().qb_launch_count(self.h))
 
     @property
+    @property
+    def period_launch_count(self) -> int:
+        """Launches that took the period kernel (v5)."""
+        return int(lib().qb_period_launch_count(self.h))
+
     def kernel_counts(self):
         """(launches of the simple kernel, launches of the fused kernel)."""
         a, b = C.c_uint64(), C.c_uint64()

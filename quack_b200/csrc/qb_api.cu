@@ -718,6 +718,8 @@ int qb_kernel_counts(const qb_ctx *ctx, uint64_t *n_simple, uint64_t *n_fused) {
   return QB_OK;
 }
 
+uint64_t qb_period_launch_count(const qb_ctx *ctx) { return ctx ? ctx->launches_period : 0; }
+
 int qb_profile_enable(qb_ctx *ctx, int max_launches) {
   if (!ctx || max_launches < 0) return QB_ERR_ARG;
   std::lock_guard<std::mutex> lk(ctx->mu);

@@ -111,10 +111,6 @@ cudaError_t launch_wtile(const BatchView &b, const Accum &a, const AdapterSet &a
 cudaError_t wtile_configure();  // opt in to the large dynamic shared memory once per device
 
 // ---- period kernel geometry (qb_period.cu; computed on the host, see period_plan) --------
-#ifndef QB_PW
-#define QB_PW 16
-#endif
-constexpr int kPeriodWarps = QB_PW;   // autonomous warps per CTA (one CTA per SM)
 constexpr uint32_t kPeriodMaxLen = 256;  // two histogram blocks of 128 positions
 
 struct PeriodPlan {
@@ -126,6 +122,7 @@ struct PeriodPlan {
   uint32_t tile_bytes;
   uint32_t reads_per_tile;   // ppt * k, a multiple of 4
   uint32_t stages;           // staged tiles per warp (2..4)
+  uint32_t warps;            // autonomous warps per CTA (one CTA per SM): 24, 20 or 16 (template parameter)
   uint32_t nblocks;          // histogram blocks (128 positions each)
   uint32_t wblock;           // bytes of one warp block (barriers, first hits, queue, stages x (seq + qual))
   uint32_t smem_base;        // shared address the dynamic shared memory must start at (checked by the kernel)

@@ -34,8 +34,6 @@
 
 namespace qb {
 
-constexpr int kPW = kPeriodWarps;
-constexpr int kPThreads = kPW * 32;
 constexpr uint32_t kPHist0 = 0x10000u;             // shared address of histogram block 0
 constexpr uint32_t kPBlockStride = 0x10000u;       // block b at kPHist0 + b * 64 KiB (its address has byte 1 == 0)
 constexpr uint32_t kPBlockBytes = kHistRows * 256u;  // 192 rows x 256 B = 48 KiB
@@ -47,10 +45,11 @@ constexpr uint32_t kPMaxRpt = 64;                  // reads per tile
 // offsets inside a warp block (multiples of 16)
 constexpr uint32_t kPoBar = 0;                     // kPMaxStages mbarriers
 constexpr uint32_t kPoCount = 32;                  // -a: number of queued anchor hits of the tile
-constexpr uint32_t kPoFhit = 48;                   // -a: first-hit position per read of the tile
-constexpr uint32_t kPoQueue = kPoFhit + kPMaxRpt * 4u;  // -a: one u16 word index per anchor hit, room for every word of a tile
-__host__ __device__ inline uint32_t pblock_hdr(int adapters, uint32_t tile_bytes) {
-  return adapters ? kPoQueue + ((tile_bytes / 2u + 15u) & ~15u) : kPoCount;
+constexpr uint32_t kPoQueue = 48;                  // -a: kPQueue u16 word indices of anchor hits
+constexpr uint32_t kPQueue = 64;                   //     (more hits in a tile: several rounds of queue + confirm)
+constexpr uint32_t kPoFhit = kPoQueue + kPQueue * 2u;  // -a: first-hit position per read of the tile
+__host__ __device__ inline uint32_t pblock_hdr(int adapters, uint32_t rpt) {
+  return adapters ? kPoFhit + ((rpt * 4u + 15u) & ~15u) : kPoCount;
 }
 
 struct PArgs {
@@ -102,8 +101,9 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
   return v;
 }
 
-template <bool kAd, int kS>
-__global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_constant__ PArgs args) {
+template <bool kAd, int kS, int kPW>
+__global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_constant__ PArgs args) {
+  constexpr uint32_t kPThreads = kPW * 32;
   extern __shared__ __align__(128) uint8_t smem[];
   const PeriodPlan &P = args.plan;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_const
     else
       wb_s = P.region_s[2] + (w - P.region_n[1]) * P.wblock;
   }
-  const uint32_t ring_s = wb_s + pblock_hdr(kAd, tb);  // stage s: bases at ring_s + 2 s buf, quality bytes + buf
+  const uint32_t ring_s = wb_s + pblock_hdr(kAd, rpt);  // stage s: bases at ring_s + 2 s buf, quality bytes + buf
   const uint32_t fhit_s = wb_s + kPoFhit, q_s = wb_s + kPoQueue, qcount_s = wb_s + kPoCount;
   const uint32_t bloom_s = P.bloom_s;
   const uint32_t kmerhist_s = P.kmerhist_s, exact_s = P.exact_s;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_const
     if (args.ad.exact)
       for (uint32_t i = tid; i < kExactSlots; i += kPThreads) ex[i] = args.ad.exact[i];
     uint32_t *fh = reinterpret_cast<uint32_t *>(gen(fhit_s));
-    for (uint32_t i = lane; i < kPMaxRpt; i += 32u) fh[i] = kNoHit;
+    for (uint32_t i = lane; i < rpt; i += 32u) fh[i] = kNoHit;
     if (lane == 0) *reinterpret_cast<uint32_t *>(gen(qcount_s)) = 0;
     uint32_t *bl = reinterpret_cast<uint32_t *>(gen(bloom_s));
     for (uint32_t i = tid; i < kPBloomBits / 32u; i += kPThreads) bl[i] = args.ad.exact ? 0u : 0xFFFFFFFFu;
@@ -255,36 +255,39 @@ __global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_const
   // window whose 10 bases lie inside one read lowers that read's first-hit position; a hit that ends on the
   // last base of its read is dropped (it can only be the first hit if there is no other, and then the
   // reference counts nothing).
-  auto confirm = [&](uint32_t seq_s, uint32_t qn) {
+  auto confirm = [&](uint32_t seq_s, uint32_t qn) {  // qn <= kPQueue
     __syncwarp();
     for (uint32_t e0 = 0; e0 < qn; e0 += 32u) {
       const uint32_t e = e0 + lane;
       if (e < qn) {
         const uint32_t b0 = lds_u16(q_s + 2u * e) * 4u;  // tile byte of the anchor's first base
         const uint32_t n = __umulhi(b0, len_magic), p0 = b0 - n * len;  // its read in the tile, its position
-        // windows start at p0 - o, o = 0..3: inside the read iff p0 >= o and p0 - o + 10 < len
-        if (p0 + 10u < len + 3u && p0 + 6u < lds_u32(fhit_s + 4u * n)) {
-          const uint32_t A = seq_s + b0;
-          const uint32_t cm = gather_codes(~p_ncodes(lds_u32(A - 4u), kc)) >> 24;  // bases -4..-1 (first word of a tile: unused)
-          const uint32_t c0 = gather_codes(~p_ncodes(lds_u32(A), kc)) >> 24;
-          const uint32_t c1 = gather_codes(~p_ncodes(lds_u32(A + 4u), kc)) >> 24;
-          const uint32_t c2 = gather_codes(~p_ncodes(lds_u32(A + 8u), kc)) >> 24;
-          // bases -3 .. 12, 2 bits each, first base least significant
-          const uint32_t ctx = (cm >> 2) | (c0 << 6) | (c1 << 14) | (c2 << 22);
+        const uint32_t A = seq_s + b0;
+        const uint32_t cm = gather_codes(~p_ncodes(lds_u32(A - 4u), kc));  // bases -4..-1 (first word of a tile: unused)
+        const uint32_t c0 = gather_codes(~p_ncodes(lds_u32(A), kc));
+        const uint32_t c1 = gather_codes(~p_ncodes(lds_u32(A + 4u), kc));
+        const uint32_t c2 = gather_codes(~p_ncodes(lds_u32(A + 8u), kc));
+        // codes of bases -4 .. 11, 2 bits each, first base least significant (the gathered codes are top bytes)
+        const uint32_t ctx = __byte_perm(__byte_perm(cm, c0, 0x0073), __byte_perm(c1, c2, 0x0073), 0x5410);
+        // window o starts at base o - 4 (o = 1..4: 3, 2, 1, 0 bases before the anchor): Bloom filter of the keys
+        uint32_t pass = 0;
 #pragma unroll
-          for (uint32_t o = 0; o < 4u; o++) {  // ascending window start: o = 3 first
-            const uint32_t oo = 3u - o;        // window starts oo bases before the anchor
-            if (p0 >= oo && p0 - oo + 10u < len) {
+        for (uint32_t o = 1; o <= 4u; o++) {
+          const uint32_t h = (((ctx >> (2u * o)) & 0xFFFFFu) * kPBloomMul) >> 18;
+          pass |= (__funnelshift_r(lds_u32(bloom_s + ((h >> 5) << 2)), 0u, h) & 1u) << o;
+        }
+        if (pass) {  // 8 % of the entries on random bases: exact set, window inside one read, first-hit rule
+#pragma unroll
+          for (uint32_t o = 1; o <= 4u; o++) {
+            const uint32_t oo = 4u - o;  // window starts oo bases before the anchor
+            if ((pass >> o & 1u) && p0 >= oo && p0 - oo + 10u < len) {
               const uint32_t key = (ctx >> (2u * o)) & 0xFFFFFu;
-              const uint32_t h = (key * kPBloomMul) >> 18;
-              if (__funnelshift_r(lds_u32(bloom_s + ((h >> 5) << 2)), 0u, h) & 1u) {  // 98 % of the non-members stop here
-                bool member;
-                if (args.ad.exact)
-                  member = lds_u32(exact_s + exact_off1(key)) == key || lds_u32(exact_s + exact_off2(key)) == key;
-                else
-                  member = (args.ad.bitmap[key >> 5] >> (key & 31u)) & 1u;
-                if (member) atomicMin(shared_ptr<uint32_t>(fhit_s) + n, p0 - oo + 9u);
-              }
+              bool member;
+              if (args.ad.exact)
+                member = lds_u32(exact_s + exact_off1(key)) == key || lds_u32(exact_s + exact_off2(key)) == key;
+              else
+                member = (args.ad.bitmap[key >> 5] >> (key & 31u)) & 1u;
+              if (member) atomicMin(shared_ptr<uint32_t>(fhit_s) + n, p0 - oo + 9u);
             }
           }
         }
@@ -366,19 +369,26 @@ __global__ void __launch_bounds__(kPThreads, 1) period_kernel(const __grid_const
       }
 
       if (kAd) {
-        // queue this lane's anchor hits: bit (ppt - 1 - pp) kS + s <-> word pp wp + 32 s + lane of the tile
-        while (hm) {
-          const uint32_t b = (uint32_t)__ffs((int)hm) - 1u;
-          hm &= hm - 1u;
-          const uint32_t pr = b / (uint32_t)kS, s = b - pr * (uint32_t)kS;
-          const uint32_t idx = atomicAdd(shared_ptr<uint32_t>(qcount_s), 1u);
-          sts_u16(q_s + 2u * idx, (ppt - 1u - pr) * wp + 32u * s + lane);
-        }
-        __syncwarp();
-        const uint32_t qn = lds_u32(qcount_s);
-        if (qn) {
+        // queue this lane's anchor hits (bit (ppt - 1 - pp) kS + s <-> word pp wp + 32 s + lane of the tile) and
+        // confirm them, kPQueue at a time; a lane that finds the queue full keeps its bit for the next round
+        bool any = false;
+        while (__any_sync(kFull, hm != 0u)) {
+          any = true;
+          while (hm) {
+            const uint32_t idx = atomicAdd(shared_ptr<uint32_t>(qcount_s), 1u);
+            if (idx >= kPQueue) break;
+            const uint32_t b = (uint32_t)__ffs((int)hm) - 1u;
+            hm &= hm - 1u;
+            const uint32_t pr = b / (uint32_t)kS, s = b - pr * (uint32_t)kS;
+            sts_u16(q_s + 2u * idx, (ppt - 1u - pr) * wp + 32u * s + lane);
+          }
+          __syncwarp();
+          const uint32_t qn = min(lds_u32(qcount_s), kPQueue);
           confirm(seq_s, qn);
           if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(qcount_s), "r"(0u) : "memory");
+          __syncwarp();
+        }
+        if (any) {
           // settle the first hits of the tile's reads: kmer_count[p + 1]++ (quack.c:215-216)
           for (uint32_t n = lane; n < rpt; n += 32u) {
             const uint32_t f = lds_u32(fhit_s + 4u * n);
@@ -421,8 +431,8 @@ static uint32_t gcd_u32(uint32_t a, uint32_t b) {
   return a;
 }
 
-PeriodPlan period_plan(uint32_t l, uint32_t first_offset, int adapters, int sm_count, uint32_t smem_optin,
-                       uint32_t smem_reserved, uint32_t qbase) {
+static PeriodPlan period_plan_w(uint32_t l, uint32_t first_offset, int adapters, int sm_count, uint32_t smem_optin,
+                                uint32_t smem_reserved, uint32_t qbase, uint32_t warps) {
   PeriodPlan p;
   memset(&p, 0, sizeof p);
   if (l < 32u || l > kPeriodMaxLen || (l & 1u) || (first_offset & 15u)) return p;
@@ -490,10 +500,10 @@ PeriodPlan period_plan(uint32_t l, uint32_t first_offset, int adapters, int sm_c
     for (; ppt >= ppt0 && !p.ok; ppt -= ppt0) {
       if (ppt * wp > 65535u || ppt * ((wp + 31u) / 32u) > 32u) continue;  // u16 queue entries, one hit bit per (period, step)
       for (uint32_t stages = want; stages >= 2u && !p.ok; stages--) {
-        const uint32_t wblock = pblock_hdr(adapters, ppt * pb) + stages * 2u * (ppt * pb + kPPad);
+        const uint32_t wblock = pblock_hdr(adapters, ppt * bk) + stages * 2u * (ppt * pb + kPPad);
         uint32_t fit = 0;
         for (int g = 0; g < 3; g++) fit += (gap[g].b - gap[g].a) / wblock;
-        if (fit < (uint32_t)kPW) continue;
+        if (fit < warps) continue;
         p.k = bk, p.wp = wp, p.steps = (wp + 31u) / 32u;
         p.ppt = ppt, p.tile_bytes = ppt * pb, p.reads_per_tile = ppt * bk;
         p.stages = stages, p.wblock = wblock;
@@ -502,7 +512,8 @@ PeriodPlan period_plan(uint32_t l, uint32_t first_offset, int adapters, int sm_c
     }
     if (p.ok) break;
   }
-  uint32_t left = (uint32_t)kPW;
+  p.warps = warps;
+  uint32_t left = warps;
   for (int g = 0; g < 3; g++) {
     uint32_t n = (gap[g].b - gap[g].a) / p.wblock;
     if (n > left) n = left;
@@ -512,6 +523,23 @@ PeriodPlan period_plan(uint32_t l, uint32_t first_offset, int adapters, int sm_c
   }
   p.smem_bytes = smem_optin;
   p.grid = (uint32_t)sm_count;
+  return p;
+}
+
+// More resident warps hide more latency (ncu: the kernel is bound by instruction issue with 4 warps per
+// scheduler): 24 warps where their blocks fit, else 20, else 16 (24 warps leave 80 registers per thread; every
+// instantiation meets that without spills).
+PeriodPlan period_plan(uint32_t l, uint32_t first_offset, int adapters, int sm_count, uint32_t smem_optin,
+                       uint32_t smem_reserved, uint32_t qbase) {
+  uint32_t forced = 0;
+  if (const char *e = getenv("QB_PT_WARPS")) forced = (uint32_t)atoi(e);  // tuning hook
+  PeriodPlan p;
+  memset(&p, 0, sizeof p);
+  for (uint32_t w : {24u, 20u, 16u}) {
+    if (forced && w != forced) continue;
+    p = period_plan_w(l, first_offset, adapters, sm_count, smem_optin, smem_reserved, qbase, w);
+    if (p.ok) break;
+  }
   return p;
 }
 
@@ -653,23 +681,34 @@ static void period_slots(const PeriodPlan &p, uint8_t *slot) {
   cache->k[l] = (uint8_t)p.k;
 }
 
-template <bool kAd>
+template <bool kAd, int kPW>
 static cudaError_t period_launch_steps(const PArgs &args, uint32_t grid, cudaStream_t stream) {
   const uint32_t smem = args.plan.smem_bytes;
   switch (args.plan.steps) {
-    case 3: period_kernel<kAd, 3><<<grid, kPThreads, smem, stream>>>(args); break;
-    case 4: period_kernel<kAd, 4><<<grid, kPThreads, smem, stream>>>(args); break;
-    case 5: period_kernel<kAd, 5><<<grid, kPThreads, smem, stream>>>(args); break;
+    case 3: period_kernel<kAd, 3, kPW><<<grid, kPW * 32, smem, stream>>>(args); break;
+    case 4: period_kernel<kAd, 4, kPW><<<grid, kPW * 32, smem, stream>>>(args); break;
+    case 5: period_kernel<kAd, 5, kPW><<<grid, kPW * 32, smem, stream>>>(args); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
+template <bool kAd>
+static cudaError_t period_launch_warps(const PArgs &args, uint32_t grid, cudaStream_t stream) {
+  switch (args.plan.warps) {
+    case 16: return period_launch_steps<kAd, 16>(args, grid, stream);
+    case 20: return period_launch_steps<kAd, 20>(args, grid, stream);
+    case 24: return period_launch_steps<kAd, 24>(args, grid, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
 
 cudaError_t period_configure() {
   cudaError_t e;
-#define QB_PCFG(A, S)                                                                                               \
-  if ((e = cudaFuncSetAttribute(period_kernel<A, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
-  QB_PCFG(false, 3) QB_PCFG(false, 4) QB_PCFG(false, 5) QB_PCFG(true, 3) QB_PCFG(true, 4) QB_PCFG(true, 5)
+#define QB_PCFG(A, S, W)                                                                                                \
+  if ((e = cudaFuncSetAttribute(period_kernel<A, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+#define QB_PCFG3(A, W) QB_PCFG(A, 3, W) QB_PCFG(A, 4, W) QB_PCFG(A, 5, W)
+  QB_PCFG3(false, 16) QB_PCFG3(false, 20) QB_PCFG3(false, 24) QB_PCFG3(true, 16) QB_PCFG3(true, 20) QB_PCFG3(true, 24)
+#undef QB_PCFG3
 #undef QB_PCFG
   return cudaSuccess;
 }
@@ -690,13 +729,13 @@ cudaError_t launch_period(const BatchView &b, const Accum &a, const AdapterSet &
   args.n_tiles = n_tiles;
   args.inc_lo = 1u, args.inc_hi = 0x10000u;
   period_slots(plan, args.slot);
-  uint32_t grid = (n_tiles + (uint32_t)kPW - 1u) / (uint32_t)kPW;
+  uint32_t grid = (n_tiles + plan.warps - 1u) / plan.warps;
   if (grid > plan.grid) grid = plan.grid;
   if (const char *g = getenv("QB_FUSED_GRID")) {  // test hook: few CTAs exercise the u16 flush path
     const uint32_t v = (uint32_t)atoi(g);
     if (v >= 1 && v < grid) grid = v;
   }
-  const cudaError_t e = ad.enabled ? period_launch_steps<true>(args, grid, stream) : period_launch_steps<false>(args, grid, stream);
+  const cudaError_t e = ad.enabled ? period_launch_warps<true>(args, grid, stream) : period_launch_warps<false>(args, grid, stream);
   if (e == cudaSuccess) *n_main_out = n_tiles * plan.reads_per_tile;
   return e;
 }
@@ -705,12 +744,12 @@ cudaError_t launch_period(const BatchView &b, const Accum &a, const AdapterSet &
 
 // tools / tests: the geometry and the counter layout the period kernel would use for reads of one length on a
 // B200 (227 KiB of shared memory per block, 1 KiB reserved).  Needs no GPU.  Returns 0 if the kernel takes
-// such batches, -1 otherwise.  info[0..5] = reads per period, words per period, steps, periods per tile,
-// reads per tile, stages; slot[p] = block << 7 | u32 column of position p.
-extern "C" int qb_period_layout(uint32_t read_len, int adapters, uint32_t info[6], uint8_t slot[256]) {
+// such batches, -1 otherwise.  info[0..6] = reads per period, words per period, steps, periods per tile,
+// reads per tile, stages, warps; slot[p] = block << 7 | u32 column of position p.
+extern "C" int qb_period_layout(uint32_t read_len, int adapters, uint32_t info[7], uint8_t slot[256]) {
   const qb::PeriodPlan p = qb::period_plan(read_len, 0, adapters, 148, 232448u - 1024u, 1024u, 33u);
   if (!p.ok) return -1;
-  if (info) info[0] = p.k, info[1] = p.wp, info[2] = p.steps, info[3] = p.ppt, info[4] = p.reads_per_tile, info[5] = p.stages;
+  if (info) info[0] = p.k, info[1] = p.wp, info[2] = p.steps, info[3] = p.ppt, info[4] = p.reads_per_tile, info[5] = p.stages, info[6] = p.warps;
   if (slot) qb::period_slots(p, slot);
   return 0;
 }

@@ -62,3 +62,48 @@ def test_generator_is_deterministic_and_shardable():
     # read-through adapters make the oracle's adapter panel non-trivial: ~10 % + chance hits
     r = po.accumulate_batch(*a, util.oracle_table())
     assert 0.09 * 3000 < r.rows[:, 96].sum() < 0.18 * 3000
+
+
+@pytest.mark.parametrize("l", [32, 36, 50, 64, 76, 100, 126, 128, 130, 150, 200, 248, 256])
+@pytest.mark.parametrize("ad", [0, 1])
+def test_period_layout_is_a_valid_counter_map(l, ad):
+    """Host side of the period kernel (no GPU needed): the plan covers whole reads and 16-byte tiles, and
+    the bank-conflict solver returns an injective position -> (block, column, half) map that is never
+    worse than the natural layout (column = position / 4)."""
+    import ctypes as C
+    L = capi.lib()
+    L.qb_period_layout.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
+    info, slot = (C.c_uint32 * 7)(), (C.c_uint8 * 256)()
+    assert L.qb_period_layout(l, ad, info, slot) == 0
+    k, wp, steps, ppt, rpt, stages, warps = list(info)
+    assert k * l == 4 * wp and steps == -(-wp // 32) and 3 <= steps <= 5
+    assert (ppt * wp * 4) % 16 == 0 and rpt == ppt * k and rpt % 4 == 0 and stages >= 2 and warps in (16, 20, 24)
+    seen = set()
+    for p in range(l):
+        blk, col = slot[p] >> 7, slot[p] & 127
+        assert col < 64 and blk < (2 if l > 128 else 1)
+        assert (blk, col, p & 1) not in seen
+        seen.add((blk, col, p & 1))
+
+    def wavefronts(bank_of):
+        tot = 0
+        for s in range(steps):
+            for j in range(4):
+                c = {}
+                for i in range(32):
+                    if 32 * s + i < wp:
+                        b = bank_of((4 * (32 * s + i) + j) % l)
+                        c[b] = c.get(b, 0) + 1
+                tot += max(c.values())
+        return tot
+    assert wavefronts(lambda p: slot[p] & 31) <= wavefronts(lambda p: ((p & 127) >> 2) & 31)
+    if l == 150:   # 4 x 150 bp: 3 of the 10 even steps cost two wavefronts, the others one
+        assert wavefronts(lambda p: slot[p] & 31) == 26
+
+
+def test_period_layout_rejects_other_lengths():
+    import ctypes as C
+    L = capi.lib()
+    L.qb_period_layout.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
+    for l in (0, 10, 31, 151, 257, 300):
+        assert L.qb_period_layout(l, 1, None, None) == -1

@@ -14,9 +14,9 @@ QB_QUICK_KERNELS=4,2 timeout 600 python tools/quick_bench.py 4000000 > $OUT/quic
 cat $OUT/quick_bench.jsonl
 QB_QUICK_KERNELS=4,2 QB_QUICK_LENS=${LENS:-50,76,100,126,200,256} timeout 300 python tools/quick_bench.py 4000000 >> $OUT/sweep.jsonl 2>&1
 QB_PT_NATURAL=1 QB_QUICK_KERNELS=4 QB_QUICK_ONLY150=1 timeout 300 python tools/quick_bench.py 4000000 >> $OUT/sweep.jsonl 2>&1
-for lib in quack_b200/lib/libqb_p*.so; do
-  [ -f $lib ] && QB_LIB=$PWD/$lib QB_QUICK_KERNELS=4 QB_QUICK_ONLY150=1 timeout 300 python tools/quick_bench.py 4000000 >> $OUT/sweep.jsonl 2>&1
-done
+for w in 16 20 24; do for st in 2 3; do
+  QB_PT_WARPS=$w QB_PT_STAGES=$st QB_QUICK_KERNELS=4 QB_QUICK_ONLY150=1 timeout 300 python tools/quick_bench.py 4000000 2>&1 | grep -v "^Traceback\|^  File\|^    " >> $OUT/sweep.jsonl
+done; done
 cat $OUT/sweep.jsonl
 if [ "$NCU" = "1" ]; then
 for mode in ad noad; do

@@ -42,7 +42,7 @@ def main():
                            "ms_avg": round(avg, 4), "ms_min": round(mn, 4), "Greads_s": round(nr / avg / 1e6, 3),
                            "Gbases_s": round(nb / avg / 1e6, 2), "GBps": round(alg / avg / 1e6, 1),
                            "frac_hbm": round(alg / avg / 1e6 / HBM, 4)}
-                    for k in ("QB_LIB", "QB_WT_READS", "QB_PT_STAGES", "QB_PT_BYTES"):
+                    for k in ("QB_LIB", "QB_WT_READS", "QB_PT_STAGES", "QB_PT_BYTES", "QB_PT_WARPS", "QB_PT_NATURAL"):
                         if os.environ.get(k):
                             rec[k] = os.path.basename(os.environ[k])
                     print(json.dumps(rec), flush=True)
