@@ -101,6 +101,9 @@ def lib() -> C.CDLL:
     # host program pieces linked into the same library (quack_b200/host/*.c)
     L.fqr_open.argtypes = [C.c_char_p]
     L.fqr_open.restype = vp
+    L.fqr_open_mt.argtypes = [C.c_char_p, C.c_int]
+    L.fqr_open_mt.restype = vp
+    L.fqr_decode_threads.argtypes = [vp]
     L.fqr_close.argtypes = [vp]
     L.fqr_close.restype = None
     L.fqr_fill.argtypes = [vp, vp, vp, vp, vp, C.c_uint64, C.c_uint32, _u32p, _u64p, _u32p]
@@ -300,11 +303,11 @@ class Context:
         return int(lib().qb_launch_count(self.h))
 
     @property
-    @property
     def period_launch_count(self) -> int:
         """Launches that took the period kernel (v5)."""
         return int(lib().qb_period_launch_count(self.h))
 
+    @property
     def kernel_counts(self):
         """(launches of the simple kernel, launches of the fused kernel)."""
         a, b = C.c_uint64(), C.c_uint64()
@@ -351,10 +354,11 @@ def read_adapters(path: str) -> np.ndarray:
     return out
 
 
-def parse_records(path: str):
-    """[(seq, qual or None)] and the final status, record by record through the host reader."""
+def parse_records(path: str, threads: int = 0):
+    """[(seq, qual or None)] and the final status, record by record through the host reader
+    (threads: BGZF pool threads, 0 = default, 1 = gzread path)."""
     L = lib()
-    r = L.fqr_open(path.encode())
+    r = L.fqr_open_mt(path.encode(), threads)
     if not r:
         raise OSError(path)
     out = []
@@ -368,10 +372,40 @@ def parse_records(path: str):
     return out, int(n)
 
 
-def read_batches(path: str, cap_bytes: int, cap_reads: int):
+def decode_throughput(path: str, threads: int = 0, cap_bytes: int = 32 << 20):
+    """Host decode + framing + packing of a whole file into scratch batches (no GPU): dict with reads,
+    decompressed bytes, wall seconds, seconds waiting for inflated data, pool threads."""
+    import time
+    L = lib()
+    r = L.fqr_open_mt(path.encode(), threads)
+    if not r:
+        raise OSError(path)
+    cap_reads = cap_bytes // 32 + 1
+    seq = np.zeros(cap_bytes + 64, dtype=np.uint8)
+    qual = np.zeros(cap_bytes + 64, dtype=np.uint8)
+    off = np.zeros(cap_reads, dtype=np.uint32)
+    ln = np.zeros(cap_reads, dtype=np.uint32)
+    n, nb, ml = C.c_uint32(), C.c_uint64(), C.c_uint32()
+    reads = bases = 0
+    t0 = time.perf_counter()
+    more = 1
+    while more > 0:
+        more = L.fqr_fill(r, seq.ctypes.data, qual.ctypes.data, off.ctypes.data, ln.ctypes.data, cap_bytes, cap_reads,
+                          C.byref(n), C.byref(nb), C.byref(ml))
+        reads += n.value
+        bases += nb.value
+    dt = time.perf_counter() - t0
+    out = {"reads": reads, "bases": bases, "text_bytes": int(L.fqr_bytes_in(r)), "seconds": dt,
+           "wait_inflate_s": float(L.fqr_inflate_seconds(r)), "threads": int(L.fqr_decode_threads(r)),
+           "status": int(L.fqr_status(r))}
+    L.fqr_close(r)
+    return out
+
+
+def read_batches(path: str, cap_bytes: int, cap_reads: int, threads: int = 0):
     """All batches the host reader packs from a file: [(seq, qual, offset, length, max_len)], status."""
     L = lib()
-    r = L.fqr_open(path.encode())
+    r = L.fqr_open_mt(path.encode(), threads)
     if not r:
         raise OSError(path)
     batches = []

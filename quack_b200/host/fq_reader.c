@@ -5,13 +5,23 @@
  *     trailing '\r' is dropped when the accumulated string is longer than one byte (kseq.h:141);
  *   - the '+' line is skipped; quality = following lines until at least as many bytes as the sequence;
  *   - quality length != sequence length -> -2 and the stream is over for quack (quack.c:193).
- * Lines are located with memchr over a 1 MiB inflate buffer instead of kseq's per-byte loops. */
+ * Lines are located with memchr over a 1 MiB inflate buffer instead of kseq's per-byte loops.
+ *
+ * Input decode: a plain / gzip / multi-member gzip file goes through gzread()
+ * like the reference (quack.c:187, kseq.h:74).  A BGZF file (the blocked gzip of bgzip / htslib, reference
+ * klib/bgzf.c:63-71: every member carries its compressed size in a 'BC' extra subfield and inflates to at
+ * most 64 KiB on its own) is inflated by a pool of threads, one block per thread at a time, and handed to
+ * the framing code in file order -- the same bytes gzread() would deliver, so everything downstream is
+ * unchanged. */
 #include "fq_reader.h"
 
 #include <ctype.h>
+#include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include "../../include/quack_b200.h"
@@ -23,8 +33,33 @@ typedef struct {
   size_t l, m;
 } fqr_str;
 
+/* ---- BGZF block pool ---- */
+#define BGZF_MAX_BLOCK 65536u
+typedef struct {
+  uint8_t *cbuf; /* deflate payload + 8-byte trailer of one block */
+  uint8_t *ubuf; /* inflated bytes */
+  uint32_t csize, usize;
+  int state; /* 0 free, 1 being inflated, 2 ready for the consumer */
+  int err;   /* 0, -1 end of file in front of this block, -3 broken block */
+} bgzf_slot;
+
+typedef struct {
+  FILE *fp;
+  int n_threads, n_slots;
+  bgzf_slot *slot;
+  pthread_t *th;
+  pthread_mutex_t mu;
+  pthread_cond_t cv_ready, cv_free;
+  uint64_t next_ticket;  /* next block to read from the file */
+  uint64_t next_consume; /* next block the framing code takes */
+  int input_done;        /* a reader saw the end of the file or a broken block: no more tickets */
+  int stop;
+  double inflate_cpu_s;  /* summed over the workers */
+} bgzf_pool;
+
 struct fqr_reader {
   gzFile f;
+  bgzf_pool *pool; /* != NULL: BGZF input decoded by the pool, f unused */
   uint8_t *buf;
   size_t begin, end;
   int is_eof, err;
@@ -42,7 +77,160 @@ static double now_s(void) {
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-fqr_reader *fqr_open(const char *path) {
+/* Reads the next BGZF block of fp into s (payload + trailer).  0 ok, -1 clean end of file, -3 not a BGZF
+ * block / truncated.  Layout (RFC 1952 + SAM spec 4.1; reference klib/bgzf.c:63-71, 330-355): 10-byte gzip
+ * header with FLG = FEXTRA, XLEN, extra subfields of which one is 'B' 'C' 2 BSIZE (block size - 1), deflate
+ * data, CRC32, ISIZE. */
+static int bgzf_read_block(FILE *fp, bgzf_slot *s) {
+  uint8_t h[12];
+  const size_t got = fread(h, 1, 12, fp);
+  if (got == 0) return -1;
+  if (got != 12 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || h[3] != 4) return -3;
+  const uint32_t xlen = (uint32_t)h[10] | (uint32_t)h[11] << 8;
+  uint8_t extra[512];
+  if (xlen < 6 || xlen > sizeof extra || fread(extra, 1, xlen, fp) != xlen) return -3;
+  uint32_t bsize = 0;
+  for (uint32_t i = 0; i + 4 <= xlen;) {
+    const uint32_t slen = (uint32_t)extra[i + 2] | (uint32_t)extra[i + 3] << 8;
+    if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= xlen) bsize = ((uint32_t)extra[i + 4] | (uint32_t)extra[i + 5] << 8) + 1u;
+    i += 4 + slen;
+  }
+  if (bsize < 12 + xlen + 8 || bsize > BGZF_MAX_BLOCK) return -3;
+  s->csize = bsize - 12 - xlen;
+  if (fread(s->cbuf, 1, s->csize, fp) != s->csize) return -3;
+  return 0;
+}
+
+static void *bgzf_worker(void *arg) {
+  bgzf_pool *p = (bgzf_pool *)arg;
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  if (inflateInit2(&zs, -15) != Z_OK) return NULL;
+  double cpu = 0;
+  for (;;) {
+    pthread_mutex_lock(&p->mu);
+    while (!p->stop && !p->input_done && p->slot[p->next_ticket % (uint64_t)p->n_slots].state != 0)
+      pthread_cond_wait(&p->cv_free, &p->mu);
+    if (p->stop || p->input_done) {
+      pthread_mutex_unlock(&p->mu);
+      break;
+    }
+    bgzf_slot *s = &p->slot[p->next_ticket++ % (uint64_t)p->n_slots];
+    const int rc = bgzf_read_block(p->fp, s); /* sequential file order: under the lock */
+    s->err = rc;
+    s->usize = 0;
+    if (rc) {
+      p->input_done = 1;
+      s->state = 2;
+      pthread_cond_broadcast(&p->cv_ready);
+      pthread_cond_broadcast(&p->cv_free);
+      pthread_mutex_unlock(&p->mu);
+      break;
+    }
+    s->state = 1;
+    pthread_mutex_unlock(&p->mu);
+
+    const double t0 = now_s();
+    int err = 0;
+    uint32_t out = 0;
+    inflateReset(&zs);
+    zs.next_in = s->cbuf;
+    zs.avail_in = s->csize - 8;
+    zs.next_out = s->ubuf;
+    zs.avail_out = BGZF_MAX_BLOCK;
+    if (inflate(&zs, Z_FINISH) != Z_STREAM_END) {
+      err = -3;
+    } else {
+      out = BGZF_MAX_BLOCK - zs.avail_out;
+      const uint8_t *t = s->cbuf + s->csize - 8;
+      const uint32_t crc = (uint32_t)t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
+      const uint32_t isize = (uint32_t)t[4] | (uint32_t)t[5] << 8 | (uint32_t)t[6] << 16 | (uint32_t)t[7] << 24;
+      if (isize != out || (uint32_t)crc32(crc32(0L, Z_NULL, 0), s->ubuf, out) != crc) err = -3; /* as gzread checks */
+    }
+    cpu += now_s() - t0;
+
+    pthread_mutex_lock(&p->mu);
+    s->usize = err ? 0 : out;
+    s->err = err;
+    s->state = 2;
+    pthread_cond_broadcast(&p->cv_ready);
+    pthread_mutex_unlock(&p->mu);
+  }
+  inflateEnd(&zs);
+  pthread_mutex_lock(&p->mu);
+  p->inflate_cpu_s += cpu;
+  pthread_mutex_unlock(&p->mu);
+  return NULL;
+}
+
+static bgzf_pool *bgzf_pool_open(FILE *fp, int n_threads) {
+  bgzf_pool *p = (bgzf_pool *)calloc(1, sizeof *p);
+  p->fp = fp;
+  p->n_threads = n_threads;
+  p->n_slots = 8 * n_threads;
+  p->slot = (bgzf_slot *)calloc((size_t)p->n_slots, sizeof *p->slot);
+  for (int i = 0; i < p->n_slots; i++) {
+    p->slot[i].cbuf = (uint8_t *)malloc(BGZF_MAX_BLOCK);
+    p->slot[i].ubuf = (uint8_t *)malloc(BGZF_MAX_BLOCK);
+  }
+  pthread_mutex_init(&p->mu, NULL);
+  pthread_cond_init(&p->cv_ready, NULL);
+  pthread_cond_init(&p->cv_free, NULL);
+  p->th = (pthread_t *)calloc((size_t)n_threads, sizeof *p->th);
+  for (int i = 0; i < n_threads; i++) pthread_create(&p->th[i], NULL, bgzf_worker, p);
+  return p;
+}
+
+static void bgzf_pool_close(bgzf_pool *p) {
+  pthread_mutex_lock(&p->mu);
+  p->stop = 1;
+  pthread_cond_broadcast(&p->cv_free);
+  pthread_mutex_unlock(&p->mu);
+  for (int i = 0; i < p->n_threads; i++) pthread_join(p->th[i], NULL);
+  for (int i = 0; i < p->n_slots; i++) {
+    free(p->slot[i].cbuf);
+    free(p->slot[i].ubuf);
+  }
+  free(p->slot);
+  free(p->th);
+  pthread_mutex_destroy(&p->mu);
+  pthread_cond_destroy(&p->cv_ready);
+  pthread_cond_destroy(&p->cv_free);
+  fclose(p->fp);
+  free(p);
+}
+
+/* 1 if the file starts with a BGZF block header */
+static int is_bgzf(FILE *fp) {
+  uint8_t h[18];
+  const size_t got = fread(h, 1, sizeof h, fp);
+  rewind(fp);
+  return got == sizeof h && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && h[3] == 4 && h[10] == 6 && h[11] == 0 &&
+         h[12] == 'B' && h[13] == 'C' && h[14] == 2 && h[15] == 0;
+}
+
+int fqr_default_threads(void) {
+  const char *e = getenv("QUACK_DECODE_THREADS");
+  if (e && atoi(e) >= 1) return atoi(e) > 64 ? 64 : atoi(e);
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  if (n < 2) return 1;
+  n /= 2; /* two mates are decoded concurrently */
+  return n > 8 ? 8 : (int)n;
+}
+
+fqr_reader *fqr_open_mt(const char *path, int threads) {
+  if (threads < 1) threads = fqr_default_threads();
+  if (threads > 1) {
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return NULL;
+    if (is_bgzf(fp)) {
+      fqr_reader *r = (fqr_reader *)calloc(1, sizeof *r);
+      r->pool = bgzf_pool_open(fp, threads);
+      r->buf = (uint8_t *)malloc(BGZF_MAX_BLOCK);
+      return r;
+    }
+    fclose(fp);
+  }
   gzFile f = gzopen(path, "r");
   if (!f) return NULL;
   gzbuffer(f, 1u << 18);
@@ -52,9 +240,16 @@ fqr_reader *fqr_open(const char *path) {
   return r;
 }
 
+fqr_reader *fqr_open(const char *path) { return fqr_open_mt(path, 0); }
+
+int fqr_decode_threads(const fqr_reader *r) { return r->pool ? r->pool->n_threads : 1; }
+
 void fqr_close(fqr_reader *r) {
   if (!r) return;
-  gzclose(r->f);
+  if (r->pool)
+    bgzf_pool_close(r->pool);
+  else
+    gzclose(r->f);
   free(r->buf);
   free(r->seq.s);
   free(r->qual.s);
@@ -69,6 +264,42 @@ double fqr_inflate_seconds(const fqr_reader *r) { return r->inflate_s; }
 static int refill(fqr_reader *r) {
   if (r->err) return -3;
   if (r->is_eof) return -1;
+  if (r->pool) { /* next inflated block, in file order; empty blocks (the BGZF end marker) are skipped */
+    bgzf_pool *p = r->pool;
+    const double t0 = now_s();
+    for (;;) {
+      pthread_mutex_lock(&p->mu);
+      bgzf_slot *s = &p->slot[p->next_consume % (uint64_t)p->n_slots];
+      while (s->state != 2) pthread_cond_wait(&p->cv_ready, &p->mu);
+      const int err = s->err;
+      uint32_t n = 0;
+      if (!err) {
+        uint8_t *t = r->buf; /* swap buffers instead of copying */
+        r->buf = s->ubuf;
+        s->ubuf = t;
+        n = s->usize;
+        s->state = 0;
+        p->next_consume++;
+        pthread_cond_broadcast(&p->cv_free);
+      }
+      pthread_mutex_unlock(&p->mu);
+      r->begin = 0;
+      r->end = n;
+      if (err) {
+        r->is_eof = 1;
+        r->inflate_s += now_s() - t0;
+        if (err == -3) {
+          r->err = 1;
+          return -3;
+        }
+        return -1;
+      }
+      if (n) break;
+    }
+    r->bytes_in += r->end;
+    r->inflate_s += now_s() - t0; /* time the framing code waited for the pool */
+    return 0;
+  }
   const double t0 = now_s();
   const int n = gzread(r->f, r->buf, FQR_BUF);
   r->inflate_s += now_s() - t0;

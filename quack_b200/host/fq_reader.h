@@ -13,8 +13,14 @@ extern "C" {
 
 typedef struct fqr_reader fqr_reader;
 
-/* gzopen()s path (gzip, multi-member gzip or plain text).  NULL if it cannot be opened. */
+/* Opens path (gzip, multi-member gzip, BGZF or plain text).  NULL if it cannot be opened.
+ * BGZF input (bgzip / htslib blocked gzip) is inflated by `threads` pool threads (0: QUACK_DECODE_THREADS or
+ * half of the online cores, at most 8; 1: no pool); every other input goes through gzread() like the
+ * reference (quack.c:187).  The bytes handed to the framing code are the same either way. */
 fqr_reader *fqr_open(const char *path);
+fqr_reader *fqr_open_mt(const char *path, int threads);
+int fqr_default_threads(void);
+int fqr_decode_threads(const fqr_reader *r); /* pool threads of this reader (1: gzread path) */
 void fqr_close(fqr_reader *r);
 
 /* Appends whole records to seq[]/qual[]/offset[]/length[] until the stream ends, cap_reads records are
@@ -31,8 +37,9 @@ int fqr_status(const fqr_reader *r); /* 0 while records keep coming, else -1/-2/
  * kseq_read() code; pointers stay valid until the next call; *qual_len == 0 for FASTA records. */
 long fqr_next(fqr_reader *r, const uint8_t **seq, const uint8_t **qual, size_t *qual_len);
 
-/* bytes of decompressed input consumed so far, and seconds spent inside gzread() (host gzip decode,
- * reported separately from the statistics path as BASELINE.json asks) */
+/* bytes of decompressed input consumed so far, and seconds spent inside gzread() -- or, with a BGZF pool,
+ * waiting for the pool's next block (host gzip decode, reported separately from the statistics path as
+ * BASELINE.json asks) */
 uint64_t fqr_bytes_in(const fqr_reader *r);
 double fqr_inflate_seconds(const fqr_reader *r);
 

@@ -13,6 +13,7 @@
  *   QB_LEN_CAP=L        longest read accepted (default 65536)
  *   QB_KERNEL=0|1|2|3   auto | simple | fused | wtile
  *   QB_STATS_JSON=path  write reads/s, bases/s and stage times there (stdout stays the SVG)
+ *   QUACK_DECODE_THREADS=n  inflate threads per BGZF input file (default: half of the cores, at most 8)
  */
 #include <pthread.h>
 #include <stdio.h>
@@ -101,6 +102,7 @@ struct mate_job {
   uint64_t reads, bases, text_bytes;
   double inflate_s, wall_s;
   int stream_status;
+  int decode_threads;
 };
 
 /* reader thread of one mate: inflate + frame + pack + submit, until the stream ends */
@@ -134,6 +136,7 @@ static void *mate_thread(void *arg) {
   j->stream_status = fqr_status(r);
   j->inflate_s = fqr_inflate_seconds(r);
   j->text_bytes = fqr_bytes_in(r);
+  j->decode_threads = fqr_decode_threads(r);
   fqr_close(r);
   j->wall_s = now_s() - t0;
   return NULL;
@@ -242,11 +245,11 @@ int main(int argc, char **argv) {
               "{\"reads\": %llu, \"bases\": %llu, \"text_bytes\": %llu, \"devices\": %d, \"launches\": %llu, "
               "\"stream_s\": %.6f, \"finish_s\": %.6f, \"render_s\": %.6f, \"total_s\": %.6f, "
               "\"host_gzip_decode_s_max_over_mates\": %.6f, \"host_gzip_decode_MBps\": %.2f, "
-              "\"reads_per_s\": %.1f, \"bases_per_s\": %.1f}\n",
+              "\"reads_per_s\": %.1f, \"bases_per_s\": %.1f, \"decode_threads\": %d}\n",
               (unsigned long long)reads, (unsigned long long)bases, (unsigned long long)text, cfg.n_devices,
               (unsigned long long)qb_launch_count(ctx), stream_s, t_finish - t_stream, t_end - t_finish, t_end - t_start,
               inflate, inflate > 0 ? (double)text / cfg.n_mates / inflate / 1e6 : 0.0, (double)reads / stream_s,
-              (double)bases / stream_s);
+              (double)bases / stream_s, jobs[0].decode_threads);
       fclose(f);
     }
   }

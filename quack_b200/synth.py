@@ -61,14 +61,44 @@ def fastq_text(seed: int, mate: int, first_read: int, n_reads: int, length: int,
 
 
 def write_fastq(path: str, seed: int, mate: int, n_reads: int, length: int = 150, adapter_rate: float = 0.1,
-                first_read: int = 0, gz_level: int | None = None, chunk: int = 250_000) -> int:
+                first_read: int = 0, gz_level: int | None = None, chunk: int = 250_000, bgzf: bool = False) -> int:
     """Writes n_reads records; gz_level=None -> plain text, else one gzip member per chunk (multi-member
-    files are what the reference's gzread handles too).  Returns bytes of text written."""
+    files are what the reference's gzread handles too) or, with bgzf=True, BGZF blocks (also a multi-member
+    gzip file to every gzip reader; the host reader inflates them in parallel).  Returns bytes of text written."""
     total = 0
     with open(path, "wb") as f:
         for r0 in range(0, n_reads, chunk):
             n = min(chunk, n_reads - r0)
             txt = fastq_text(seed, mate, first_read + r0, n, length, adapter_rate)
             total += len(txt)
-            f.write(txt if gz_level is None else gzip.compress(txt, compresslevel=gz_level, mtime=0))
+            if bgzf:
+                f.write(bgzf_bytes(txt, gz_level if gz_level is not None else 1)[: -len(BGZF_EOF)])
+            else:
+                f.write(txt if gz_level is None else gzip.compress(txt, compresslevel=gz_level, mtime=0))
+        if bgzf:
+            f.write(BGZF_EOF)
     return total
+
+
+BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def bgzf_bytes(data: bytes, level: int = 1, block: int = 65280) -> bytes:
+    """`data` as a BGZF stream (SAM spec 4.1; reference klib/bgzf.c): independent gzip members of at most
+    `block` uncompressed bytes, each with its size in a 'BC' extra subfield, then the empty end marker.  Any
+    gzip reader (the reference's gzread included) sees one multi-member gzip file."""
+    import struct
+    import zlib
+    out = []
+    for i in range(0, len(data), block):
+        chunk = data[i: i + block]
+        co = zlib.compressobj(level, zlib.DEFLATED, -15)
+        payload = co.compress(chunk) + co.flush()
+        if len(payload) + 26 > 65536:   # incompressible: store
+            co = zlib.compressobj(0, zlib.DEFLATED, -15)
+            payload = co.compress(chunk) + co.flush()
+        bsize = len(payload) + 25
+        out.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + payload +
+                   struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+    out.append(BGZF_EOF)
+    return b"".join(out)

@@ -77,6 +77,26 @@ def test_cli_paired_200k_vs_reference_binary(tmp_path, golden_dir):
         assert r.stdout == open(out, "rb").read()
 
 
+def test_cli_bgzf_input_parallel_decode(tmp_path):
+    """The same reads as BGZF files (decoded by the reader's thread pool) and as gzip files (gzread, like the
+    reference): identical SVG; the reference binary reads the BGZF files too (multi-member gzip)."""
+    g1, g2 = str(tmp_path / "g_1.fq.gz"), str(tmp_path / "g_2.fq.gz")
+    b1, b2 = str(tmp_path / "b_1.fq.gz"), str(tmp_path / "b_2.fq.gz")
+    for mate, g, b in ((1, g1, b1), (2, g2, b2)):
+        synth.write_fastq(g, 2, mate, 60_000, 150, 0.1, gz_level=1)
+        synth.write_fastq(b, 2, mate, 60_000, 150, 0.1, gz_level=1, bgzf=True)
+    outs = {}
+    for tag, f1, f2, thr in (("gz", g1, g2, "1"), ("bgzf1", b1, b2, "1"), ("bgzf4", b1, b2, "4")):
+        js = str(tmp_path / (tag + ".json"))
+        r = _run(["-1", f1, "-2", f2, "-a", util.ADAPTER_FA, "-n", "x"], {"QUACK_DECODE_THREADS": thr, "QB_STATS_JSON": js})
+        assert r.returncode == 0, r.stderr
+        outs[tag] = r.stdout
+        assert json.load(open(js))["decode_threads"] == (4 if tag == "bgzf4" else 1)
+    assert outs["gz"] == outs["bgzf1"] == outs["bgzf4"]
+    if po.have_ref():
+        assert outs["gz"] == po.ref_svg(["-1", b1, "-2", b2, "-a", util.ADAPTER_FA, "-n", "x"])
+
+
 def test_cli_errors(tmp_path):
     r = _run(["-u", str(tmp_path / "missing.fq")])
     assert r.returncode == 2 and b"cannot open" in r.stderr and r.stdout == b""

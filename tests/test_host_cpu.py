@@ -169,3 +169,88 @@ def test_cli_usage_and_exit_codes():
             ref = subprocess.run([po.REF_BIN, *args], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
             got = run(*args)
             assert (got.returncode, got.stdout, got.stderr) == (ref.returncode, ref.stdout, ref.stderr), args
+
+
+# ---- parallel BGZF decode: same bytes to the framing code as gzread() ----
+
+def _fastq_blob(n=3000, seed=5):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        l = int(rng.integers(1, 400))
+        s = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=l))
+        q = bytes((rng.integers(2, 42, size=l) + 33).astype(np.uint8))
+        out.append(b"@r%d some comment\n%s\n+\n%s\n" % (i, s, q))
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("block", [64, 1000, 65280])
+@pytest.mark.parametrize("threads", [1, 2, 8])
+def test_bgzf_pool_equals_gzread_and_oracle(block, threads, tmp_path):
+    """Records straddle block boundaries (tiny blocks), every thread count gives the serial result."""
+    from quack_b200 import synth
+    blob = _fastq_blob()
+    b, g = tmp_path / "r.fq.bgz", tmp_path / "r.fq.gz"
+    b.write_bytes(synth.bgzf_bytes(blob, block=block))
+    g.write_bytes(gzip.compress(blob, 1))
+    assert gzip.decompress(b.read_bytes()) == blob            # a BGZF file is a multi-member gzip file
+    want = capi.parse_records(str(g), 1)
+    assert want[1] == -1 and len(want[0]) == 3000
+    assert capi.parse_records(str(b), threads) == want
+    assert po.parse_records(str(b)) == want
+    # the batching entry point, small batches
+    bb, st = capi.read_batches(str(b), 20000, 100, threads)
+    gb, gst = capi.read_batches(str(g), 20000, 100, 1)
+    assert st == gst == -1 and len(bb) == len(gb)
+    for x, y in zip(bb, gb):
+        assert all(np.array_equal(u, v) for u, v in zip(x[:4], y[:4])) and x[4] == y[4]
+
+
+def test_bgzf_pool_edge_cases(tmp_path):
+    from quack_b200 import synth
+    blob = _fastq_blob(400, seed=6)
+    good = synth.bgzf_bytes(blob, block=3000)
+    cases = {}
+    cases["empty"] = (synth.bgzf_bytes(b""), 0, -1)
+    cases["no_eof_marker"] = (good[: -len(synth.BGZF_EOF)], 400, -1)
+    p = tmp_path / "x.bgz"
+    for name, (data, n, rc) in cases.items():
+        p.write_bytes(data)
+        for t in (1, 4):
+            recs, st = capi.parse_records(str(p), t)
+            assert (len(recs), st) == (n, rc), (name, t)
+    # a block cut short, a flipped payload byte, a gzip member without the BGZF subfield: stream error (-3,
+    # where kseq_read() returns -3 too), the records of the intact blocks in front of it are kept
+    first = int.from_bytes(good[16:18], "little") + 1
+    second = int.from_bytes(good[first + 16: first + 18], "little") + 1
+    t = tmp_path / "plain.fq"
+    t.write_bytes(blob)
+    want, _ = capi.parse_records(str(t), 1)
+    broken = {
+        "truncated": good[: first + second - 5],
+        "flipped": good[: first + 30] + bytes([good[first + 30] ^ 0x55]) + good[first + 31:],
+        "plain_member": good[:first] + gzip.compress(b"@z\nAC\n+\nII\n"),
+    }
+    for name, data in broken.items():
+        p.write_bytes(data)
+        recs, st = capi.parse_records(str(p), 4)
+        assert st == -3, name
+        if recs and recs[-1][1] is None:   # kseq semantics: a record cut inside its sequence comes back as FASTA
+            recs = recs[:-1]
+        assert 0 < len(recs) < len(want) and recs == want[: len(recs)], name   # a prefix of the true record list
+
+
+def test_bgzf_is_only_used_for_bgzf(tmp_path):
+    """Plain text and ordinary gzip keep the gzread() path whatever the thread count."""
+    p = tmp_path / "a.fq"
+    p.write_bytes(b"@a\nACGT\n+\nIIII\n")
+    assert capi.decode_throughput(str(p), 8)["threads"] == 1
+    g = tmp_path / "a.fq.gz"
+    g.write_bytes(gzip.compress(b"@a\nACGT\n+\nIIII\n"))
+    d = capi.decode_throughput(str(g), 8)
+    assert d["threads"] == 1 and d["reads"] == 1
+    from quack_b200 import synth
+    b = tmp_path / "a.fq.bgz"
+    b.write_bytes(synth.bgzf_bytes(b"@a\nACGT\n+\nIIII\n"))
+    d = capi.decode_throughput(str(b), 8)
+    assert d["threads"] == 8 and d["reads"] == 1 and d["bases"] == 4

@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Host decode throughput: inflate + framing + packing of one synthetic
+150-bp FASTQ file, no GPU involved.  gzip file through gzread() (the reference's path, quack.c:187) against
+the same reads as a BGZF file through the reader's inflate pool at 1..N threads.  One JSON line per run.
+usage: decode_bench.py [n_reads] [max_threads]"""
+import json
+import os
+import sys
+import tempfile
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from quack_b200 import capi, synth
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
+tmax = int(sys.argv[2]) if len(sys.argv) > 2 else (os.cpu_count() or 8)
+with tempfile.TemporaryDirectory() as d:
+    gz, bg = os.path.join(d, "s.fq.gz"), os.path.join(d, "s.fq.bgz")
+    text = synth.write_fastq(gz, 2, 1, n, 150, 0.1, gz_level=1)
+    synth.write_fastq(bg, 2, 1, n, 150, 0.1, gz_level=1, bgzf=True)
+    runs = [("gzip/gzread", gz, 1)] + [("bgzf/pool", bg, t) for t in (1, 2, 4, 8, 12, 16, 24, 32) if t <= tmax]
+    base = None
+    for name, path, t in runs:
+        best = None
+        for _ in range(2):
+            r = capi.decode_throughput(path, t)
+            if best is None or r["seconds"] < best["seconds"]:
+                best = r
+        assert best["reads"] == n and best["status"] == -1
+        rate = best["reads"] / best["seconds"]
+        base = base or rate
+        print(json.dumps({"input": name, "file_MB": round(os.path.getsize(path) / 1e6, 1), "threads": best["threads"],
+                          "reads": n, "seconds": round(best["seconds"], 3), "Mreads_s": round(rate / 1e6, 3),
+                          "text_MBps": round(best["text_bytes"] / best["seconds"] / 1e6, 1),
+                          "wait_for_inflate_s": round(best["wait_inflate_s"], 3), "vs_gzread": round(rate / base, 2),
+                          "cores": os.cpu_count()}), flush=True)
