@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
   extern __shared__ __align__(128) uint8_t smem[];
   const PeriodPlan &P = args.plan;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  // (making `warp` provably warp-uniform with a shuffle moves the TMA operands into uniform registers and drops
+  // the elect loops around UBLKCP, but measured 1.5-3 % slower: profiles/r01c_v5/notes.md)
   const uint32_t smem_s = smem_u32(smem);
   constexpr uint32_t kFull = 0xffffffffu;
 
