@@ -50,7 +50,7 @@ typedef enum {
 } qb_status;
 
 typedef enum {
-  QB_KERNEL_AUTO = 0,      /* period kernel for batches of back-to-back reads of one even length in [32, 256]; else the
+  QB_KERNEL_AUTO = 0,      /* period kernel for batches of back-to-back reads of one length in [32, 256]; else the
                               fused kernel up to 320 bp, the warp-tile kernel, or simple */
   QB_KERNEL_SIMPLE = 1,    /* one warp per read, global atomics: any len_cap, slow */
   QB_KERNEL_FUSED = 2,     /* CTA-wide TMA-staged tiles, joint (base,score) shared-memory histogram (v3) */

@@ -238,7 +238,7 @@ int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaS
                             (uint32_t)d.smem_reserved, ctx->qbase);
   if (kernel == QB_KERNEL_PERIOD) {
     if (!pplan.ok)
-      return fail(ctx, QB_ERR_CAPACITY, "the period kernel needs a batch of back-to-back reads of one even length in [32, %u]",
+      return fail(ctx, QB_ERR_CAPACITY, "the period kernel needs a batch of back-to-back reads of one length in [32, %u]",
                   qb::kPeriodMaxLen);
     kernel = QB_KERNEL_AUTO;  // for the reads that do not fill a tile
   }

@@ -114,12 +114,13 @@ cudaError_t wtile_configure();  // opt in to the large dynamic shared memory onc
 constexpr uint32_t kPeriodMaxLen = 256;  // two histogram blocks of 128 positions
 
 struct PeriodPlan {
-  uint32_t len;              // the common read length l (even, 32..256)
+  uint32_t len;              // the common read length l (32..256; odd lengths up to 159)
   uint32_t k;                // reads per period: k * l is a multiple of 4
   uint32_t wp;               // 32-bit words per period = k * l / 4
   uint32_t steps;            // warp steps per period = ceil(wp / 32): 3, 4 or 5 (template parameter)
-  uint32_t ppt;              // periods per tile: tile_bytes = ppt * k * l is a multiple of 16
-  uint32_t tile_bytes;
+  uint32_t ppt;              // periods per tile
+  uint32_t tile_bytes;       // ppt * k * l, a multiple of 4
+  uint32_t buf_bytes;        // one staged buffer (bases or quality bytes of a tile + alignment slack + padding)
   uint32_t reads_per_tile;   // ppt * k, a multiple of 4
   uint32_t stages;           // staged tiles per warp (2..4)
   uint32_t warps;            // autonomous warps per CTA (one CTA per SM): 24, 20 or 16 (template parameter)

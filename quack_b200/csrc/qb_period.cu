@@ -1,6 +1,6 @@
 // qb_period.cu -- period kernel (v5) for quack's per-read statistics accumulation
 // (reference: the while loop of read_fastq(), quack.c:193-221), for batches whose reads all have ONE length
-// l (even, 32..256 bp) and lie back to back -- the shape of untrimmed Illumina data (configs 1-3, 5).
+// l (32..256 bp) and lie back to back -- the shape of untrimmed Illumina data (configs 1-3, 5).
 //
 // The v3 / v4 kernels are bound by the shared-memory pipe (ncu: 84 % busy once the 1.4-cycle cost of a shared
 // atomic is counted): they touch every base three times there (TMA fill, flat pass that writes key bytes,
@@ -48,6 +48,11 @@ constexpr uint32_t kPoCount = 32;                  // -a: number of queued ancho
 constexpr uint32_t kPoQueue = 48;                  // -a: kPQueue u16 word indices of anchor hits
 constexpr uint32_t kPQueue = 64;                   //     (more hits in a tile: several rounds of queue + confirm)
 constexpr uint32_t kPoFhit = kPoQueue + kPQueue * 2u;  // -a: first-hit position per read of the tile
+// one staged buffer: the tile's bytes from the 16-byte boundary below its first byte to the one above its last
+// (tile_bytes is a multiple of 4, not of 16: a tile starts 0, 4, 8 or 12 bytes behind a boundary) + padding
+__host__ __device__ inline uint32_t pbuf_bytes(uint32_t tile_bytes) {
+  return ((tile_bytes + 15u) & ~15u) + ((tile_bytes & 15u) ? 16u : 0u) + kPPad;
+}
 __host__ __device__ inline uint32_t pblock_hdr(int adapters, uint32_t rpt) {
   return adapters ? kPoFhit + ((rpt * 4u + 15u) & ~15u) : kPoCount;
 }
@@ -101,7 +106,7 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
   return v;
 }
 
-template <bool kAd, int kS, int kPW>
+template <bool kAd, int kS, int kPW, bool kOdd>
 __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_constant__ PArgs args) {
   constexpr uint32_t kPThreads = kPW * 32;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -119,7 +124,8 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
   auto gen = [&](uint32_t shared_addr) -> uint8_t * { return smem + (shared_addr - smem_s); };
 
   const uint32_t len = P.len, wp = P.wp, pbytes = P.wp * 4u, ppt = P.ppt, rpt = P.reads_per_tile;
-  const uint32_t tb = P.tile_bytes, buf = P.tile_bytes + kPPad, stages = P.stages, nblocks = P.nblocks;
+  const uint32_t tb = P.tile_bytes, buf = P.buf_bytes, stages = P.stages, nblocks = P.nblocks;
+  const bool aligned = (tb & 15u) == 0u;  // every tile starts on a 16-byte boundary (4 x 150 bp x 2 = 1200 B)
   const uint32_t last = wp - 32u * (uint32_t)(kS - 1);  // active lanes of the last step (1..32)
 
   // ---- this warp's block ----
@@ -198,6 +204,15 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
   for (int s = 0; s < kS; s++)
 #pragma unroll
     for (int j = 0; j < 4; j++) col[s][j] = p_slot_addr(args.slot[(4u * (32u * s + lane) + j) % len]);
+  // Even l: the j-th byte of a word always holds positions of the parity of j, the increments are the two
+  // constants.  Odd l: the parity also depends on the read inside the period -> one increment per column.
+  uint32_t inc[kOdd ? kS : 1][4];
+  if (kOdd) {
+#pragma unroll
+    for (int s = 0; s < (kOdd ? kS : 1); s++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) inc[s][j] = (((4u * (32u * s + lane) + j) % len) & 1u) ? inc_hi : inc_lo;
+  }
   const uint32_t afilt_or = P.afilt_s | ((lane >> 2) * 4u);  // this lane's copy of the anchor map (8 copies, 32-byte rows)
   const uint32_t nxt = (lane + 1u) & 31u;
   const uint32_t len_magic = 0xFFFFFFFFu / len + 1u;  // floor(b / len) = umulhi(b, len_magic) for b < 2^24
@@ -244,9 +259,17 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
       const size_t off = (size_t)t * tb;
       // the TMA (async proxy) write must be ordered behind the generic-proxy accesses to the buffer
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive_expect_tx_s(bar_s, 2u * tb);
-      bulk_g2s_s(dst, args.seq + off, tb, bar_s);
-      bulk_g2s_s(dst + buf, args.qual + off, tb, bar_s);
+      if (aligned) {
+        mbar_arrive_expect_tx_s(bar_s, 2u * tb);
+        bulk_g2s_s(dst, args.seq + off, tb, bar_s);
+        bulk_g2s_s(dst + buf, args.qual + off, tb, bar_s);
+      } else {
+        const uint32_t so = (uint32_t)(off & 15u);       // the copy starts at the 16-byte boundary below the tile
+        const uint32_t bytes = (so + tb + 15u) & ~15u;   // (the batch buffers are readable 64 bytes past their end)
+        mbar_arrive_expect_tx_s(bar_s, 2u * bytes);
+        bulk_g2s_s(dst, args.seq + (off - so), bytes, bar_s);
+        bulk_g2s_s(dst + buf, args.qual + (off - so), bytes, bar_s);
+      }
     }
   };
 
@@ -313,7 +336,7 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
         if (t2 < n_tiles) issue(s2, t2);
       }
       mbar_wait(wb_s + kPoBar + 8u * st, phase);
-      const uint32_t seq_s = ring_s + 2u * st * buf;
+      const uint32_t seq_s = ring_s + 2u * st * buf + (aligned ? 0u : (uint32_t)(((size_t)tile * tb) & 15u));
       uint32_t hm = 0;  // -a: this lane's anchor hits of the tile, one bit per (period, step)
 
       for (uint32_t pp = 0; pp < ppt; pp++) {
@@ -362,10 +385,10 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
         for (int s = 0; s < kS; s++) {
           const bool act = s < kS - 1 || lane < last;
           if (act) {
-            red_shared_add<0u>(__byte_perm(K[s], col[s][0], 0x7604), inc_lo);
-            red_shared_add<0u>(__byte_perm(K[s], col[s][1], 0x7614), inc_hi);
-            red_shared_add<0u>(__byte_perm(K[s], col[s][2], 0x7624), inc_lo);
-            red_shared_add<0u>(__byte_perm(K[s], col[s][3], 0x7634), inc_hi);
+            red_shared_add<0u>(__byte_perm(K[s], col[s][0], 0x7604), kOdd ? inc[kOdd ? s : 0][0] : inc_lo);
+            red_shared_add<0u>(__byte_perm(K[s], col[s][1], 0x7614), kOdd ? inc[kOdd ? s : 0][1] : inc_hi);
+            red_shared_add<0u>(__byte_perm(K[s], col[s][2], 0x7624), kOdd ? inc[kOdd ? s : 0][2] : inc_lo);
+            red_shared_add<0u>(__byte_perm(K[s], col[s][3], 0x7634), kOdd ? inc[kOdd ? s : 0][3] : inc_hi);
           }
         }
       }
@@ -424,20 +447,12 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
 // plan: period / tile geometry and shared-memory map
 // ------------------------------------------------------------------------------------------
 
-static uint32_t gcd_u32(uint32_t a, uint32_t b) {
-  while (b) {
-    const uint32_t t = a % b;
-    a = b;
-    b = t;
-  }
-  return a;
-}
-
 static PeriodPlan period_plan_w(uint32_t l, uint32_t first_offset, int adapters, int sm_count, uint32_t smem_optin,
-                                uint32_t smem_reserved, uint32_t qbase, uint32_t warps) {
+                                uint32_t smem_reserved, uint32_t qbase, uint32_t warps, bool full_tiles) {
   PeriodPlan p;
   memset(&p, 0, sizeof p);
-  if (l < 32u || l > kPeriodMaxLen || (l & 1u) || (first_offset & 15u)) return p;
+  if (l < 32u || l > kPeriodMaxLen || (first_offset & 15u)) return p;
+  if ((l & 1u) && warps != 16u) return p;  // odd lengths keep one increment per column in registers: 16 warps
   p.len = l;
   p.qbase = qbase;
   p.nblocks = l > 128u ? 2u : 1u;
@@ -477,10 +492,10 @@ static PeriodPlan period_plan_w(uint32_t l, uint32_t first_offset, int adapters,
   if (want > kPMaxStages) want = kPMaxStages;
 
   // Reads per period: a multiple of k0 (so that the period is a whole number of words) with 3..5 warp steps;
-  // candidates in order of how well they fill the last step.  Periods per tile: tile bytes a multiple of 16,
+  // candidates in order of how well they fill the last step.  Periods per tile:
   // reads per tile a multiple of 4 (the rest of the batch goes to a kernel that loads 4 offsets at a time),
   // about `target` bytes.  The first candidate whose kPW warp blocks fit the gaps wins.
-  const uint32_t k0 = (l & 3u) ? 2u : 1u;
+  const uint32_t k0 = (l & 1u) ? 4u : ((l & 3u) ? 2u : 1u);
   bool used[64] = {false};
   for (;;) {
     uint32_t bk = 0;
@@ -494,21 +509,22 @@ static PeriodPlan period_plan_w(uint32_t l, uint32_t first_offset, int adapters,
     if (!bk) return p;
     used[bk] = true;
     const uint32_t wp = bk * l / 4u, pb = wp * 4u;
-    uint32_t ppt0 = 16u / gcd_u32(pb, 16u);
+    uint32_t ppt0 = 1;
     while ((ppt0 * bk) & 3u) ppt0 *= 2u;
     if (ppt0 * bk > kPMaxRpt) continue;
     uint32_t ppt = ppt0;
     while (ppt * pb < target && (ppt + ppt0) * bk <= kPMaxRpt) ppt += ppt0;
     for (; ppt >= ppt0 && !p.ok; ppt -= ppt0) {
-      if (ppt * wp > 65535u || ppt * ((wp + 31u) / 32u) > 32u) continue;  // u16 queue entries, one hit bit per (period, step)
+      if (ppt * wp > 65535u || ppt * ((wp + 31u) / 32u) > 32u) continue;
+      if (full_tiles && ppt * pb < target && (ppt + ppt0) * bk <= kPMaxRpt) break;  // smaller tiles: only in the second round  // u16 queue entries, one hit bit per (period, step)
       for (uint32_t stages = want; stages >= 2u && !p.ok; stages--) {
-        const uint32_t wblock = pblock_hdr(adapters, ppt * bk) + stages * 2u * (ppt * pb + kPPad);
+        const uint32_t wblock = pblock_hdr(adapters, ppt * bk) + stages * 2u * pbuf_bytes(ppt * pb);
         uint32_t fit = 0;
         for (int g = 0; g < 3; g++) fit += (gap[g].b - gap[g].a) / wblock;
         if (fit < warps) continue;
         p.k = bk, p.wp = wp, p.steps = (wp + 31u) / 32u;
         p.ppt = ppt, p.tile_bytes = ppt * pb, p.reads_per_tile = ppt * bk;
-        p.stages = stages, p.wblock = wblock;
+        p.stages = stages, p.wblock = wblock, p.buf_bytes = pbuf_bytes(ppt * pb);
         p.ok = 1;
       }
     }
@@ -537,19 +553,22 @@ PeriodPlan period_plan(uint32_t l, uint32_t first_offset, int adapters, int sm_c
   if (const char *e = getenv("QB_PT_WARPS")) forced = (uint32_t)atoi(e);  // tuning hook
   PeriodPlan p;
   memset(&p, 0, sizeof p);
-  for (uint32_t w : {24u, 20u, 16u}) {
-    if (forced && w != forced) continue;
-    p = period_plan_w(l, first_offset, adapters, sm_count, smem_optin, smem_reserved, qbase, w);
-    if (p.ok) break;
-  }
+  // tile size first (the per-tile costs -- TMA issue, barrier, the -a confirmation pass -- are fixed), then warps
+  for (int full = 1; full >= 0 && !p.ok; full--)
+    for (uint32_t w : {24u, 20u, 16u}) {
+      if (forced && w != forced) continue;
+      p = period_plan_w(l, first_offset, adapters, sm_count, smem_optin, smem_reserved, qbase, w, full != 0);
+      if (p.ok) break;
+    }
   return p;
 }
 
 // ------------------------------------------------------------------------------------------
 // Position -> u16 slot of a histogram row.
-// The half-word is position & 1 (l is even, so the j-th byte of a word always holds positions of one parity
-// and the increments are compile-time constants); odd position p shares the u32 column of p - 1.  The column
-// of an even position is free, and it decides the BANK its 188 counters live in.  The 32 lanes of warp step
+// The half-word is position & 1; positions 2 e and 2 e + 1 share a u32 column.  (For even l the j-th byte of a
+// word always holds positions of the parity of j, so the increments are two constants; for odd l the kernel
+// keeps one increment per column register.)  The column of a pair is free, and it decides the BANK its 188
+// counters live in.  The 32 lanes of warp step
 // (s, j) update positions (4 (32 s + lane) + j) mod l: a conflict-free step needs 32 different banks.  All
 // steps cannot be conflict-free (a bank holds at most 2 * nblocks even positions, and a position occurs in k
 // steps), so the solver looks for the smallest set of steps to give up and colours the conflict graph of the
@@ -560,8 +579,8 @@ namespace {
 
 struct SlotSolver {
   uint32_t E = 0, cap = 0, nsets = 0;
-  uint8_t set[16][32];
-  uint32_t set_n[16];
+  uint8_t set[20][32];
+  uint32_t set_n[20];
   uint64_t rng = 0x9E3779B97F4A7C15ull;
   uint32_t rnd() {
     rng ^= rng << 13, rng ^= rng >> 7, rng ^= rng << 17;
@@ -623,7 +642,7 @@ struct SlotCache {  // the last table solved for each read length
 }  // namespace
 
 static void period_slots(const PeriodPlan &p, uint8_t *slot) {
-  const uint32_t l = p.len, E = l / 2u, cap = 2u * p.nblocks;
+  const uint32_t l = p.len, E = (l + 1u) / 2u, cap = 2u * p.nblocks;  // E pairs of positions (one u32 column each)
   // natural layout (also the fallback): positions 4 c .. 4 c + 3 of a block in bank c
   for (uint32_t pos = 0; pos < kPeriodMaxLen; pos++) {
     const uint32_t blk = pos >> 7, q = pos & 127u;
@@ -639,7 +658,7 @@ static void period_slots(const PeriodPlan &p, uint8_t *slot) {
   SlotSolver sv;
   sv.E = E, sv.cap = cap;
   for (uint32_t s = 0; s < p.steps; s++)
-    for (uint32_t j = 0; j < 4u; j += 2u) {
+    for (uint32_t j = 0; j < 4u; j += (l & 1u) ? 1u : 2u) {  // even l: byte j + 1 touches the same columns as byte j
       uint32_t n = 0;
       for (uint32_t i = 0; i < 32u && 32u * s + i < p.wp; i++) sv.set[sv.nsets][n++] = (uint8_t)(((4u * (32u * s + i) + j) % l) / 2u);
       sv.set_n[sv.nsets++] = n;
@@ -672,7 +691,8 @@ static void period_slots(const PeriodPlan &p, uint8_t *slot) {
     const uint32_t b = best_bank[e], i = cnt[b]++;
     if (i >= cap) ok = false;
     const uint8_t v = (uint8_t)((i >> 1) << 7 | (b + 32u * (i & 1u)));
-    slot[2u * e] = v, slot[2u * e + 1u] = v;
+    slot[2u * e] = v;
+    if (2u * e + 1u < kPeriodMaxLen) slot[2u * e + 1u] = v;
   }
   if (!ok)  // cannot happen (the natural layout respects the capacity); keep the natural layout
     for (uint32_t pos = 0; pos < kPeriodMaxLen; pos++) {
@@ -683,33 +703,35 @@ static void period_slots(const PeriodPlan &p, uint8_t *slot) {
   cache->k[l] = (uint8_t)p.k;
 }
 
-template <bool kAd, int kPW>
+template <bool kAd, int kPW, bool kOdd>
 static cudaError_t period_launch_steps(const PArgs &args, uint32_t grid, cudaStream_t stream) {
   const uint32_t smem = args.plan.smem_bytes;
   switch (args.plan.steps) {
-    case 3: period_kernel<kAd, 3, kPW><<<grid, kPW * 32, smem, stream>>>(args); break;
-    case 4: period_kernel<kAd, 4, kPW><<<grid, kPW * 32, smem, stream>>>(args); break;
-    case 5: period_kernel<kAd, 5, kPW><<<grid, kPW * 32, smem, stream>>>(args); break;
+    case 3: period_kernel<kAd, 3, kPW, kOdd><<<grid, kPW * 32, smem, stream>>>(args); break;
+    case 4: period_kernel<kAd, 4, kPW, kOdd><<<grid, kPW * 32, smem, stream>>>(args); break;
+    case 5: period_kernel<kAd, 5, kPW, kOdd><<<grid, kPW * 32, smem, stream>>>(args); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 template <bool kAd>
 static cudaError_t period_launch_warps(const PArgs &args, uint32_t grid, cudaStream_t stream) {
+  if (args.plan.len & 1u) return args.plan.warps == 16u ? period_launch_steps<kAd, 16, true>(args, grid, stream) : cudaErrorInvalidValue;
   switch (args.plan.warps) {
-    case 16: return period_launch_steps<kAd, 16>(args, grid, stream);
-    case 20: return period_launch_steps<kAd, 20>(args, grid, stream);
-    case 24: return period_launch_steps<kAd, 24>(args, grid, stream);
+    case 16: return period_launch_steps<kAd, 16, false>(args, grid, stream);
+    case 20: return period_launch_steps<kAd, 20, false>(args, grid, stream);
+    case 24: return period_launch_steps<kAd, 24, false>(args, grid, stream);
     default: return cudaErrorInvalidValue;
   }
 }
 
 cudaError_t period_configure() {
   cudaError_t e;
-#define QB_PCFG(A, S, W)                                                                                                \
-  if ((e = cudaFuncSetAttribute(period_kernel<A, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
-#define QB_PCFG3(A, W) QB_PCFG(A, 3, W) QB_PCFG(A, 4, W) QB_PCFG(A, 5, W)
-  QB_PCFG3(false, 16) QB_PCFG3(false, 20) QB_PCFG3(false, 24) QB_PCFG3(true, 16) QB_PCFG3(true, 20) QB_PCFG3(true, 24)
+#define QB_PCFG(A, S, W, O)                                                                                             \
+  if ((e = cudaFuncSetAttribute(period_kernel<A, S, W, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+#define QB_PCFG3(A, W, O) QB_PCFG(A, 3, W, O) QB_PCFG(A, 4, W, O) QB_PCFG(A, 5, W, O)
+  QB_PCFG3(false, 16, false) QB_PCFG3(false, 20, false) QB_PCFG3(false, 24, false) QB_PCFG3(true, 16, false)
+  QB_PCFG3(true, 20, false) QB_PCFG3(true, 24, false) QB_PCFG3(false, 16, true) QB_PCFG3(true, 16, true)
 #undef QB_PCFG3
 #undef QB_PCFG
   return cudaSuccess;

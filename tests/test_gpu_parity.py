@@ -30,7 +30,7 @@ def keys(table):
 
 
 # ---- period kernel (v5): uniform-length batches only ----
-PERIOD_LENS = [32, 36, 50, 64, 76, 100, 126, 128, 130, 150, 200, 248, 256]
+PERIOD_LENS = [32, 33, 36, 50, 51, 64, 76, 100, 101, 126, 128, 130, 150, 151, 200, 248, 250, 256]
 
 
 @pytest.mark.parametrize("l", PERIOD_LENS)
@@ -44,7 +44,7 @@ def test_period_uniform(l, ad, resident, table, keys):
     util.assert_same(got, po.accumulate_batch(*batch, table if ad else None), f"period {l}")
 
 
-@pytest.mark.parametrize("l", [100, 150])
+@pytest.mark.parametrize("l", [100, 150, 151])
 def test_period_all_byte_values(l, table, keys):
     rng = np.random.default_rng(l)
     n = 6000
