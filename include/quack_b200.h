@@ -159,6 +159,10 @@ uint64_t qb_launch_count(const qb_ctx *ctx);
 int qb_kernel_counts(const qb_ctx *ctx, uint64_t *n_simple, uint64_t *n_fused);
 /* How many launches took the period kernel (they are also counted in n_fused above). */
 uint64_t qb_period_launch_count(const qb_ctx *ctx);
+/* Bytes queued for host-to-device copy by qb_submit() / qb_submit_from() / qb_accumulate_host() so far: bases +
+ * quality bytes of every batch, plus offsets / lengths of the reads that do not take the period kernel (it needs
+ * none: the host verified the batch shape).  bench.py reports e2e.h2d_bytes_per_step from this counter. */
+uint64_t qb_h2d_bytes(const qb_ctx *ctx);
 /* Live kernel timing: after qb_profile_enable(ctx, n) every statistics-kernel launch is bracketed by
  * a CUDA event pair on the stream it is launched on (up to n launches, then recording stops).
  * qb_profile_collect() synchronises and returns the per-launch durations in ms and the algorithmic

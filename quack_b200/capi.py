@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
     L.qb_kernel_counts.argtypes = [vp, _u64p, _u64p]
     L.qb_period_launch_count.argtypes = [vp]
     L.qb_period_launch_count.restype = C.c_uint64
+    L.qb_h2d_bytes.argtypes = [vp]
+    L.qb_h2d_bytes.restype = C.c_uint64
     L.qb_profile_enable.argtypes = [vp, C.c_int]
     L.qb_profile_collect.argtypes = [vp, C.POINTER(C.c_float), _u64p, C.c_int]
     L.qb_timer_start.argtypes = [vp, C.c_int]
@@ -301,6 +303,11 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(lib().qb_launch_count(self.h))
+
+    @property
+    def h2d_bytes(self) -> int:
+        """Bytes queued for host-to-device copy by the submit calls so far."""
+        return int(lib().qb_h2d_bytes(self.h))
 
     @property
     def period_launch_count(self) -> int:

@@ -98,6 +98,7 @@ struct qb_ctx {
   uint64_t next_slot = 0;
   std::string err;
   uint64_t launches = 0, launches_fused = 0, launches_simple = 0, launches_period = 0;
+  uint64_t h2d_bytes = 0;  // bytes queued for host-to-device copy by qb_submit*() so far
   size_t acc_u64 = 0;  // len_cap*97 + counters
   qb::AdapterSet ad_host_template{};
   uint32_t n_anchors = 0;     // distinct 7-mer anchors of the adapter set
@@ -225,17 +226,24 @@ int launch_other(qb_ctx *ctx, Device &d, const qb::BatchView &v, qb::Accum ac, c
   return QB_OK;
 }
 
+// the period-kernel plan for a batch view, ok = 0 if the batch goes to the other kernels
+qb::PeriodPlan period_plan_for(const qb_ctx *ctx, const Device &d, const qb::BatchView &v, int adapters) {
+  const int kernel = ctx->cfg.kernel;
+  qb::PeriodPlan p{};
+  if ((kernel == QB_KERNEL_AUTO || kernel == QB_KERNEL_PERIOD) && v.uniform_len && v.uniform_len <= ctx->cfg.len_cap &&
+      (!v.max_len || v.uniform_len <= v.max_len))
+    p = qb::period_plan(v.uniform_len, v.first_offset, adapters, d.sm_count, (uint32_t)d.smem_optin,
+                        (uint32_t)d.smem_reserved, ctx->qbase);
+  return p;
+}
+
 // chooses and launches the statistics kernel(s) for one device-resident batch
 int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaStream_t stream) {
   if (v.n_reads == 0) return QB_OK;
   const qb::AdapterSet ad = adapter_set(ctx, d);
   qb::Accum ac = accum(ctx, d, mate);
   int kernel = ctx->cfg.kernel;
-  qb::PeriodPlan pplan{};
-  if ((kernel == QB_KERNEL_AUTO || kernel == QB_KERNEL_PERIOD) && v.uniform_len && v.uniform_len <= ctx->cfg.len_cap &&
-      (!v.max_len || v.uniform_len <= v.max_len))
-    pplan = qb::period_plan(v.uniform_len, v.first_offset, ad.enabled, d.sm_count, (uint32_t)d.smem_optin,
-                            (uint32_t)d.smem_reserved, ctx->qbase);
+  const qb::PeriodPlan pplan = period_plan_for(ctx, d, v, ad.enabled);
   if (kernel == QB_KERNEL_PERIOD) {
     if (!pplan.ok)
       return fail(ctx, QB_ERR_CAPACITY, "the period kernel needs a batch of back-to-back reads of one length in [32, %u]",
@@ -518,11 +526,22 @@ static int submit_on(qb_ctx *ctx, int di, int si, int mate, const uint8_t *seq, 
       QB_CUDA(ctx, cudaMemcpyAsync(s.d_seq, seq, n_bytes, cudaMemcpyHostToDevice, s.stream));
       QB_CUDA(ctx, cudaMemcpyAsync(s.d_qual, qual, n_bytes, cudaMemcpyHostToDevice, s.stream));
     }
-    QB_CUDA(ctx, cudaMemcpyAsync(s.d_off, offset, (size_t)n_reads * 4, cudaMemcpyHostToDevice, s.stream));
-    QB_CUDA(ctx, cudaMemcpyAsync(s.d_len, length, (size_t)n_reads * 4, cudaMemcpyHostToDevice, s.stream));
     qb::BatchView v{s.d_seq, s.d_qual, s.d_off, s.d_len, n_reads, n_bytes, max_len ? max_len : ctx->cfg.len_cap, s.d_tiles};
     if (ctx->cfg.kernel == QB_KERNEL_AUTO || ctx->cfg.kernel == QB_KERNEL_PERIOD)
       v.uniform_len = detect_uniform(offset, length, n_reads, &v.first_offset);
+    // The period kernel needs no offsets / lengths on the device (the host just verified the batch shape): only
+    // those of the reads it leaves to the other kernels (< reads_per_tile at the end of the batch) are copied.
+    uint32_t r0 = 0;
+    const qb::PeriodPlan pp = period_plan_for(ctx, d, v, ctx->cfg.adapters_enabled ? 1 : 0);
+    if (pp.ok) r0 = n_reads / pp.reads_per_tile * pp.reads_per_tile;
+    if (r0 < n_reads) {
+      QB_CUDA(ctx, cudaMemcpyAsync(s.d_off + r0, offset + r0, (size_t)(n_reads - r0) * 4, cudaMemcpyHostToDevice, s.stream));
+      QB_CUDA(ctx, cudaMemcpyAsync(s.d_len + r0, length + r0, (size_t)(n_reads - r0) * 4, cudaMemcpyHostToDevice, s.stream));
+    }
+    {
+      std::lock_guard<std::mutex> lk(ctx->mu);
+      ctx->h2d_bytes += 2 * n_bytes + 8ull * (n_reads - r0);
+    }
     int rc = launch_batch(ctx, d, v, mate, s.stream);
     if (rc) return rc;
   }
@@ -719,6 +738,7 @@ int qb_kernel_counts(const qb_ctx *ctx, uint64_t *n_simple, uint64_t *n_fused) {
 }
 
 uint64_t qb_period_launch_count(const qb_ctx *ctx) { return ctx ? ctx->launches_period : 0; }
+uint64_t qb_h2d_bytes(const qb_ctx *ctx) { return ctx ? ctx->h2d_bytes : 0; }
 
 int qb_profile_enable(qb_ctx *ctx, int max_launches) {
   if (!ctx || max_launches < 0) return QB_ERR_ARG;
