@@ -376,9 +376,17 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
     QB_CREATE_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.id));
     QB_CREATE_CUDA(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.id));
     QB_CREATE_CUDA(cudaDeviceGetAttribute(&d.smem_reserved, cudaDevAttrReservedSharedMemoryPerBlock, d.id));
-    QB_CREATE_CUDA(qb::fused_configure());
-    QB_CREATE_CUDA(qb::wtile_configure());
-    QB_CREATE_CUDA(qb::period_configure());
+    {  // opt every kernel in to the large dynamic shared memory: once per device and process (42 + 4 kernels)
+      static std::mutex cfg_mu;
+      static bool configured[256] = {false};
+      std::lock_guard<std::mutex> lk(cfg_mu);
+      if (d.id >= 256 || !configured[d.id]) {
+        QB_CREATE_CUDA(qb::fused_configure());
+        QB_CREATE_CUDA(qb::wtile_configure());
+        QB_CREATE_CUDA(qb::period_configure());
+        if (d.id < 256) configured[d.id] = true;
+      }
+    }
     QB_CREATE_CUDA(cudaStreamCreateWithFlags(&d.main_stream, cudaStreamNonBlocking));
     d.acc.resize(cfg.n_mates);
     for (int m = 0; m < cfg.n_mates; m++) {

@@ -106,7 +106,7 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
   return v;
 }
 
-template <bool kAd, int kS, int kPW, bool kOdd>
+template <bool kAd, int kS, int kPW, bool kOdd, bool kAligned>
 __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_constant__ PArgs args) {
   constexpr uint32_t kPThreads = kPW * 32;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
 
   const uint32_t len = P.len, wp = P.wp, pbytes = P.wp * 4u, ppt = P.ppt, rpt = P.reads_per_tile;
   const uint32_t tb = P.tile_bytes, buf = P.buf_bytes, stages = P.stages, nblocks = P.nblocks;
-  const bool aligned = (tb & 15u) == 0u;  // every tile starts on a 16-byte boundary (4 x 150 bp x 2 = 1200 B)
+  constexpr bool aligned = kAligned;  // tile_bytes % 16 == 0: every tile starts on a 16-byte boundary (8 x 150 bp)
   const uint32_t last = wp - 32u * (uint32_t)(kS - 1);  // active lanes of the last step (1..32)
 
   // ---- this warp's block ----
@@ -703,35 +703,40 @@ static void period_slots(const PeriodPlan &p, uint8_t *slot) {
   cache->k[l] = (uint8_t)p.k;
 }
 
-template <bool kAd, int kPW, bool kOdd>
+template <bool kAd, int kPW, bool kOdd, bool kAligned>
 static cudaError_t period_launch_steps(const PArgs &args, uint32_t grid, cudaStream_t stream) {
   const uint32_t smem = args.plan.smem_bytes;
   switch (args.plan.steps) {
-    case 3: period_kernel<kAd, 3, kPW, kOdd><<<grid, kPW * 32, smem, stream>>>(args); break;
-    case 4: period_kernel<kAd, 4, kPW, kOdd><<<grid, kPW * 32, smem, stream>>>(args); break;
-    case 5: period_kernel<kAd, 5, kPW, kOdd><<<grid, kPW * 32, smem, stream>>>(args); break;
+    case 3: period_kernel<kAd, 3, kPW, kOdd, kAligned><<<grid, kPW * 32, smem, stream>>>(args); break;
+    case 4: period_kernel<kAd, 4, kPW, kOdd, kAligned><<<grid, kPW * 32, smem, stream>>>(args); break;
+    case 5: period_kernel<kAd, 5, kPW, kOdd, kAligned><<<grid, kPW * 32, smem, stream>>>(args); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
+// instantiated: even lengths x {16, 20, 24 warps} x {tiles on 16-byte boundaries or not}; odd lengths x 16 warps
 template <bool kAd>
 static cudaError_t period_launch_warps(const PArgs &args, uint32_t grid, cudaStream_t stream) {
-  if (args.plan.len & 1u) return args.plan.warps == 16u ? period_launch_steps<kAd, 16, true>(args, grid, stream) : cudaErrorInvalidValue;
+  if (args.plan.len & 1u)
+    return args.plan.warps == 16u ? period_launch_steps<kAd, 16, true, false>(args, grid, stream) : cudaErrorInvalidValue;
+  const bool al = (args.plan.tile_bytes & 15u) == 0u;
   switch (args.plan.warps) {
-    case 16: return period_launch_steps<kAd, 16, false>(args, grid, stream);
-    case 20: return period_launch_steps<kAd, 20, false>(args, grid, stream);
-    case 24: return period_launch_steps<kAd, 24, false>(args, grid, stream);
+    case 16: return al ? period_launch_steps<kAd, 16, false, true>(args, grid, stream) : period_launch_steps<kAd, 16, false, false>(args, grid, stream);
+    case 20: return al ? period_launch_steps<kAd, 20, false, true>(args, grid, stream) : period_launch_steps<kAd, 20, false, false>(args, grid, stream);
+    case 24: return al ? period_launch_steps<kAd, 24, false, true>(args, grid, stream) : period_launch_steps<kAd, 24, false, false>(args, grid, stream);
     default: return cudaErrorInvalidValue;
   }
 }
 
 cudaError_t period_configure() {
   cudaError_t e;
-#define QB_PCFG(A, S, W, O)                                                                                             \
-  if ((e = cudaFuncSetAttribute(period_kernel<A, S, W, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
-#define QB_PCFG3(A, W, O) QB_PCFG(A, 3, W, O) QB_PCFG(A, 4, W, O) QB_PCFG(A, 5, W, O)
-  QB_PCFG3(false, 16, false) QB_PCFG3(false, 20, false) QB_PCFG3(false, 24, false) QB_PCFG3(true, 16, false)
-  QB_PCFG3(true, 20, false) QB_PCFG3(true, 24, false) QB_PCFG3(false, 16, true) QB_PCFG3(true, 16, true)
+#define QB_PCFG(A, S, W, O, L)                                                                                          \
+  if ((e = cudaFuncSetAttribute(period_kernel<A, S, W, O, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+#define QB_PCFG3(A, W, O, L) QB_PCFG(A, 3, W, O, L) QB_PCFG(A, 4, W, O, L) QB_PCFG(A, 5, W, O, L)
+#define QB_PCFG_EVEN(A, W) QB_PCFG3(A, W, false, true) QB_PCFG3(A, W, false, false)
+  QB_PCFG_EVEN(false, 16) QB_PCFG_EVEN(false, 20) QB_PCFG_EVEN(false, 24) QB_PCFG_EVEN(true, 16) QB_PCFG_EVEN(true, 20)
+  QB_PCFG_EVEN(true, 24) QB_PCFG3(false, 16, true, false) QB_PCFG3(true, 16, true, false)
+#undef QB_PCFG_EVEN
 #undef QB_PCFG3
 #undef QB_PCFG
   return cudaSuccess;
