@@ -10,6 +10,7 @@ nproc > $OUT/nproc.txt; free -g >> $OUT/nproc.txt
 echo "pytest rc=$?" >> $OUT/pytest_gpu.log
 timeout 300 python tools/microbench.py > $OUT/microbench.txt 2>&1
 timeout 600 python tools/decode_bench.py 2000000 16 > $OUT/decode_bench.jsonl 2>&1
+timeout 900 python tools/cli_bench.py 2000000 1,4,8 > $OUT/cli_bench.jsonl 2>&1
 QB_QUICK_KERNELS=0,4,2,3 timeout 600 python tools/quick_bench.py 4000000 > $OUT/quick_bench.jsonl 2>&1
 QB_QUICK_KERNELS=4,2 QB_QUICK_LENS=50,76,100,126,200,256 timeout 600 python tools/quick_bench.py 4000000 > $OUT/quick_bench_lens.jsonl 2>&1
 ( time timeout 900 python bench.py --steps 5 --warmup 3 ) > $OUT/bench.json 2> $OUT/bench.err
