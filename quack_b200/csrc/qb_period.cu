@@ -376,9 +376,9 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
             const uint32_t nx = lane < 31u ? r[s] : (s + 1 < kS ? r[s + 1] : 0u);  // codes of the next word
             const uint32_t an = __byte_perm(gc[s], nx, 0x7773);  // bits 13:0 = the 7-mer starting at this word
             const uint32_t fw = lds_u32((an & 0x3FE0u) | afilt_or);
-            uint32_t hit = __funnelshift_r(fw, 0u, an) & 1u;
-            if (s == kS - 1 && !act) hit = 0;
-            hm |= hit << s;
+            // bit (an & 31) of the filter word rotated to bit s of the hit mask
+            const uint32_t rot = __funnelshift_r(fw, fw, an - (uint32_t)s);
+            hm |= rot & ((s < kS - 1 || act) ? (1u << s) : 0u);
           }
         }
 #pragma unroll
@@ -415,11 +415,15 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
         }
         if (any) {
           // settle the first hits of the tile's reads: kmer_count[p + 1]++ (quack.c:215-216)
-          for (uint32_t n = lane; n < rpt; n += 32u) {
-            const uint32_t f = lds_u32(fhit_s + 4u * n);
-            if (f != kNoHit) {
-              red_shared_add<0u>(kmerhist_s + (f + 1u) * 4u, 1u);
-              asm volatile("st.shared.u32 [%0], %1;" ::"r"(fhit_s + 4u * n), "r"(kNoHit) : "memory");
+#pragma unroll
+          for (uint32_t h = 0; h < kPMaxRpt; h += 32u) {  // reads_per_tile <= kPMaxRpt: two predicated rounds, no loop
+            const uint32_t n = h + lane;
+            if (n < rpt) {
+              const uint32_t f = lds_u32(fhit_s + 4u * n);
+              if (f != kNoHit) {
+                red_shared_add<0u>(kmerhist_s + (f + 1u) * 4u, 1u);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(fhit_s + 4u * n), "r"(kNoHit) : "memory");
+              }
             }
           }
           __syncwarp();
