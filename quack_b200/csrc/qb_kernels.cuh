@@ -128,7 +128,7 @@ struct PeriodPlan {
   uint32_t wblock;           // bytes of one warp block (barriers, first hits, queue, stages x (seq + qual))
   uint32_t smem_base;        // shared address the dynamic shared memory must start at (checked by the kernel)
   uint32_t smem_bytes;
-  uint32_t afilt_s, exact_s, kmerhist_s, bloom_s;  // shared addresses of the CTA-wide arrays
+  uint32_t afilt_s, exact_s, kmerhist_s, bloom_s, slot_s;  // shared addresses of the CTA-wide arrays
   uint32_t region_s[3], region_n[3];      // warp blocks: region_n[i] blocks from region_s[i]
   uint32_t qbase;
   uint32_t grid;

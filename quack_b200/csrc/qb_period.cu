@@ -178,6 +178,9 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
         }
       }
   }
+  // the slot table into shared memory: indexing the kernel arguments with a per-thread position is a divergent
+  // constant load (one transaction per lane): 20 of them per thread cost ~10 us per launch
+  if (tid < kPeriodMaxLen / 4u) reinterpret_cast<uint32_t *>(gen(P.slot_s))[tid] = reinterpret_cast<const uint32_t *>(args.slot)[tid];
   if (lane == 0) {
     for (uint32_t s = 0; s < stages; s++) mbar_init(reinterpret_cast<uint64_t *>(gen(wb_s + kPoBar + 8u * s)), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
 #pragma unroll
   for (int s = 0; s < kS; s++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) col[s][j] = p_slot_addr(args.slot[(4u * (32u * s + lane) + j) % len]);
+    for (int j = 0; j < 4; j++) col[s][j] = p_slot_addr(lds_u8(P.slot_s + (4u * (32u * s + lane) + j) % len));
   // Even l: the j-th byte of a word always holds positions of the parity of j, the increments are the two
   // constants.  Odd l: the parity also depends on the read inside the period -> one increment per column.
   uint32_t inc[kOdd ? kS : 1][4];
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
 
   auto flush = [&]() {  // all warps are behind a barrier
     for (uint32_t pos = tid; pos < len; pos += kPThreads) {
-      const uint32_t base = p_slot_addr(args.slot[pos]);
+      const uint32_t base = p_slot_addr(lds_u8(P.slot_s + pos));
       const uint32_t sh = (pos & 1u) * 16u;
       unsigned long long *row = args.a.rows + (size_t)pos * kRow;
       uint32_t cc[4] = {0, 0, 0, 0};
@@ -489,6 +492,7 @@ static PeriodPlan period_plan_w(uint32_t l, uint32_t first_offset, int adapters,
     if (!(p.kmerhist_s = take(2, (l + 1u) * 4u))) return p;
     if (!(p.bloom_s = take(2, kPBloomBits / 8u))) return p;
   }
+  if (!(p.slot_s = take(0, kPeriodMaxLen))) return p;
   uint32_t want = 3, target = 1024u;
   if (const char *e = getenv("QB_PT_STAGES")) want = (uint32_t)atoi(e);  // tuning hooks
   if (const char *e = getenv("QB_PT_BYTES")) target = (uint32_t)atoi(e);
