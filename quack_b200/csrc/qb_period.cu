@@ -459,7 +459,7 @@ static PeriodPlan period_plan_w(uint32_t l, uint32_t first_offset, int adapters,
   PeriodPlan p;
   memset(&p, 0, sizeof p);
   if (l < 32u || l > kPeriodMaxLen || (first_offset & 15u)) return p;
-  if ((l & 1u) && warps != 16u) return p;  // odd lengths keep one increment per column in registers: 16 warps
+  if ((l & 1u) && warps > 20u) return p;  // odd lengths keep one increment per column in registers: 20 warps at most
   p.len = l;
   p.qbase = qbase;
   p.nblocks = l > 128u ? 2u : 1u;
@@ -722,11 +722,13 @@ static cudaError_t period_launch_steps(const PArgs &args, uint32_t grid, cudaStr
   }
   return cudaGetLastError();
 }
-// instantiated: even lengths x {16, 20, 24 warps} x {tiles on 16-byte boundaries or not}; odd lengths x 16 warps
+// instantiated: even lengths x {16, 20, 24 warps} x {tiles on 16-byte boundaries or not}; odd lengths x {16, 20 warps}
 template <bool kAd>
 static cudaError_t period_launch_warps(const PArgs &args, uint32_t grid, cudaStream_t stream) {
   if (args.plan.len & 1u)
-    return args.plan.warps == 16u ? period_launch_steps<kAd, 16, true, false>(args, grid, stream) : cudaErrorInvalidValue;
+    return args.plan.warps == 16u   ? period_launch_steps<kAd, 16, true, false>(args, grid, stream)
+           : args.plan.warps == 20u ? period_launch_steps<kAd, 20, true, false>(args, grid, stream)
+                                    : cudaErrorInvalidValue;
   const bool al = (args.plan.tile_bytes & 15u) == 0u;
   switch (args.plan.warps) {
     case 16: return al ? period_launch_steps<kAd, 16, false, true>(args, grid, stream) : period_launch_steps<kAd, 16, false, false>(args, grid, stream);
@@ -744,6 +746,7 @@ cudaError_t period_configure() {
 #define QB_PCFG_EVEN(A, W) QB_PCFG3(A, W, false, true) QB_PCFG3(A, W, false, false)
   QB_PCFG_EVEN(false, 16) QB_PCFG_EVEN(false, 20) QB_PCFG_EVEN(false, 24) QB_PCFG_EVEN(true, 16) QB_PCFG_EVEN(true, 20)
   QB_PCFG_EVEN(true, 24) QB_PCFG3(false, 16, true, false) QB_PCFG3(true, 16, true, false)
+  QB_PCFG3(false, 20, true, false) QB_PCFG3(true, 20, true, false)
 #undef QB_PCFG_EVEN
 #undef QB_PCFG3
 #undef QB_PCFG

@@ -77,7 +77,7 @@ def test_period_layout_is_a_valid_counter_map(l, ad):
     assert L.qb_period_layout(l, ad, info, slot) == 0
     k, wp, steps, ppt, rpt, stages, warps = list(info)
     assert k * l == 4 * wp and steps == -(-wp // 32) and 3 <= steps <= 5
-    assert rpt == ppt * k and rpt % 4 == 0 and stages >= 2 and warps in (16, 20, 24) and (l % 2 == 0 or warps == 16)
+    assert rpt == ppt * k and rpt % 4 == 0 and stages >= 2 and warps in (16, 20, 24) and (l % 2 == 0 or warps <= 20)
     seen = set()
     for p in range(l):
         blk, col = slot[p] >> 7, slot[p] & 127
