@@ -33,6 +33,12 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line, and NCCL writes its version banner there (NCCL_DEBUG=VERSION, which
+# the GPU boxes set; NCCL honours NCCL_DEBUG_FILE only above that level): WARN + log file = stderr
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
