@@ -680,16 +680,26 @@ static void period_slots(const PeriodPlan &p, uint8_t *slot) {
     for (uint32_t a = 0; a < sv.set_n[si]; a++) m = ++c[sv.set[si][a]] > m ? c[sv.set[si][a]] : m;
     lower += m;
   }
+  // subsets of steps to give up, smallest first (Gosper's hack walks the masks of one size); the search is
+  // bounded: at most kBudget colourings (a few milliseconds), then the best layout found so far stands
   const uint32_t all = (1u << sv.nsets) - 1u;
-  for (uint32_t nsac = 0; nsac <= 4u && best > lower + nsac; nsac++) {
-    for (uint32_t sac = 0; sac <= all && best > lower + nsac; sac++) {
-      if ((uint32_t)__builtin_popcount(sac) != nsac) continue;
-      for (int t = 0; t < 4; t++)
+  constexpr int kBudget = 400;
+  int calls = 0;
+  for (uint32_t nsac = 0; nsac <= 4u && nsac <= sv.nsets && best > lower + nsac && calls < kBudget; nsac++) {
+    uint32_t sac = nsac ? (1u << nsac) - 1u : 0u;
+    for (;;) {
+      for (int t = 0; t < 2 && calls < kBudget; t++) {
+        calls++;
         if (sv.colour(all & ~sac, bank)) {
           const uint32_t c = sv.cost(bank);
           if (c < best) best = c, memcpy(best_bank, bank, E);
           break;
         }
+      }
+      if (nsac == 0 || best <= lower + nsac || calls >= kBudget) break;
+      const uint32_t c = sac & (0u - sac), r = sac + c;  // next mask with the same number of bits
+      sac = (((r ^ sac) >> 2) / c) | r;
+      if (sac > all) break;
     }
   }
   // banks -> columns: the i-th even position of bank b takes column b (i = 0), b + 32 (1), then block 1
@@ -787,7 +797,7 @@ cudaError_t launch_period(const BatchView &b, const Accum &a, const AdapterSet &
 // such batches, -1 otherwise.  info[0..6] = reads per period, words per period, steps, periods per tile,
 // reads per tile, stages, warps; slot[p] = block << 7 | u32 column of position p.
 extern "C" int qb_period_layout(uint32_t read_len, int adapters, uint32_t info[7], uint8_t slot[256]) {
-  const qb::PeriodPlan p = qb::period_plan(read_len, 0, adapters, 148, 232448u - 1024u, 1024u, 33u);
+  const qb::PeriodPlan p = qb::period_plan(read_len, 0, adapters, 148, 232448u, 1024u, 33u);
   if (!p.ok) return -1;
   if (info) info[0] = p.k, info[1] = p.wp, info[2] = p.steps, info[3] = p.ppt, info[4] = p.reads_per_tile, info[5] = p.stages, info[6] = p.warps;
   if (slot) qb::period_slots(p, slot);

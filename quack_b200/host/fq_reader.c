@@ -177,7 +177,10 @@ static bgzf_pool *bgzf_pool_open(FILE *fp, int n_threads) {
   pthread_cond_init(&p->cv_ready, NULL);
   pthread_cond_init(&p->cv_free, NULL);
   p->th = (pthread_t *)calloc((size_t)n_threads, sizeof *p->th);
-  for (int i = 0; i < n_threads; i++) pthread_create(&p->th[i], NULL, bgzf_worker, p);
+  int started = 0;
+  for (int i = 0; i < n_threads; i++)
+    if (pthread_create(&p->th[started], NULL, bgzf_worker, p) == 0) started++;
+  p->n_threads = started; /* fewer threads than asked for still decode the file; none: the caller falls back */
   return p;
 }
 
@@ -224,12 +227,17 @@ fqr_reader *fqr_open_mt(const char *path, int threads) {
     FILE *fp = fopen(path, "rb");
     if (!fp) return NULL;
     if (is_bgzf(fp)) {
-      fqr_reader *r = (fqr_reader *)calloc(1, sizeof *r);
-      r->pool = bgzf_pool_open(fp, threads);
-      r->buf = (uint8_t *)malloc(BGZF_MAX_BLOCK);
-      return r;
+      bgzf_pool *pool = bgzf_pool_open(fp, threads);
+      if (pool->n_threads > 0) {
+        fqr_reader *r = (fqr_reader *)calloc(1, sizeof *r);
+        r->pool = pool;
+        r->buf = (uint8_t *)malloc(BGZF_MAX_BLOCK);
+        return r;
+      }
+      bgzf_pool_close(pool); /* no thread could be started: gzread path below (closes fp) */
+    } else {
+      fclose(fp);
     }
-    fclose(fp);
   }
   gzFile f = gzopen(path, "r");
   if (!f) return NULL;
