@@ -455,12 +455,56 @@ long fqr_next(fqr_reader *r, const uint8_t **seq, const uint8_t **qual, size_t *
   return l;
 }
 
+/* Fast path of fqr_fill for the canonical record -- '@' header line, ONE non-empty sequence line, a '+' line,
+ * ONE quality line of the same length, no '\r', all four newlines inside the current buffer: the bytes go
+ * straight from the inflate buffer into the batch, with exactly the result parse_record() would give (every
+ * other shape -- multi-line records, '\r', a record cut by the buffer end, FASTA, garbage -- returns 0 and
+ * takes parse_record()).  Returns 1 and sets s/q/l without consuming anything; the caller commits with
+ * r->begin = *next. */
+static inline int fast_record(const fqr_reader *r, const uint8_t **s, const uint8_t **q, size_t *l, size_t *next) {
+  if (r->last_char != 0 || r->pending || r->begin >= r->end) return 0;
+  const uint8_t *p = r->buf + r->begin, *end = r->buf + r->end;
+  if (*p != '@') return 0;
+  const uint8_t *n1 = (const uint8_t *)memchr(p, '\n', (size_t)(end - p));
+  if (!n1 || n1 + 1 >= end) return 0;
+  const uint8_t *sq = n1 + 1;
+  if (*sq == '\n' || *sq == '>' || *sq == '+' || *sq == '@') return 0;
+  const uint8_t *n2 = (const uint8_t *)memchr(sq, '\n', (size_t)(end - sq));
+  if (!n2 || n2 + 1 >= end || n2[-1] == '\r' || n2[1] != '+') return 0;
+  const uint8_t *n3 = (const uint8_t *)memchr(n2 + 1, '\n', (size_t)(end - (n2 + 1)));
+  if (!n3) return 0;
+  const size_t len = (size_t)(n2 - sq);
+  const uint8_t *ql = n3 + 1;
+  if ((size_t)(end - ql) < len + 1 || ql[len] != '\n' || ql[len - 1] == '\r') return 0;
+  if (memchr(ql, '\n', len)) return 0; /* a shorter first quality line: parse_record() joins lines */
+  *s = sq, *q = ql, *l = len, *next = (size_t)(ql + len + 1 - r->buf);
+  return 1;
+}
+
 int fqr_fill(fqr_reader *r, uint8_t *seq, uint8_t *qual, uint32_t *offset, uint32_t *length, uint64_t cap_bytes,
              uint32_t cap_reads, uint32_t *n_reads, uint64_t *n_bytes, uint32_t *max_len) {
   uint32_t n = 0, longest = 0;
   uint64_t bytes = 0;
   int more = 1;
   while (r->status == 0 && n < cap_reads) {
+    const uint8_t *fs, *fq;
+    size_t fl, fnext;
+    if (fast_record(r, &fs, &fq, &fl, &fnext)) {
+      if (fl > cap_bytes) { /* same outcome as below, through the general path */
+      } else if (bytes + fl > cap_bytes) {
+        break; /* does not fit: nothing was consumed, the next batch starts with it */
+      } else {
+        memcpy(seq + bytes, fs, fl);
+        memcpy(qual + bytes, fq, fl);
+        offset[n] = (uint32_t)bytes;
+        length[n] = (uint32_t)fl;
+        if (fl > longest) longest = (uint32_t)fl;
+        bytes += fl;
+        n++;
+        r->begin = fnext;
+        continue;
+      }
+    }
     if (!r->pending) {
       int fasta;
       const long l = parse_record(r, &fasta);
