@@ -50,17 +50,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
     deps.append(os.path.join(HERE, "..", "include", "quack_b200.h"))
     out = lib_path()
     if force or not _newer(out, deps):
+        hdrs = [d for d in deps if d.endswith((".h", ".cuh"))]
+        extra = os.environ.get("QB_NVCC_EXTRA", "").split()
+        tag = ("." + "".join(c if c.isalnum() else "_" for c in " ".join(extra))) if extra else ""
+        jobs = []
         objs = []
         for c in host_lib_srcs:  # plain C translation units, compiled as C
             o = os.path.join(LIBDIR, os.path.basename(c) + ".o")
-            subprocess.run(["gcc", "-O3", "-std=c11", "-D_DEFAULT_SOURCE", "-fPIC", "-Wall", "-c", c, "-o", o,
-                            "-I" + os.path.join(HERE, "..", "include")], check=True)
             objs.append(o)
-        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("QB_NVCC_EXTRA", "").split(), "-shared", "-o", out, *srcs, *objs,
-               "-ldl", "-lz", "-lpthread"]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        subprocess.run(cmd, check=True)
+            if force or not _newer(o, [c] + hdrs):
+                jobs.append(["gcc", "-O3", "-std=c11", "-D_DEFAULT_SOURCE", "-fPIC", "-Wall", "-c", c, "-o", o,
+                             "-I" + os.path.join(HERE, "..", "include")])
+        for c in srcs:  # one object per translation unit: only what changed is recompiled, all of them in parallel
+            o = os.path.join(LIBDIR, os.path.basename(c) + tag + ".o")
+            objs.append(o)
+            if force or not _newer(o, [c] + hdrs):
+                cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-c", c, "-o", o]
+                if verbose:
+                    cmd.insert(1, "-Xptxas=-v")
+                jobs.append(cmd)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+            for r in ex.map(lambda cmd: subprocess.run(cmd, check=True), jobs):
+                pass
+        subprocess.run([_nvcc(), *NVCC_FLAGS, "-shared", "-o", out, *objs, "-ldl", "-lz", "-lpthread"], check=True)
     main_c = os.path.join(HOST, "quack_main.c")
     if os.path.exists(main_c):
         os.makedirs(BINDIR, exist_ok=True)

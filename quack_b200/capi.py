@@ -250,9 +250,10 @@ class Context:
         self._chk(lib().qb_reset(self.h, mate))
 
     def finish(self, mate: int = 0) -> Result:
-        rows = np.zeros((self.len_cap, ROW), dtype=np.uint64)
         ml, n = C.c_uint64(), C.c_uint64()
-        self._chk(lib().qb_finish(self.h, mate, rows.ctypes.data, self.len_cap, C.byref(ml), C.byref(n)))
+        self._chk(lib().qb_finish(self.h, mate, None, 0, C.byref(ml), C.byref(n)))   # the reduce; longest read
+        rows = np.zeros((max(int(ml.value), 1), ROW), dtype=np.uint64)
+        self._chk(lib().qb_finish(self.h, mate, rows.ctypes.data, rows.shape[0], C.byref(ml), C.byref(n)))
         return Result(rows[: ml.value].copy(), int(ml.value), int(n.value))
 
     def invalid_quality_count(self, mate: int = 0) -> int:

@@ -10,7 +10,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -31,6 +34,7 @@ struct NcclApi {
   ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -52,11 +56,12 @@ NcclApi *nccl_api() {
     QB_SYM(CommInitAll, "ncclCommInitAll");
     QB_SYM(CommDestroy, "ncclCommDestroy");
     QB_SYM(Reduce, "ncclReduce");
+    QB_SYM(AllReduce, "ncclAllReduce");
     QB_SYM(GroupStart, "ncclGroupStart");
     QB_SYM(GroupEnd, "ncclGroupEnd");
     QB_SYM(GetErrorString, "ncclGetErrorString");
 #undef QB_SYM
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.CommDestroy && api.Reduce &&
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.CommDestroy && api.Reduce && api.AllReduce &&
              api.GroupStart && api.GroupEnd && api.GetErrorString;
   });
   return api.ok ? &api : nullptr;
@@ -70,7 +75,12 @@ struct Slot {
   uint2 *d_tiles = nullptr;  // tile descriptors of the warp-tile kernel (one per read at most)
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
-  bool pending = false;
+  // Ownership (guarded by qb_ctx::mu).  FREE: nobody uses the buffers.  HELD: a host thread got the slot from
+  // qb_acquire()/qb_submit_from() and may write its pinned buffers; no other thread is ever handed it.  PENDING:
+  // submitted; copies and the kernel are queued behind `done`, the next owner waits for that event first.
+  enum State { FREE = 0, HELD = 1, PENDING = 2 };
+  State state = FREE;
+  uint64_t seq = 0;  // submit order, so that the oldest pending slot is recycled first
 };
 
 struct Device {
@@ -78,8 +88,10 @@ struct Device {
   int sm_count = 0;
   int smem_optin = 0;
   int smem_reserved = 0;  // shared memory the driver keeps per block: dynamic shared memory starts behind it
-  std::vector<unsigned long long *> acc;  // per mate: [len_cap*97 rows][kNumCounters]
-  unsigned long long *reduce_buf = nullptr;
+  unsigned long long *acc_all = nullptr;  // one allocation: n_mates x ([cur_cap*97 rows][kNumCounters])
+  std::vector<unsigned long long *> acc;  // per mate: acc_all + mate * acc_u64
+  unsigned long long *reduce_buf = nullptr;  // same size as acc_all: NCCL receive buffer
+  unsigned long long *d_scalar = nullptr;    // one u64: the ranks agree on the accumulator size through it
   uint32_t *d_bitmap = nullptr, *d_anchor = nullptr, *d_exact = nullptr;
   std::vector<Slot> slots;
   cudaStream_t main_stream = nullptr;
@@ -95,11 +107,19 @@ struct qb_ctx {
   qb_config cfg;
   std::vector<Device> dev;
   std::mutex mu;
-  uint64_t next_slot = 0;
+  std::condition_variable cv_slot;  // a HELD slot was submitted (or released on an error path)
+  uint64_t next_slot = 0, submit_seq = 0;
+  std::mutex err_mu;
   std::string err;
-  uint64_t launches = 0, launches_fused = 0, launches_simple = 0, launches_period = 0;
-  uint64_t h2d_bytes = 0;  // bytes queued for host-to-device copy by qb_submit*() so far
-  size_t acc_u64 = 0;  // len_cap*97 + counters
+  std::atomic<uint64_t> launches{0}, launches_fused{0}, launches_simple{0}, launches_period{0};
+  std::atomic<uint64_t> h2d_bytes{0};  // bytes queued for host-to-device copy by qb_submit*() so far
+  // The accumulators hold cur_cap rows, not cfg.len_cap: they start small and grow (grow_accumulators) when a
+  // batch announces a longer read, so a context opened for 2^20-bp reads costs nothing until one shows up.
+  // Launches read the accumulator pointers under a shared lock, growth swaps them under the exclusive lock.
+  std::shared_mutex acc_mu;
+  uint32_t cur_cap = 0;
+  size_t acc_u64 = 0;  // cur_cap*97 + counters, per mate
+  std::atomic<bool> result_valid{false};  // h_result holds the reduced accumulators of every mate (qb_finish)
   qb::AdapterSet ad_host_template{};
   uint32_t n_anchors = 0;     // distinct 7-mer anchors of the adapter set
   double anchor_density = 0;  // n_anchors / 2^14: filter pass rate per probe on random bases
@@ -132,10 +152,12 @@ int fail(qb_ctx *ctx, int code, const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
-  if (ctx)
+  if (ctx) {
+    std::lock_guard<std::mutex> lk(ctx->err_mu);  // both mate threads may fail at once
     ctx->err = buf;
-  else
+  } else {
     g_create_error = buf;
+  }
   return code;
 }
 
@@ -168,8 +190,8 @@ qb::AdapterSet adapter_set(const qb_ctx *ctx, const Device &d) {
 qb::Accum accum(const qb_ctx *ctx, const Device &d, int mate) {
   qb::Accum a;
   a.rows = d.acc[mate];
-  a.counters = d.acc[mate] + (size_t)ctx->cfg.len_cap * qb::kRow;
-  a.len_cap = ctx->cfg.len_cap;
+  a.counters = d.acc[mate] + (size_t)ctx->cur_cap * qb::kRow;
+  a.len_cap = ctx->cur_cap;
   return a;
 }
 
@@ -193,7 +215,7 @@ int launch_other(qb_ctx *ctx, Device &d, const qb::BatchView &v, qb::Accum ac, c
     // The shared-memory histogram is sized by the longest read of THIS batch (the caller's max_len
     // promise; a longer read is counted as an error and fails qb_finish), not by len_cap: a context
     // opened for 65536-bp reads still runs short-read batches on the shared-memory kernels.
-    uint32_t eff_cap = ctx->cfg.len_cap;
+    uint32_t eff_cap = ctx->cur_cap;
     if (v.max_len && v.max_len < eff_cap) eff_cap = v.max_len < 11u ? 11u : v.max_len;
     // AUTO: the v3 kernel measured faster than v4 wherever both fit (profiles/r01c)
     if (kernel != QB_KERNEL_WTILE)
@@ -214,11 +236,8 @@ int launch_other(qb_ctx *ctx, Device &d, const qb::BatchView &v, qb::Accum ac, c
       kernel = QB_KERNEL_SIMPLE;
     }
   }
-  {
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    ctx->launches++;
-    (kernel == QB_KERNEL_SIMPLE ? ctx->launches_simple : ctx->launches_fused)++;
-  }
+  ctx->launches++;
+  (kernel == QB_KERNEL_SIMPLE ? ctx->launches_simple : ctx->launches_fused)++;
   cudaError_t e = kernel == QB_KERNEL_WTILE   ? qb::launch_wtile(v, ac, ad, wplan, stream)
                   : kernel == QB_KERNEL_FUSED ? qb::launch_fused(v, ac, ad, plan, stream)
                                               : qb::launch_simple(v, ac, ad, d.sm_count, stream);
@@ -237,9 +256,75 @@ qb::PeriodPlan period_plan_for(const qb_ctx *ctx, const Device &d, const qb::Bat
   return p;
 }
 
+// (Re)allocates the accumulators of every device for `cap` rows per mate, keeping what was counted so far.
+// Caller holds acc_mu exclusively (or is qb_create).
+int alloc_accumulators(qb_ctx *ctx, uint32_t cap) {
+  const size_t new_u64 = (size_t)cap * qb::kRow + qb::kNumCounters;
+  const int nm = ctx->cfg.n_mates;
+  for (Device &d : ctx->dev) {
+    QB_CUDA(ctx, cudaSetDevice(d.id));
+    if (d.acc_all) QB_CUDA(ctx, cudaDeviceSynchronize());  // kernels in flight still count into the old rows
+    unsigned long long *fresh = nullptr, *rbuf = nullptr;
+    QB_CUDA(ctx, cudaMalloc(&fresh, new_u64 * 8 * nm));
+    QB_CUDA(ctx, cudaMemset(fresh, 0, new_u64 * 8 * nm));
+    QB_CUDA(ctx, cudaMalloc(&rbuf, new_u64 * 8 * nm));
+    if (d.acc_all) {
+      for (int m = 0; m < nm; m++) {
+        QB_CUDA(ctx, cudaMemcpy(fresh + m * new_u64, d.acc[m], (size_t)ctx->cur_cap * qb::kRow * 8, cudaMemcpyDeviceToDevice));
+        QB_CUDA(ctx, cudaMemcpy(fresh + m * new_u64 + (size_t)cap * qb::kRow, d.acc[m] + (size_t)ctx->cur_cap * qb::kRow,
+                                qb::kNumCounters * 8, cudaMemcpyDeviceToDevice));
+      }
+      cudaFree(d.acc_all);
+      cudaFree(d.reduce_buf);
+    }
+    d.acc_all = fresh;
+    d.reduce_buf = rbuf;
+    d.acc.resize(nm);
+    for (int m = 0; m < nm; m++) d.acc[m] = fresh + m * new_u64;
+    if (!d.d_scalar) QB_CUDA(ctx, cudaMalloc(&d.d_scalar, 8));
+  }
+  if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  ctx->h_result = nullptr;
+  QB_CUDA(ctx, cudaHostAlloc(&ctx->h_result, new_u64 * 8 * nm, cudaHostAllocDefault));
+  ctx->cur_cap = cap;
+  ctx->acc_u64 = new_u64;
+  ctx->result_valid = false;
+  return QB_OK;
+}
+
+uint32_t grown_cap(const qb_ctx *ctx, uint32_t need) {
+  uint32_t cap = ctx->cur_cap ? ctx->cur_cap : 512u;
+  while (cap < need) cap *= 2u;
+  return cap > ctx->cfg.len_cap ? ctx->cfg.len_cap : cap;
+}
+
+// makes room for reads of up to `need` bp (<= cfg.len_cap); cheap when the rows exist already
+int ensure_cap(qb_ctx *ctx, uint32_t need) {
+  {
+    std::shared_lock<std::shared_mutex> lk(ctx->acc_mu);
+    if (need <= ctx->cur_cap) return QB_OK;
+  }
+  std::unique_lock<std::shared_mutex> lk(ctx->acc_mu);
+  if (need <= ctx->cur_cap) return QB_OK;
+  return alloc_accumulators(ctx, grown_cap(ctx, need));
+}
+
+int launch_batch_locked(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaStream_t stream);
+
 // chooses and launches the statistics kernel(s) for one device-resident batch
 int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaStream_t stream) {
   if (v.n_reads == 0) return QB_OK;
+  // rows for the longest read this batch may hold (max_len = 0: unknown, whatever len_cap allows)
+  const uint32_t need = v.max_len && v.max_len < ctx->cfg.len_cap ? v.max_len : ctx->cfg.len_cap;
+  const int rc = ensure_cap(ctx, need);
+  if (rc) return rc;
+  ctx->result_valid = false;
+  std::shared_lock<std::shared_mutex> lk(ctx->acc_mu);
+  QB_CUDA(ctx, cudaSetDevice(d.id));  // growth may have switched this thread's device
+  return launch_batch_locked(ctx, d, v, mate, stream);
+}
+
+int launch_batch_locked(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaStream_t stream) {
   const qb::AdapterSet ad = adapter_set(ctx, d);
   qb::Accum ac = accum(ctx, d, mate);
   int kernel = ctx->cfg.kernel;
@@ -271,7 +356,6 @@ int launch_batch(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate, cudaS
     const cudaError_t e = qb::launch_period(v, ac, ad, pplan, stream, &n_main);
     if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     if (n_main) {
-      std::lock_guard<std::mutex> lk(ctx->mu);
       ctx->launches++;
       ctx->launches_fused++;
       ctx->launches_period++;
@@ -304,7 +388,16 @@ int qb_device_count(void) {
   return n;
 }
 
-const char *qb_last_error(const qb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+const char *qb_last_error(const qb_ctx *ctx) {
+  if (!ctx) return g_create_error.c_str();
+  // a copy per calling thread: another thread may replace ctx->err while the caller still reads the text
+  thread_local std::string copy;
+  {
+    std::lock_guard<std::mutex> lk(const_cast<qb_ctx *>(ctx)->err_mu);
+    copy = ctx->err;
+  }
+  return copy.c_str();
+}
 
 void *qb_host_alloc(size_t bytes) {
   void *p = nullptr;
@@ -337,7 +430,6 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
   ctx->cfg = cfg;
   ctx->cfg.device_ids = nullptr;
   ctx->cfg.adapter_keys = nullptr;
-  ctx->acc_u64 = (size_t)cfg.len_cap * qb::kRow + qb::kNumCounters;
   if (const char *qb_env = getenv("QB_QBASE")) {
     const int v = atoi(qb_env);
     if (v >= 33 && v <= 64) ctx->qbase = (uint32_t)v;
@@ -388,12 +480,6 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
       }
     }
     QB_CREATE_CUDA(cudaStreamCreateWithFlags(&d.main_stream, cudaStreamNonBlocking));
-    d.acc.resize(cfg.n_mates);
-    for (int m = 0; m < cfg.n_mates; m++) {
-      QB_CREATE_CUDA(cudaMalloc(&d.acc[m], ctx->acc_u64 * 8));
-      QB_CREATE_CUDA(cudaMemset(d.acc[m], 0, ctx->acc_u64 * 8));
-    }
-    QB_CREATE_CUDA(cudaMalloc(&d.reduce_buf, ctx->acc_u64 * 8));
     if (cfg.adapters_enabled) {
       QB_CREATE_CUDA(cudaMalloc(&d.d_bitmap, bitmap.size() * 4));
       QB_CREATE_CUDA(cudaMemcpy(d.d_bitmap, bitmap.data(), bitmap.size() * 4, cudaMemcpyHostToDevice));
@@ -424,7 +510,11 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
     }
     QB_CREATE_CUDA(cudaDeviceSynchronize());
   }
-  QB_CREATE_CUDA(cudaHostAlloc(&ctx->h_result, ctx->acc_u64 * 8, cudaHostAllocDefault));
+  if (alloc_accumulators(ctx, grown_cap(ctx, cfg.len_cap < 512u ? cfg.len_cap : 512u)) != QB_OK) {
+    g_create_error = ctx->err;
+    qb_destroy(ctx);
+    return QB_ERR_CUDA;
+  }
   if (cfg.n_devices > 1) {
     std::vector<ncclComm_t> comms(cfg.n_devices);
     std::vector<int> ids(cfg.n_devices);
@@ -463,8 +553,9 @@ void qb_destroy(qb_ctx *ctx) {
       if (s.stream) cudaStreamDestroy(s.stream);
       if (s.done) cudaEventDestroy(s.done);
     }
-    for (auto p : d.acc) cudaFree(p);
+    cudaFree(d.acc_all);
     cudaFree(d.reduce_buf);
+    cudaFree(d.d_scalar);
     cudaFree(d.d_bitmap);
     cudaFree(d.d_anchor);
     cudaFree(d.d_exact);
@@ -481,26 +572,63 @@ void qb_destroy(qb_ctx *ctx) {
   delete ctx;
 }
 
-// picks the next slot round-robin over devices x ring and waits until its previous use finished
+// Hands the calling thread a slot nobody else holds: the next FREE slot in round-robin order over devices x ring,
+// else the PENDING slot that was submitted first (its event is waited for outside the lock), else -- every slot is
+// HELD by other threads -- it sleeps until one of them submits.  The slot stays HELD (exclusively the caller's)
+// until submit_on() queues its work or release_slot() gives it back.
 static int take_slot(qb_ctx *ctx, int *dev_index, int *slot_index) {
   const uint64_t total = (uint64_t)ctx->dev.size() * ctx->cfg.ring_depth;
-  uint64_t k;
+  int di = -1, si = -1;
+  bool wait_event = false;
   {
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    k = ctx->next_slot++ % total;
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    for (;;) {
+      int best = -1;
+      uint64_t best_seq = 0;
+      for (uint64_t i = 0; i < total && di < 0; i++) {
+        const uint64_t k = (ctx->next_slot + i) % total;
+        Slot &s = ctx->dev[k % ctx->dev.size()].slots[k / ctx->dev.size()];
+        if (s.state == Slot::FREE) {
+          di = (int)(k % ctx->dev.size()), si = (int)(k / ctx->dev.size());
+          ctx->next_slot = k + 1;
+        } else if (s.state == Slot::PENDING && (best < 0 || s.seq < best_seq)) {
+          best = (int)k, best_seq = s.seq;
+        }
+      }
+      if (di < 0 && best >= 0) {
+        di = (int)((uint64_t)best % ctx->dev.size()), si = (int)((uint64_t)best / ctx->dev.size());
+        ctx->next_slot = (uint64_t)best + 1;
+        wait_event = true;
+      }
+      if (di >= 0) break;
+      ctx->cv_slot.wait(lk);
+    }
+    ctx->dev[di].slots[si].state = Slot::HELD;
   }
-  const int di = (int)(k % ctx->dev.size());
-  const int si = (int)(k / ctx->dev.size());
   Device &d = ctx->dev[di];
   Slot &s = d.slots[si];
-  QB_CUDA(ctx, cudaSetDevice(d.id));
-  if (s.pending) {
-    QB_CUDA(ctx, cudaEventSynchronize(s.done));
-    s.pending = false;
+  cudaError_t e = cudaSetDevice(d.id);
+  if (e == cudaSuccess && wait_event) e = cudaEventSynchronize(s.done);
+  if (e != cudaSuccess) {
+    {
+      std::lock_guard<std::mutex> lk(ctx->mu);
+      s.state = Slot::FREE;
+    }
+    ctx->cv_slot.notify_all();
+    return fail(ctx, QB_ERR_CUDA, "waiting for a ring slot failed: %s", cudaGetErrorString(e));
   }
   *dev_index = di;
   *slot_index = si;
   return QB_OK;
+}
+
+// error paths: a HELD slot goes back to the ring so that other threads do not wait for it forever
+static void release_slot(qb_ctx *ctx, int di, int si) {
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->dev[di].slots[si].state = Slot::FREE;
+  }
+  ctx->cv_slot.notify_all();
 }
 
 int qb_acquire(qb_ctx *ctx, qb_batch *out) {
@@ -520,9 +648,28 @@ int qb_acquire(qb_ctx *ctx, qb_batch *out) {
   return QB_OK;
 }
 
+static int submit_queue(qb_ctx *ctx, int di, int si, int mate, const uint8_t *seq, const uint8_t *qual,
+                        const uint32_t *offset, const uint32_t *length, uint32_t n_reads, uint64_t n_bytes,
+                        uint32_t max_len);
+
+// queues the work of a HELD slot and turns it PENDING (FREE again if queuing failed)
 static int submit_on(qb_ctx *ctx, int di, int si, int mate, const uint8_t *seq, const uint8_t *qual,
                      const uint32_t *offset, const uint32_t *length, uint32_t n_reads, uint64_t n_bytes,
                      uint32_t max_len) {
+  const int rc = submit_queue(ctx, di, si, mate, seq, qual, offset, length, n_reads, n_bytes, max_len);
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Slot &s = ctx->dev[di].slots[si];
+    s.state = rc == QB_OK ? Slot::PENDING : Slot::FREE;
+    s.seq = ++ctx->submit_seq;
+  }
+  ctx->cv_slot.notify_all();
+  return rc;
+}
+
+static int submit_queue(qb_ctx *ctx, int di, int si, int mate, const uint8_t *seq, const uint8_t *qual,
+                        const uint32_t *offset, const uint32_t *length, uint32_t n_reads, uint64_t n_bytes,
+                        uint32_t max_len) {
   if (n_reads > ctx->cfg.batch_reads || n_bytes > ctx->cfg.batch_bytes)
     return fail(ctx, QB_ERR_CAPACITY, "batch of %u reads / %llu bytes exceeds the slot (%u / %llu)", n_reads,
                 (unsigned long long)n_bytes, ctx->cfg.batch_reads, (unsigned long long)ctx->cfg.batch_bytes);
@@ -546,15 +693,11 @@ static int submit_on(qb_ctx *ctx, int di, int si, int mate, const uint8_t *seq, 
       QB_CUDA(ctx, cudaMemcpyAsync(s.d_off + r0, offset + r0, (size_t)(n_reads - r0) * 4, cudaMemcpyHostToDevice, s.stream));
       QB_CUDA(ctx, cudaMemcpyAsync(s.d_len + r0, length + r0, (size_t)(n_reads - r0) * 4, cudaMemcpyHostToDevice, s.stream));
     }
-    {
-      std::lock_guard<std::mutex> lk(ctx->mu);
-      ctx->h2d_bytes += 2 * n_bytes + 8ull * (n_reads - r0);
-    }
+    ctx->h2d_bytes += 2 * n_bytes + 8ull * (n_reads - r0);
     int rc = launch_batch(ctx, d, v, mate, s.stream);
     if (rc) return rc;
   }
   QB_CUDA(ctx, cudaEventRecord(s.done, s.stream));
-  s.pending = true;
   return QB_OK;
 }
 
@@ -564,6 +707,13 @@ int qb_submit(qb_ctx *ctx, const qb_batch *b, int mate, uint32_t n_reads, uint64
   if (!b || b->device_index < 0 || b->device_index >= (int)ctx->dev.size() || b->slot < 0 ||
       b->slot >= ctx->cfg.ring_depth)
     return fail(ctx, QB_ERR_ARG, "bad batch handle");
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const Slot &s = ctx->dev[b->device_index].slots[b->slot];
+    if (s.state != Slot::HELD || b->seq != s.h_seq)
+      return fail(ctx, QB_ERR_ARG, "qb_submit: slot %d of device %d is not held by a qb_acquire() (submitted twice?)",
+                  b->slot, b->device_index);
+  }
   return submit_on(ctx, b->device_index, b->slot, mate, b->seq, b->qual, b->offset, b->length, n_reads, n_bytes,
                    max_len);
 }
@@ -592,11 +742,16 @@ int qb_accumulate_host(qb_ctx *ctx, int mate, const uint8_t *seq, const uint8_t 
     uint32_t max_len = 0;
     while (r1 < n_reads && r1 - r0 < b.cap_reads) {
       const uint64_t o = offset[r1], l = length[r1];
-      if (o < end) return fail(ctx, QB_ERR_LAYOUT, "offsets must be ascending and reads must not overlap (read %llu)",
-                               (unsigned long long)r1);
-      if (l > ctx->cfg.len_cap)
+      if (o < end) {
+        release_slot(ctx, b.device_index, b.slot);
+        return fail(ctx, QB_ERR_LAYOUT, "offsets must be ascending and reads must not overlap (read %llu)",
+                    (unsigned long long)r1);
+      }
+      if (l > ctx->cfg.len_cap) {
+        release_slot(ctx, b.device_index, b.slot);
         return fail(ctx, QB_ERR_CAPACITY, "read %llu has length %llu > len_cap %u", (unsigned long long)r1,
                     (unsigned long long)l, ctx->cfg.len_cap);
+      }
       if (o + l - base > b.cap_bytes) break;
       b.offset[r1 - r0] = (uint32_t)(o - base);
       b.length[r1 - r0] = (uint32_t)l;
@@ -604,7 +759,10 @@ int qb_accumulate_host(qb_ctx *ctx, int mate, const uint8_t *seq, const uint8_t 
       end = o + l;
       r1++;
     }
-    if (r1 == r0) return fail(ctx, QB_ERR_CAPACITY, "read %llu does not fit an empty slot", (unsigned long long)r0);
+    if (r1 == r0) {
+      release_slot(ctx, b.device_index, b.slot);
+      return fail(ctx, QB_ERR_CAPACITY, "read %llu does not fit an empty slot", (unsigned long long)r0);
+    }
     memcpy(b.seq, seq + base, end - base);
     memcpy(b.qual, qual + base, end - base);
     rc = qb_submit(ctx, &b, mate, (uint32_t)(r1 - r0), end - base, max_len);
@@ -616,14 +774,23 @@ int qb_accumulate_host(qb_ctx *ctx, int mate, const uint8_t *seq, const uint8_t 
 
 int qb_sync(qb_ctx *ctx) {
   if (!ctx) return QB_ERR_ARG;
+  uint64_t seen;  // submissions up to this one are covered by the stream synchronisation below
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    seen = ctx->submit_seq;
+  }
   for (Device &d : ctx->dev) {
     QB_CUDA(ctx, cudaSetDevice(d.id));
-    for (Slot &s : d.slots) {
-      QB_CUDA(ctx, cudaStreamSynchronize(s.stream));
-      s.pending = false;
-    }
+    for (Slot &s : d.slots) QB_CUDA(ctx, cudaStreamSynchronize(s.stream));
     QB_CUDA(ctx, cudaStreamSynchronize(d.main_stream));
   }
+  {  // everything submitted so far is done; slots held by other threads stay theirs
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (Device &d : ctx->dev)
+      for (Slot &s : d.slots)
+        if (s.state == Slot::PENDING && s.seq <= seen) s.state = Slot::FREE;
+  }
+  ctx->cv_slot.notify_all();
   return QB_OK;
 }
 
@@ -632,10 +799,12 @@ int qb_reset(qb_ctx *ctx, int mate) {
   if (rc) return rc;
   rc = qb_sync(ctx);
   if (rc) return rc;
+  std::unique_lock<std::shared_mutex> lk(ctx->acc_mu);
   for (Device &d : ctx->dev) {
     QB_CUDA(ctx, cudaSetDevice(d.id));
     QB_CUDA(ctx, cudaMemset(d.acc[mate], 0, ctx->acc_u64 * 8));
   }
+  ctx->result_valid = false;
   return QB_OK;
 }
 
@@ -662,20 +831,32 @@ int qb_comm_init_rank(qb_ctx *ctx, int n_ranks, int rank, const uint8_t id_in[QB
   return QB_OK;
 }
 
-int qb_finish(qb_ctx *ctx, int mate, uint64_t *rows_out, uint64_t rows_cap, uint64_t *max_length,
-              uint64_t *n_reads) {
-  int rc = check_mate(ctx, mate);
+// Synchronises and brings the summed accumulators of EVERY mate to h_result: one grouped reduce over the devices of
+// this process and / or one reduce over the ranks, one device-to-host copy.  The result is kept until new work is
+// submitted, so the qb_finish() of the second mate costs a memcpy.
+static int reduce_all(qb_ctx *ctx) {
+  int rc = qb_sync(ctx);
   if (rc) return rc;
-  rc = qb_sync(ctx);
-  if (rc) return rc;
+  NcclApi *nc = nccl_api();
   Device &root = ctx->dev[0];
-  const unsigned long long *src = root.acc[mate];
+  if (ctx->rank_comm && ctx->n_ranks > 1) {
+    // the ranks may have grown their accumulators differently: agree on the largest row count first
+    QB_CUDA(ctx, cudaSetDevice(root.id));
+    unsigned long long cap = ctx->cur_cap;
+    QB_CUDA(ctx, cudaMemcpyAsync(root.d_scalar, &cap, 8, cudaMemcpyHostToDevice, root.main_stream));
+    QB_NCCL(ctx, nc->AllReduce(root.d_scalar, root.d_scalar, 1, ncclUint64, ncclMax, ctx->rank_comm, root.main_stream));
+    QB_CUDA(ctx, cudaMemcpyAsync(&cap, root.d_scalar, 8, cudaMemcpyDeviceToHost, root.main_stream));
+    QB_CUDA(ctx, cudaStreamSynchronize(root.main_stream));
+    if ((rc = ensure_cap(ctx, (uint32_t)cap))) return rc;
+  }
+  std::unique_lock<std::shared_mutex> lk(ctx->acc_mu);
+  const size_t n = ctx->acc_u64 * (size_t)ctx->cfg.n_mates;
+  const unsigned long long *src = root.acc_all;
   if (ctx->dev.size() > 1) {
-    // one grouped ncclReduce of [rows | counters] from every device of this process to device 0
-    NcclApi *nc = nccl_api();
+    // one grouped ncclReduce of every mate's [rows | counters] from every device of this process to device 0
     QB_NCCL(ctx, nc->GroupStart());
     for (Device &d : ctx->dev)
-      QB_NCCL(ctx, nc->Reduce(d.acc[mate], d.reduce_buf, ctx->acc_u64, ncclUint64, ncclSum, 0, d.comm, d.main_stream));
+      QB_NCCL(ctx, nc->Reduce(d.acc_all, d.reduce_buf, n, ncclUint64, ncclSum, 0, d.comm, d.main_stream));
     QB_NCCL(ctx, nc->GroupEnd());
     for (Device &d : ctx->dev) {
       QB_CUDA(ctx, cudaSetDevice(d.id));
@@ -686,20 +867,27 @@ int qb_finish(qb_ctx *ctx, int mate, uint64_t *rows_out, uint64_t rows_cap, uint
   QB_CUDA(ctx, cudaSetDevice(root.id));
   if (ctx->rank_comm && ctx->n_ranks > 1) {
     // one ncclReduce across the ranks (one process per GPU) to rank 0, over NVLink/NVSwitch
-    QB_NCCL(ctx, nccl_api()->Reduce(src, root.reduce_buf, ctx->acc_u64, ncclUint64, ncclSum, 0, ctx->rank_comm,
-                                    root.main_stream));
-    QB_CUDA(ctx, cudaStreamSynchronize(root.main_stream));
+    QB_NCCL(ctx, nc->Reduce(src, root.reduce_buf, n, ncclUint64, ncclSum, 0, ctx->rank_comm, root.main_stream));
     if (ctx->rank == 0) src = root.reduce_buf;
   }
-  QB_CUDA(ctx, cudaMemcpyAsync(ctx->h_result, src, ctx->acc_u64 * 8, cudaMemcpyDeviceToHost, root.main_stream));
+  QB_CUDA(ctx, cudaMemcpyAsync(ctx->h_result, src, n * 8, cudaMemcpyDeviceToHost, root.main_stream));
   QB_CUDA(ctx, cudaStreamSynchronize(root.main_stream));
+  ctx->result_valid = true;
+  return QB_OK;
+}
 
-  const uint32_t cap = ctx->cfg.len_cap;
-  unsigned long long *rows = ctx->h_result;
+int qb_finish(qb_ctx *ctx, int mate, uint64_t *rows_out, uint64_t rows_cap, uint64_t *max_length,
+              uint64_t *n_reads) {
+  int rc = check_mate(ctx, mate);
+  if (rc) return rc;
+  if (!ctx->result_valid && (rc = reduce_all(ctx))) return rc;
+
+  const uint32_t cap = ctx->cur_cap;
+  unsigned long long *rows = ctx->h_result + (size_t)mate * ctx->acc_u64;
   const unsigned long long *cnt = rows + (size_t)cap * qb::kRow;
   if (cnt[qb::kCntError])
-    return fail(ctx, QB_ERR_CAPACITY, "%llu tile(s)/read(s) exceeded len_cap, the max_len given at submit, or the batch layout rules; result invalid",
-                cnt[qb::kCntError]);
+    return fail(ctx, QB_ERR_CAPACITY, "%llu tile(s)/read(s) exceeded len_cap (%u), the max_len given at submit, or the batch layout rules; result invalid",
+                cnt[qb::kCntError], ctx->cfg.len_cap);
   uint64_t ml = 0;
   for (uint32_t i = 0; i < cap; i++)
     if (rows[(size_t)i * qb::kRow + qb::kColLength]) ml = i + 1;  // quack.c:194-198, derived
@@ -728,7 +916,7 @@ int qb_invalid_quality_count(qb_ctx *ctx, int mate, uint64_t *out) {
   for (Device &d : ctx->dev) {
     unsigned long long v = 0;
     QB_CUDA(ctx, cudaSetDevice(d.id));
-    QB_CUDA(ctx, cudaMemcpy(&v, d.acc[mate] + (size_t)ctx->cfg.len_cap * qb::kRow + qb::kCntInvalidQual, 8,
+    QB_CUDA(ctx, cudaMemcpy(&v, d.acc[mate] + (size_t)ctx->cur_cap * qb::kRow + qb::kCntInvalidQual, 8,
                             cudaMemcpyDeviceToHost));
     total += v;
   }
@@ -736,7 +924,7 @@ int qb_invalid_quality_count(qb_ctx *ctx, int mate, uint64_t *out) {
   return QB_OK;
 }
 
-uint64_t qb_launch_count(const qb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t qb_launch_count(const qb_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int qb_kernel_counts(const qb_ctx *ctx, uint64_t *n_simple, uint64_t *n_fused) {
   if (!ctx) return QB_ERR_ARG;
@@ -745,8 +933,8 @@ int qb_kernel_counts(const qb_ctx *ctx, uint64_t *n_simple, uint64_t *n_fused) {
   return QB_OK;
 }
 
-uint64_t qb_period_launch_count(const qb_ctx *ctx) { return ctx ? ctx->launches_period : 0; }
-uint64_t qb_h2d_bytes(const qb_ctx *ctx) { return ctx ? ctx->h2d_bytes : 0; }
+uint64_t qb_period_launch_count(const qb_ctx *ctx) { return ctx ? ctx->launches_period.load() : 0; }
+uint64_t qb_h2d_bytes(const qb_ctx *ctx) { return ctx ? ctx->h2d_bytes.load() : 0; }
 
 int qb_profile_enable(qb_ctx *ctx, int max_launches) {
   if (!ctx || max_launches < 0) return QB_ERR_ARG;

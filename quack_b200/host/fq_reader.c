@@ -19,7 +19,9 @@
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <fcntl.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -40,7 +42,7 @@ typedef struct {
   uint8_t *ubuf; /* inflated bytes */
   uint32_t csize, usize;
   int state; /* 0 free, 1 being inflated, 2 ready for the consumer */
-  int err;   /* 0, -1 end of file in front of this block, -3 broken block */
+  int err;   /* 0, -1 end of file in front of this block, -3 broken block, -6 a gzip member that is not BGZF */
 } bgzf_slot;
 
 typedef struct {
@@ -55,11 +57,13 @@ typedef struct {
   int input_done;        /* a reader saw the end of the file or a broken block: no more tickets */
   int stop;
   double inflate_cpu_s;  /* summed over the workers */
+  long long switch_off;  /* err -6: file offset of the member the serial zlib path continues from */
 } bgzf_pool;
 
 struct fqr_reader {
   gzFile f;
   bgzf_pool *pool; /* != NULL: BGZF input decoded by the pool, f unused */
+  char *path;      /* to reopen the file when a BGZF file continues with ordinary gzip members */
   uint8_t *buf;
   size_t begin, end;
   int is_eof, err;
@@ -77,24 +81,29 @@ static double now_s(void) {
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-/* Reads the next BGZF block of fp into s (payload + trailer).  0 ok, -1 clean end of file, -3 not a BGZF
- * block / truncated.  Layout (RFC 1952 + SAM spec 4.1; reference klib/bgzf.c:63-71, 330-355): 10-byte gzip
- * header with FLG = FEXTRA, XLEN, extra subfields of which one is 'B' 'C' 2 BSIZE (block size - 1), deflate
- * data, CRC32, ISIZE. */
-static int bgzf_read_block(FILE *fp, bgzf_slot *s) {
+/* Reads the next BGZF block of fp into s (payload + trailer).  0 ok; -1 end of the stream: clean end of file, or
+ * bytes that do not start a gzip member (gzread ignores such trailing garbage the same way); -3 truncated block;
+ * -6 a gzip member that is not a BGZF block (*member_off = where it starts: the caller hands the rest of the file
+ * to zlib, which is what gzread would have done all along).  Layout (RFC 1952 + SAM spec 4.1; reference
+ * klib/bgzf.c:63-71, 330-355): 10-byte gzip header with FLG = FEXTRA, XLEN, extra subfields of which one is
+ * 'B' 'C' 2 BSIZE (block size - 1), deflate data, CRC32, ISIZE. */
+static int bgzf_read_block(FILE *fp, bgzf_slot *s, long long *member_off) {
   uint8_t h[12];
+  *member_off = (long long)ftello(fp);
   const size_t got = fread(h, 1, 12, fp);
-  if (got == 0) return -1;
-  if (got != 12 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || h[3] != 4) return -3;
+  if (got < 2 || h[0] != 0x1f || h[1] != 0x8b) return -1;
+  if (got != 12 || h[2] != 8 || h[3] != 4) return -6;
   const uint32_t xlen = (uint32_t)h[10] | (uint32_t)h[11] << 8;
   uint8_t extra[512];
-  if (xlen < 6 || xlen > sizeof extra || fread(extra, 1, xlen, fp) != xlen) return -3;
+  if (xlen < 6 || xlen > sizeof extra) return -6;
+  if (fread(extra, 1, xlen, fp) != xlen) return -3;
   uint32_t bsize = 0;
   for (uint32_t i = 0; i + 4 <= xlen;) {
     const uint32_t slen = (uint32_t)extra[i + 2] | (uint32_t)extra[i + 3] << 8;
     if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= xlen) bsize = ((uint32_t)extra[i + 4] | (uint32_t)extra[i + 5] << 8) + 1u;
     i += 4 + slen;
   }
+  if (bsize == 0) return -6;
   if (bsize < 12 + xlen + 8 || bsize > BGZF_MAX_BLOCK) return -3;
   s->csize = bsize - 12 - xlen;
   if (fread(s->cbuf, 1, s->csize, fp) != s->csize) return -3;
@@ -116,9 +125,11 @@ static void *bgzf_worker(void *arg) {
       break;
     }
     bgzf_slot *s = &p->slot[p->next_ticket++ % (uint64_t)p->n_slots];
-    const int rc = bgzf_read_block(p->fp, s); /* sequential file order: under the lock */
+    long long member_off = 0;
+    const int rc = bgzf_read_block(p->fp, s, &member_off); /* sequential file order: under the lock */
     s->err = rc;
     s->usize = 0;
+    if (rc == -6) p->switch_off = member_off;
     if (rc) {
       p->input_done = 1;
       s->state = 2;
@@ -207,7 +218,7 @@ static void bgzf_pool_close(bgzf_pool *p) {
 static int is_bgzf(FILE *fp) {
   uint8_t h[18];
   const size_t got = fread(h, 1, sizeof h, fp);
-  rewind(fp);
+  if (fseeko(fp, 0, SEEK_SET) != 0) return 0;
   return got == sizeof h && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && h[3] == 4 && h[10] == 6 && h[11] == 0 &&
          h[12] == 'B' && h[13] == 'C' && h[14] == 2 && h[15] == 0;
 }
@@ -223,7 +234,10 @@ int fqr_default_threads(void) {
 
 fqr_reader *fqr_open_mt(const char *path, int threads) {
   if (threads < 1) threads = fqr_default_threads();
-  if (threads > 1) {
+  /* The BGZF probe reads the head of the file and seeks back: only on regular files.  A pipe, a FIFO, /dev/stdin or
+   * a process substitution is opened exactly once, by gzopen(), like the reference does (quack.c:187). */
+  struct stat st;
+  if (threads > 1 && stat(path, &st) == 0 && S_ISREG(st.st_mode)) {
     FILE *fp = fopen(path, "rb");
     if (!fp) return NULL;
     if (is_bgzf(fp)) {
@@ -232,6 +246,7 @@ fqr_reader *fqr_open_mt(const char *path, int threads) {
         fqr_reader *r = (fqr_reader *)calloc(1, sizeof *r);
         r->pool = pool;
         r->buf = (uint8_t *)malloc(BGZF_MAX_BLOCK);
+        r->path = strdup(path);
         return r;
       }
       bgzf_pool_close(pool); /* no thread could be started: gzread path below (closes fp) */
@@ -256,8 +271,9 @@ void fqr_close(fqr_reader *r) {
   if (!r) return;
   if (r->pool)
     bgzf_pool_close(r->pool);
-  else
+  else if (r->f)
     gzclose(r->f);
+  free(r->path);
   free(r->buf);
   free(r->seq.s);
   free(r->qual.s);
@@ -293,6 +309,25 @@ static int refill(fqr_reader *r) {
       pthread_mutex_unlock(&p->mu);
       r->begin = 0;
       r->end = n;
+      if (err == -6) {
+        /* the file goes on with an ordinary gzip member: the blocks in front of it were delivered, zlib takes
+         * the rest from that member on -- the bytes gzread() would have produced for the whole file */
+        const long long off = p->switch_off;
+        bgzf_pool_close(p);
+        r->pool = NULL;
+        const int fd = open(r->path, O_RDONLY);
+        if (fd < 0 || lseek(fd, (off_t)off, SEEK_SET) < 0 || !(r->f = gzdopen(fd, "r"))) {
+          if (fd >= 0) close(fd);
+          r->is_eof = r->err = 1;
+          return -3;
+        }
+        gzbuffer(r->f, 1u << 18);
+        free(r->buf); /* a 64 KiB block buffer so far (fully consumed): the gzread path fills FQR_BUF at a time */
+        r->buf = (uint8_t *)malloc(FQR_BUF);
+        r->begin = r->end = 0;
+        r->inflate_s += now_s() - t0;
+        return refill(r);
+      }
       if (err) {
         r->is_eof = 1;
         r->inflate_s += now_s() - t0;

@@ -10,7 +10,8 @@
  * Extra knobs live in the environment so that the five reference options stay untouched:
  *   QB_DEVICES=N        number of GPUs to spread batches over (default 1)
  *   QB_BATCH_MB=M       pinned slot size in MiB for seq[] and for qual[] (default 16)
- *   QB_LEN_CAP=L        longest read accepted (default 65536)
+ *   QB_LEN_CAP=L        longest read accepted (default and maximum 1048576; the accumulators start at 512 rows
+ *                       and grow with the longest read seen, so the limit costs nothing until it is needed)
  *   QB_KERNEL=0|1|2|3   auto | simple | fused | wtile
  *   QB_CLEAN_EXIT=1     free everything before exit (default: _exit after the SVG is flushed)
  *   QB_STATS_JSON=path  write reads/s, bases/s and stage times there (stdout stays the SVG)
@@ -105,6 +106,7 @@ struct mate_job {
   double inflate_s, wall_s;
   int stream_status;
   int decode_threads;
+  uint32_t len_cap;
 };
 
 /* reader thread of one mate: inflate + frame + pack + submit, until the stream ends */
@@ -127,6 +129,13 @@ static void *mate_thread(void *arg) {
     if (more < 0) {
       j->rc = QB_ERR_CAPACITY;
       snprintf(j->err, sizeof j->err, "%s: a record is longer than a batch slot (raise QB_BATCH_MB)", j->path);
+      qb_submit(j->ctx, &b, j->mate, 0, 0, 0);
+      break;
+    }
+    if (max_len > j->len_cap) {
+      j->rc = QB_ERR_CAPACITY;
+      snprintf(j->err, sizeof j->err, "%s: a read of %u bp is longer than QB_LEN_CAP=%u (the limit is 1048576)", j->path,
+               max_len, j->len_cap);
       qb_submit(j->ctx, &b, j->mate, 0, 0, 0);
       break;
     }
@@ -173,7 +182,7 @@ int main(int argc, char **argv) {
   qb_config cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.n_devices = (int)env_long("QB_DEVICES", 1);
-  cfg.len_cap = (uint32_t)env_long("QB_LEN_CAP", 65536);
+  cfg.len_cap = (uint32_t)env_long("QB_LEN_CAP", 1 << 20);
   cfg.n_mates = paired ? 2 : 1;
   cfg.adapters_enabled = adapters;
   cfg.adapter_keys = keys;
@@ -194,6 +203,7 @@ int main(int argc, char **argv) {
   for (int m = 0; m < cfg.n_mates; m++) {
     jobs[m].ctx = ctx;
     jobs[m].mate = m;
+    jobs[m].len_cap = cfg.len_cap;
     jobs[m].path = paired ? (m == 0 ? o.forward : o.reverse) : o.unpaired;
     pthread_create(&th[m], NULL, mate_thread, &jobs[m]);
   }
@@ -204,13 +214,30 @@ int main(int argc, char **argv) {
       qb_destroy(ctx);
       return 2;
     }
+  for (int m = 0; m < cfg.n_mates; m++) {
+    /* -1 is the clean end of the stream.  Anything else ended it early: like the reference (quack.c:193: any
+     * negative kseq_read() leaves the loop) the records in front of the damage are reported, but not silently */
+    const int st = jobs[m].stream_status;
+    if (st != -1 && st != 0)
+      fprintf(stderr, "quack: warning: %s: %s; the report covers the %llu records in front of it\n", jobs[m].path,
+              st == -2   ? "truncated record (quality string shorter than the sequence)"
+              : st == -3 ? "the compressed stream is damaged or truncated"
+              : st == -5 ? "a record without quality line (FASTA) in a FASTQ input"
+                         : "the stream ended with an error",
+              (unsigned long long)jobs[m].reads);
+  }
   const double t_stream = now_s();
 
   qr_data data[2];
   memset(data, 0, sizeof data);
   for (int m = 0; m < cfg.n_mates; m++) {
-    data[m].rows = (uint64_t *)malloc(sizeof(uint64_t) * QB_ROW_U64 * (size_t)cfg.len_cap);
-    if (qb_finish(ctx, m, data[m].rows, cfg.len_cap, &data[m].max_length, &data[m].n_reads)) {
+    /* longest read first (the reduce runs once, for both mates), then exactly that many rows */
+    int frc = qb_finish(ctx, m, NULL, 0, &data[m].max_length, &data[m].n_reads);
+    if (!frc) {
+      data[m].rows = (uint64_t *)malloc(sizeof(uint64_t) * QB_ROW_U64 * (size_t)(data[m].max_length ? data[m].max_length : 1));
+      frc = qb_finish(ctx, m, data[m].rows, data[m].max_length, &data[m].max_length, &data[m].n_reads);
+    }
+    if (frc) {
       fprintf(stderr, "quack: %s\n", qb_last_error(ctx));
       qb_destroy(ctx);
       return 2;

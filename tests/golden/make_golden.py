@@ -6,7 +6,8 @@ Run in the build container only (needs /root/reference and `make -C oracle ref`)
     python tests/golden/make_golden.py
 
 Inputs (committed): kat_t.fq, kat_k.fq, framing.fq (record-framing edge
-cases), adapters_all.fa (= zcat /root/reference/all.fa.gz, the adapter set configs 2-4 name).
+cases), kat_p.dat (KAT-P: the reference's own parser fixture klib/test/kseq_test.dat -- 2 FASTA records and a
+multi-line FASTQ record with an empty line inside the quality block), adapters_all.fa (= zcat /root/reference/all.fa.gz, the adapter set configs 2-4 name).
 Outputs (committed): rand_small.fq.gz, golden_raw.npz, golden_parse.json, golden_transform.json,
 golden_adapter_keys.npy, svg/*.svg.  The reference itself cannot travel to the GPU box; these
 files are how its answers do.
@@ -74,8 +75,9 @@ def main():
     np.savez_compressed(os.path.join(HERE, "golden_raw.npz"), **raw)
 
     parse = {}
-    for name in ("framing", "kat_k"):
-        recs, rc = po.ref_parse_records(fixtures[name])
+    fixtures_parse = dict(fixtures, kat_p=os.path.join(HERE, "kat_p.dat"))  # KAT-P = klib/test/kseq_test.dat
+    for name in ("framing", "kat_k", "kat_p"):
+        recs, rc = po.ref_parse_records(fixtures_parse[name])
         parse[name] = {"rc": rc, "records": [[s.decode("latin1"), q.decode("latin1") if q else None] for s, q in recs]}
     json.dump(parse, open(os.path.join(HERE, "golden_parse.json"), "w"), indent=1)
 

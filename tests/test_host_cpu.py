@@ -6,6 +6,7 @@ import hashlib
 import json
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -21,12 +22,14 @@ def built():
     build()
 
 
-FILES = {"kat_t": "kat_t.fq", "kat_k": "kat_k.fq", "framing": "framing.fq", "rand_small": "rand_small.fq.gz"}
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FILES = {"kat_t": "kat_t.fq", "kat_k": "kat_k.fq", "framing": "framing.fq", "rand_small": "rand_small.fq.gz",
+         "kat_p": "kat_p.dat"}   # kat_p = the reference's own parser fixture, klib/test/kseq_test.dat
 
 
 def test_reader_matches_reference_parse(golden_dir):
     gold = json.load(open(os.path.join(golden_dir, "golden_parse.json")))
-    for name in ("framing", "kat_k"):
+    for name in ("framing", "kat_k", "kat_p"):
         recs, rc = capi.parse_records(os.path.join(golden_dir, FILES[name]))
         assert rc == gold[name]["rc"]
         assert [[s.decode("latin1"), q.decode("latin1") if q else None] for s, q in recs] == gold[name]["records"]
@@ -219,8 +222,8 @@ def test_bgzf_pool_edge_cases(tmp_path):
         for t in (1, 4):
             recs, st = capi.parse_records(str(p), t)
             assert (len(recs), st) == (n, rc), (name, t)
-    # a block cut short, a flipped payload byte, a gzip member without the BGZF subfield: stream error (-3,
-    # where kseq_read() returns -3 too), the records of the intact blocks in front of it are kept
+    # a block cut short, a flipped payload byte: stream error (-3, where kseq_read() returns -3 too), the records
+    # of the intact blocks in front of it are kept
     first = int.from_bytes(good[16:18], "little") + 1
     second = int.from_bytes(good[first + 16: first + 18], "little") + 1
     t = tmp_path / "plain.fq"
@@ -229,7 +232,6 @@ def test_bgzf_pool_edge_cases(tmp_path):
     broken = {
         "truncated": good[: first + second - 5],
         "flipped": good[: first + 30] + bytes([good[first + 30] ^ 0x55]) + good[first + 31:],
-        "plain_member": good[:first] + gzip.compress(b"@z\nAC\n+\nII\n"),
     }
     for name, data in broken.items():
         p.write_bytes(data)
@@ -238,6 +240,66 @@ def test_bgzf_pool_edge_cases(tmp_path):
         if recs and recs[-1][1] is None:   # kseq semantics: a record cut inside its sequence comes back as FASTA
             recs = recs[:-1]
         assert 0 < len(recs) < len(want) and recs == want[: len(recs)], name   # a prefix of the true record list
+
+
+def test_bgzf_followed_by_other_members_reads_like_gzread(tmp_path):
+    """A BGZF file that continues with an ordinary gzip member, or ends in bytes that are no gzip member at all:
+    gzread() (the reference, quack.c:187) decodes the member and ignores the garbage; so does the pool."""
+    from quack_b200 import synth
+    blob = _fastq_blob(400, seed=7)
+    good = synth.bgzf_bytes(blob, block=3000)
+    first = int.from_bytes(good[16:18], "little") + 1
+    tail = b"@z\nACGTACGTAC\n+\nIIIIIIIIII\n"
+    cases = {
+        "plain_member_mid": good[:first] + gzip.compress(tail),
+        "plain_member_after_all": good[: -len(synth.BGZF_EOF)] + gzip.compress(tail) + gzip.compress(tail),
+        "bgzf_after_plain_member": good[:first] + gzip.compress(tail) + synth.bgzf_bytes(tail),
+        "trailing_garbage": good + b"this is not gzip",
+        "trailing_zeros": good + bytes(64),
+    }
+    p = tmp_path / "m.bgz"
+    for name, data in cases.items():
+        p.write_bytes(data)
+        want = capi.parse_records(str(p), 1)        # gzread path
+        assert len(want[0]) > 0 and want[1] in (-1, -2), name   # (a member boundary may cut a record: -2, as gzread)
+        assert po.parse_records(str(p)) == want, name
+        for t in (2, 8):
+            assert capi.parse_records(str(p), t) == want, (name, t)
+            bb, st = capi.read_batches(str(p), 20000, 100, t)
+            n_fastq = len([r for r in want[0] if r[1] is not None])
+            assert st in (-1, -2, -5) and sum(len(b[2]) for b in bb) in (n_fastq, len(want[0])), (name, t)
+
+
+@pytest.mark.parametrize("kind", ["plain", "gz", "bgzf"])
+def test_reader_on_a_pipe(kind, tmp_path):
+    """Non-seekable input (FIFO, process substitution, /dev/stdin): opened exactly once, nothing is lost to the
+    BGZF probe, whatever the thread count (the reference reads pipes through one gzopen, quack.c:187)."""
+    import threading
+    from quack_b200 import synth
+    blob = _fastq_blob(1000, seed=9)
+    data = {"plain": blob, "gz": gzip.compress(blob, 1), "bgzf": synth.bgzf_bytes(blob)}[kind]
+    f = tmp_path / "reg"
+    f.write_bytes(data)
+    want = capi.parse_records(str(f), 1)
+    assert len(want[0]) == 1000 and want[1] == -1
+    for threads in (0, 4):
+        fifo = str(tmp_path / f"fifo{threads}")
+        os.mkfifo(fifo)
+
+        def feed():
+            with open(fifo, "wb") as w:
+                w.write(data)
+        th = threading.Thread(target=feed)
+        th.start()
+        got = capi.parse_records(fifo, threads)
+        th.join()
+        assert got == want, threads
+    # the program itself on /dev/stdin never gets as far as CUDA without a GPU; the reader is what matters here
+    r = subprocess.run([sys.executable, "-c",
+                        "import sys; sys.path.insert(0, %r); from quack_b200 import capi; "
+                        "r, st = capi.parse_records('/dev/stdin', 4); print(len(r), st)" % ROOT],
+                       input=data, stdout=subprocess.PIPE, check=True)
+    assert r.stdout.split() == [b"1000", b"-1"]
 
 
 def test_bgzf_is_only_used_for_bgzf(tmp_path):

@@ -11,6 +11,7 @@ import pytest
 from oracle import pyoracle as po
 
 FIXTURES = {"kat_t": "kat_t.fq", "kat_k": "kat_k.fq", "framing": "framing.fq", "rand_small": "rand_small.fq.gz"}
+PARSE_FIXTURES = dict(FIXTURES, kat_p="kat_p.dat")   # KAT-P: klib/test/kseq_test.dat, the reference's parser fixture
 
 
 @pytest.fixture(scope="module")
@@ -84,8 +85,8 @@ def test_kat_k_known_answers(golden_dir, table):
 
 def test_framing_matches_reference_reader(golden_dir):
     gold = json.load(open(os.path.join(golden_dir, "golden_parse.json")))
-    for name in ("framing", "kat_k"):
-        recs, rc = po.parse_records(os.path.join(golden_dir, FIXTURES[name]))
+    for name in ("framing", "kat_k", "kat_p"):
+        recs, rc = po.parse_records(os.path.join(golden_dir, PARSE_FIXTURES[name]))
         assert rc == gold[name]["rc"]
         assert [[s.decode("latin1"), q.decode("latin1") if q else None] for s, q in recs] == gold[name]["records"]
     recs, rc = po.parse_records(os.path.join(golden_dir, "framing.fq"))
