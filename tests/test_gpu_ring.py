@@ -136,7 +136,7 @@ def mate_files(tmp_path_factory):
     f = {}
     for mate in (1, 2):
         for kind, kw in (("plain", {}), ("gz", {"gz_level": 1}), ("bgzf", {"gz_level": 1, "bgzf": True})):
-            p = str(d / f"m{mate}.{kind}.fq" + ("" if kind == "plain" else ".gz"))
+            p = str(d / (f"m{mate}.{kind}.fq" + ("" if kind == "plain" else ".gz")))
             synth.write_fastq(p, 2, mate, 150_000, 150, 0.1, **kw)
             f[(mate, kind)] = p
     return f
