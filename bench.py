@@ -91,32 +91,59 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+# --------------------------------------------------------------------------------- inputs on disk
+
+ADAPTER_FA = os.path.join(ROOT, "tests", "golden", "adapters_all.fa")
+GEN_BIN = os.path.join(ROOT, "quack_b200", "bin", "qb_gen_fastq")
+QUACK_BIN = os.path.join(ROOT, "quack_b200", "bin", "quack")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "quack")
+WORKLOAD = ("configs[1]: paired-end 2x150 bp, adapters all.fa.gz (333 10-mers), read-through adapters in 10% of pairs")
+
+
+def bench_config(pairs: int, world: int) -> dict:
+    """The `config` object: the same in both arms (the reference arm says in cpu_baseline.sample what it timed)."""
+    return {"workload": WORKLOAD, "pairs_per_gpu": pairs, "reads_per_step": 2 * pairs * world, "generator_seed": SEED}
+
+
+def scratch_dir(need_bytes: int):
+    """/dev/shm when it has the room (the files then never touch a disk), else the default temp directory."""
+    try:
+        st = os.statvfs("/dev/shm")
+        if st.f_bavail * st.f_frsize > need_bytes * 1.25:
+            return "/dev/shm"
+    except OSError:
+        pass
+    return None
+
+
+def gen_fastq(path: str, mate: int, first: int, n: int, mode: str = "plain", threads: int | None = None):
+    """Config-2 reads [first, first + n) of one mate through the standalone generator tool (tools/gen_fastq.cpp):
+    the same reads qb_gen_reads() produces, written without loading libquack_b200.so."""
+    cmd = [GEN_BIN, path, str(SEED), str(mate), str(first), str(n), str(READ_LEN), str(READ_LEN), str(ADAPTER_RATE),
+           mode, "1"]
+    if threads:
+        cmd.append(str(threads))
+    subprocess.run(cmd, check=True)
+
+
 # --------------------------------------------------------------------------------- CPU baseline
-
-def make_sample_files(tmp: str, pairs: int, gz_pairs: int):
-    from quack_b200 import synth
-    paths = {}
-    for mate in (1, 2):
-        p = os.path.join(tmp, f"sample_{mate}.fq")
-        synth.write_fastq(p, SEED, mate, pairs, READ_LEN, ADAPTER_RATE)
-        paths[mate] = p
-        if gz_pairs:
-            g = os.path.join(tmp, f"sample_{mate}.fq.gz")
-            synth.write_fastq(g, SEED, mate, gz_pairs, READ_LEN, ADAPTER_RATE, gz_level=1)
-            paths[(mate, "gz")] = g
-    return paths
-
 
 def cpu_baseline(pairs: int = 500_000, gz_pairs: int = 100_000):
     """Reference read_fastq() (or the oracle port when oracle/_ref is absent) on host cores, 1 thread."""
     from oracle import pyoracle as po
-    from quack_b200 import capi, synth
+    from quack_b200 import capi
     use_ref = po.have_ref()
     out = {"unit": "reads/s", "cores": 1, "kind": "reference" if use_ref else "port"}
-    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
-        paths = make_sample_files(tmp, pairs, gz_pairs)
-        table = po.AdapterTable.from_file(synth.ADAPTER_FA)
-        run = (lambda p: po.ref_read_fastq(p, synth.ADAPTER_FA)) if use_ref else (lambda p: po.read_fastq(p, table))
+    with tempfile.TemporaryDirectory(dir=scratch_dir(pairs * 700)) as tmp:
+        paths = {}
+        for mate in (1, 2):
+            paths[mate] = os.path.join(tmp, f"sample_{mate}.fq")
+            gen_fastq(paths[mate], mate, 0, pairs)
+            if gz_pairs:
+                paths[(mate, "gz")] = os.path.join(tmp, f"sample_{mate}.fq.gz")
+                gen_fastq(paths[(mate, "gz")], mate, 0, gz_pairs, "gz")
+        table = po.AdapterTable.from_file(ADAPTER_FA)
+        run = (lambda p: po.ref_read_fastq(p, ADAPTER_FA)) if use_ref else (lambda p: po.read_fastq(p, table))
         t0 = time.perf_counter()
         n = sum(run(paths[m]).n_reads for m in (1, 2))
         dt = time.perf_counter() - t0
@@ -135,49 +162,119 @@ def cpu_baseline(pairs: int = 500_000, gz_pairs: int = 100_000):
     return out
 
 
-def _ref_worker(args):
-    path1, path2, adapters = args
+def e2e_file(pairs: int = 2_000_000):
+    """File -> SVG, wall clock: the `quack` program of this repo and the unmodified reference binary on the SAME
+    config-2 shaped .fq.gz files (multi-member gzip as SURVEY 8d specifies, and the same reads as BGZF), SVGs compared
+    byte for byte; host gzip decode and CUDA start-up of the process broken out (QB_STATS_JSON)."""
+    out = {"pairs": pairs, "unit": "reads/s", "reads": 2 * pairs}
+    with tempfile.TemporaryDirectory(dir=scratch_dir(pairs * 700)) as tmp:
+        files = {}
+        for mode in ("gz", "bgzf"):
+            for mate in (1, 2):
+                files[(mode, mate)] = os.path.join(tmp, f"{mode}_{mate}.fq.gz")
+                gen_fastq(files[(mode, mate)], mate, 0, pairs, mode)
+        out["gz_bytes"] = sum(os.path.getsize(files[("gz", m)]) for m in (1, 2))
+        common = ["-a", ADAPTER_FA, "-n", "cfg2"]
+        svg_ref = None
+        if os.path.exists(REF_BIN):
+            t0 = time.perf_counter()
+            r = subprocess.run([REF_BIN, "-1", files[("gz", 1)], "-2", files[("gz", 2)], *common], stdout=subprocess.PIPE,
+                               stderr=subprocess.DEVNULL)
+            dt = time.perf_counter() - t0
+            svg_ref = r.stdout
+            out["reference"] = {"seconds": dt, "value": 2 * pairs / dt, "cores": 1, "input": "multi-member gzip",
+                                "program": "oracle/_ref/quack (unmodified reference, single-threaded)"}
+        for mode in ("gz", "bgzf"):
+            js = os.path.join(tmp, "stats.json")
+            best = None
+            for _ in range(2):
+                env = dict(os.environ, QB_STATS_JSON=js)
+                t0 = time.perf_counter()
+                r = subprocess.run([QUACK_BIN, "-1", files[(mode, 1)], "-2", files[(mode, 2)], *common],
+                                   stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+                dt = time.perf_counter() - t0
+                if r.returncode != 0:
+                    raise RuntimeError(r.stderr.decode()[-400:])
+                if best is None or dt < best[0]:
+                    best = (dt, r.stdout, json.load(open(js)))
+            dt, svg, st = best
+            rec = {"seconds": dt, "value": 2 * pairs / dt, "input": "multi-member gzip" if mode == "gz" else "BGZF",
+                   "create_s": st["create_s"], "stream_s": st["stream_s"], "finish_s": st["finish_s"],
+                   "render_s": st["render_s"],
+                   "host_decode": {"MBps_text": st["host_gzip_decode_MBps"], "threads_per_file": st["decode_threads"],
+                                   "seconds_waiting_for_inflate": st["host_gzip_decode_s_max_over_mates"],
+                                   "cores": os.cpu_count()},
+                   "svg_identical_to_reference": (svg == svg_ref) if svg_ref is not None else None}
+            if svg_ref is not None and svg != svg_ref:
+                raise AssertionError(f"SVG of the {mode} run differs from the reference's")
+            if svg_ref is not None:
+                rec["speedup_vs_reference"] = out["reference"]["seconds"] / dt
+            out["ours_" + mode] = rec
+    return out
+
+
+_REF_ADAPTERS = None
+
+
+def _ref_worker(job):
+    path1, path2 = job
     from oracle import pyoracle as po
     if po.have_ref():
-        return po.ref_read_fastq(path1, adapters).n_reads + po.ref_read_fastq(path2, adapters).n_reads
-    t = po.AdapterTable.from_file(adapters)
+        return po.ref_read_fastq(path1, ADAPTER_FA).n_reads + po.ref_read_fastq(path2, ADAPTER_FA).n_reads
+    t = po.AdapterTable.from_file(ADAPTER_FA)
     return po.read_fastq(path1, t).n_reads + po.read_fastq(path2, t).n_reads
 
 
 def bench_reference(args):
-    """--impl reference: the reference's own read_fastq() on this box's host cores.  The reference is
-    single-threaded, so the box's capacity is shown as one independent reference instance per core,
-    each over the same bounded sample of the workload."""
+    """--impl reference: the reference's own read_fastq() on this box's host cores, on the GPU arm's workload.  The
+    reference is single-threaded, so 'all the host threads it can use' = one independent reference instance per
+    core, each over its shard of the step's pairs (uncompressed FASTQ text: no inflate in the timed region, which
+    favours the reference).  libquack_b200.so is never loaded here; the inputs come from the standalone generator."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     from oracle import pyoracle as po
-    from quack_b200 import synth
+    kind = "reference" if po.have_ref() else "port"
+    if po.have_ref():
+        po.ref()          # the parent maps oracle/_ref/libquack_ref.so too (the workers are forks of it)
+    else:
+        po.lib()
     cores = min(os.cpu_count() or 1, 64)
-    pairs = int(os.environ.get("QB_REF_SAMPLE_PAIRS", "100000"))
-    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as tmp:
-        paths = make_sample_files(tmp, pairs, 0)
-        job = (paths[1], paths[2], synth.ADAPTER_FA)
+    pairs = int(os.environ.get("QB_BENCH_PAIRS", str(args.pairs)))
+    # the step's workload is `pairs` per GPU; with N > 1 the CPU arm times a bounded sample of it: one GPU's share
+    sample_pairs = int(os.environ.get("QB_REF_SAMPLE_PAIRS", str(pairs)))
+    shard = (sample_pairs + cores - 1) // cores
+    with tempfile.TemporaryDirectory(dir=scratch_dir(sample_pairs * 700)) as tmp:
+        jobs = []
+        for i in range(cores):
+            first, n = i * shard, min(shard, sample_pairs - i * shard)
+            if n <= 0:
+                break
+            p = [os.path.join(tmp, f"shard{i}_{m}.fq") for m in (1, 2)]
+            for m in (1, 2):
+                gen_fastq(p[m - 1], m, first, n)
+            jobs.append(tuple(p))
         times = []
-        with mp.get_context("fork").Pool(cores) as pool:
+        with mp.get_context("fork").Pool(len(jobs)) as pool:
             for i in range(args.warmup + args.steps):
                 t0 = time.perf_counter()
-                n = sum(pool.map(_ref_worker, [job] * cores))
+                n = sum(pool.map(_ref_worker, jobs, chunksize=1))
                 dt = time.perf_counter() - t0
+                assert n == 2 * sample_pairs, (n, sample_pairs)
                 if i >= args.warmup:
                     times.append(dt)
         sec = sum(times) / len(times)
         value = n / sec
-    kind = "reference" if po.have_ref() else "port"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s", "bases_per_s": value * READ_LEN,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1]: paired-end 2x150 bp, adapters all.fa.gz", "sample_pairs_per_instance": pairs,
-                   "instances": cores},
-        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": kind,
-                         "sample": f"{cores} independent single-threaded instances x {pairs} pairs, uncompressed FASTQ"},
+        "config": bench_config(pairs, max(1, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": len(jobs), "kind": kind,
+                         "sample": (f"{sample_pairs} pairs per step ({'all of' if args.gpus <= 1 else 'one GPU share of'} the "
+                                    f"step's workload), {len(jobs)} independent single-threaded reference instances, one "
+                                    f"shard of {shard} pairs each, uncompressed FASTQ text (kseq parsing inside, no inflate)")},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -236,6 +333,13 @@ def bench_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # every rank streams its batches from its own pinned arena: keep the ranks' host threads on disjoint cores
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cpus) // world)
+            os.sched_setaffinity(0, set(cpus[local_rank * per:(local_rank + 1) * per]) or set(cpus))
+        except (AttributeError, OSError):
+            pass
 
     def barrier():
         if world > 1:
@@ -325,16 +429,17 @@ def bench_ours(args):
     # which kernel the timed launches took, and its measured DRAM traffic (one `ncu --set full` capture of the same
     # kernel on the same read shape, dram__bytes_read.sum + dram__bytes_write.sum, scaled per read)
     kname = "qb::period_kernel<adapters,5 steps,20 warps>" if ctx.period_launch_count else "qb::fused_kernel<true,96>"
-    traffic = None
-    try:
+    traffic, traffic_src = None, None
+    try:  # one `ncu --set full` capture of this kernel at this launch size (profiles/bench_traffic.json says which)
         with open(os.path.join(ROOT, "profiles", "bench_traffic.json")) as f:
             tj = json.load(f)
             if tj.get("kernel_family") == ("period" if ctx.period_launch_count else "fused"):
                 traffic = tj["dram_bytes_per_read"] * db[0].info[0]
+                traffic_src = tj.get("source")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": kname,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kname,
                 "algorithmic_bytes_per_launch": alg_bytes_launch, "kernel_ms_mean": ker_mean,
                 "kernel_ms_min": min(ker_ms) if ker_ms else None, "launches_timed": len(ker_ms),
                 "kernel_share_of_step": 2 * ker_mean / (ms_dev / args.steps)}
@@ -342,6 +447,12 @@ def bench_ours(args):
     # ---- e2e: the same workload streamed from pinned host memory through qb_submit_from ----
     e2e_pairs = int(os.environ.get("QB_BENCH_E2E_PAIRS", str(pairs)))
     h2d_gbs = ctx.measure_h2d(256 << 20, 3, 0)
+    # the N-GPU ingest ceiling: every rank copies at the same time (shared PCIe switches / host memory show up here)
+    barrier()
+    h2d_conc = ctx.measure_h2d(256 << 20, 6, 0)
+    barrier()
+    h2d_conc_sum = allsum(h2d_conc)
+    h2d_conc_min = -allmax(-h2d_conc)
     arena = Arena(capi, first, e2e_pairs, reads_per_batch)
     ctx.reset(0)
     ctx.reset(1)
@@ -375,11 +486,30 @@ def bench_ours(args):
            "host_batch_bytes_per_step": arena.bytes,
            "h2d_gbs_achieved": h2d_step / e2e_s / 1e9, "h2d_gbs_link_measured": h2d_gbs,
            "frac_of_h2d_roofline": h2d_step / e2e_s / 1e9 / h2d_gbs,
+           "h2d_gbs_all_ranks_copying": {"sum": h2d_conc_sum, "slowest_rank": h2d_conc_min,
+                                         "note": "256 MiB pinned copies issued by every rank at once: the node's ingest ceiling"},
+           "frac_of_concurrent_h2d_roofline": h2d_step * world / e2e_s / 1e9 / h2d_conc_sum,
            "note": "offsets/lengths (8 B/read) stay on the host for batches the period kernel takes: the host verified their shape"}
     arena.free()
     for b in db:
         b.free()
     ctx.close()
+
+    # ---- the other kernels of the path, kernel only, CUDA events (rank 0; secondary to the headline) ----
+    other = {}
+    if rank == 0 and not args.no_other_kernels:
+        def kernel_only(len_min, len_max, cap, ad, n):
+            with capi.Context(cap, adapter_keys=keys if ad else None, device_ids=[local_rank]) as c2:
+                b = c2.generate(SEED if len_min == len_max else 4, 1, 0, n, len_min, len_max, ADAPTER_RATE)
+                nr, nb = b.info
+                avg, mn = b.time(0, warmup=3, iters=10, flush_l2=False)
+                b.free()
+            alg = 2 * nb + 8 * nr
+            return {"reads_per_launch": nr, "kernel_ms_mean": avg, "achieved": alg / avg / 1e6, "unit": "GB/s",
+                    "frac": alg / avg / 1e6 / peak, "reads_per_s": nr / avg * 1e3}
+        other["config1_5_150bp_no_adapters"] = kernel_only(READ_LEN, READ_LEN, READ_LEN, False, 10_000_000)
+        other["config4_ragged_35_300_no_adapters"] = kernel_only(35, 300, 304, False, 5_000_000)
+        other["config4_ragged_35_300_adapters"] = kernel_only(35, 300, 304, True, 5_000_000)
 
     if rank == 0:
         line = {
@@ -387,12 +517,18 @@ def bench_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "wall_ms_per_step": wall_ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "configs[1]: paired-end 2x150 bp, adapters all.fa.gz (333 10-mers), "
-                                   "read-through adapters in 10% of pairs",
-                       "pairs_per_gpu": pairs, "reads_per_step": total_reads_step, "parallelism": f"shard{world}",
-                       "l2": "inputs (3.1 GB per launch) larger than L2", "generator_seed": SEED},
+            "config": bench_config(pairs, world),
+            "notes": {"parallelism": f"shard{world}: reads shard over the ranks, one ncclReduce of the count arrays",
+                      "l2": "inputs (3.1 GB per launch) larger than L2"},
             "roofline": roofline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks, "checked": checked,
         }
+        if other:
+            line["roofline_other_kernels"] = other
+        if world == 1 and not args.no_e2e_file:
+            try:
+                line["e2e_file"] = e2e_file(int(os.environ.get("QB_BENCH_FILE_PAIRS", "2000000")))
+            except Exception as ex:
+                line["e2e_file"] = {"error": repr(ex)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline()
@@ -411,6 +547,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=10_000_000, help="pairs per GPU (configs[1]: 10M)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e-file", action="store_true", help="skip the file -> SVG comparison with the reference binary")
+    ap.add_argument("--no-other-kernels", action="store_true", help="skip the secondary kernel-only numbers")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)

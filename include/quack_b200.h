@@ -180,6 +180,11 @@ int qb_measure_h2d(qb_ctx *ctx, int device_index, uint64_t bytes, int iters, dou
  * warp steps per period, periods per tile, reads per tile, stages, warps per CTA; slot[p] = histogram block << 7 | 32-bit
  * column of position p (its bank is the column modulo 32). */
 int qb_period_layout(uint32_t read_len, int adapters, uint32_t info[7], uint8_t slot[256]);
+/* Tools: the rest of that plan.  out = reads per period, words per period, steps, periods per tile, reads per tile,
+ * stages, warps, histogram blocks, bytes per warp block, header bytes of it, tiles in the -a packed-code ring, ring
+ * row stride, shared address of the ring when it lives in the unused columns of histogram block 1 (else 0), ring
+ * bytes per warp there, ring offset inside the warp block otherwise, bytes of one staged buffer. */
+int qb_period_plan_info(uint32_t read_len, int adapters, uint32_t out[16]);
 
 /* ---- host helpers that define the kernel's inputs ---- */
 /* lookup[(c-65)&~32] of quack.c:150,201 extended to all byte values. */

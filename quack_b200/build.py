@@ -42,7 +42,7 @@ def _nvcc() -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libquack_b200.so (kernels + C-ABI) and, when present, the host program."""
     os.makedirs(LIBDIR, exist_ok=True)
-    srcs = [os.path.join(CSRC, f) for f in ("qb_kernels.cu", "qb_wtile.cu", "qb_period.cu", "qb_api.cu", "qb_host.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("qb_kernels.cu", "qb_wtile.cu", "qb_period.cu", "qb_api.cu", "qb_host.cpp", "qb_gen.cpp")]
     host_lib_srcs = [os.path.join(HOST, f) for f in ("fq_reader.c", "render.c")
                      if os.path.exists(os.path.join(HOST, f))]
     deps = srcs + host_lib_srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
@@ -82,11 +82,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             subprocess.run(["gcc", "-O3", "-std=c11", "-D_DEFAULT_SOURCE", "-Wall", "-o", quack_bin(), main_c,
                             "-I" + os.path.join(HERE, "..", "include"), "-L" + LIBDIR, "-lquack_b200",
                             "-Wl,-rpath,$ORIGIN/../lib", "-lz", "-lm", "-lpthread"], check=True)
-    gen_c = os.path.join(HOST, "gen_fastq.c")
-    if os.path.exists(gen_c):
+    # the standalone writer of the synthetic benchmark inputs: the generator's translation unit + a main, no library
+    gen_cpp = os.path.join(HERE, "..", "tools", "gen_fastq.cpp")
+    gen_dep = [gen_cpp, os.path.join(CSRC, "qb_gen.cpp"), os.path.join(CSRC, "qb_host.h")]
+    if os.path.exists(gen_cpp):
         os.makedirs(BINDIR, exist_ok=True)
-        if force or not _newer(gen_bin(), [gen_c, out]):
-            subprocess.run(["gcc", "-O3", "-std=c11", "-D_DEFAULT_SOURCE", "-Wall", "-o", gen_bin(), gen_c,
-                            "-I" + os.path.join(HERE, "..", "include"), "-L" + LIBDIR, "-lquack_b200",
-                            "-Wl,-rpath,$ORIGIN/../lib", "-lz", "-lm", "-lpthread"], check=True)
+        if force or not _newer(gen_bin(), gen_dep):
+            subprocess.run(["g++", "-O3", "-std=c++17", "-Wall", "-o", gen_bin(), gen_cpp, os.path.join(CSRC, "qb_gen.cpp"),
+                            "-lz", "-lpthread"], check=True)
     return out

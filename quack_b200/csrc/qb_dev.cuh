@@ -144,6 +144,20 @@ __device__ __forceinline__ uint32_t key_bytes(uint32_t sw, uint32_t qw, const Ke
   bad = lop3<0xFE>(bad, qs, qs + c.x11);
   return lop3<0xF2>(qs << 2, nc >> 6, c.m03);  // (qs << 2) | (~(nc >> 6) & 0x03030303)
 }
+// The same with the 2-bit codes as a by-product (`code`: one clean code per byte, what the adapter scan gathers
+// with one multiply) and the key bytes formed by a multiply-add on the other pipe: qs * 4 + code == (qs << 2) | code
+// whenever no quality byte is out of the window (then the word is re-keyed anyway).
+__device__ __forceinline__ uint32_t key_bytes_c(uint32_t sw, uint32_t qw, const KeyConsts &c, uint32_t &nc,
+                                                uint32_t &bad, uint32_t &code) {
+  const uint32_t n_cg = lop3<0x6A>(sw, c.m5b, c.x43) + c.a7f;
+  const uint32_t n_g = lop3<0x6A>(sw, c.m1f, c.x07) + c.a3f;
+  const uint32_t n_t = lop3<0x6A>(sw, c.m1f, c.x14) + c.a3f;
+  nc = lop3<0xE4>(n_cg, n_g & n_t, c.m80);
+  const uint32_t qs = qw - c.qsub;
+  bad = lop3<0xFE>(bad, qs, qs + c.x11);
+  code = lop3<0x0C>(nc >> 6, c.m03, c.m03);  // ~(nc >> 6) & 0x03030303
+  return qs * 4u + code;
+}
 // key bytes of a word that has an out-of-window quality byte: dummy row, code kept
 __device__ __forceinline__ uint32_t key_bytes_bad(uint32_t nc) {
   return (~(nc >> 6) & 0x03030303u) | ((kScoreBins << 2) * 0x01010101u);

@@ -128,8 +128,16 @@ struct PeriodPlan {
   uint32_t wblock;           // bytes of one warp block (barriers, first hits, queue, stages x (seq + qual))
   uint32_t smem_base;        // shared address the dynamic shared memory must start at (checked by the kernel)
   uint32_t smem_bytes;
-  uint32_t afilt_s, exact_s, kmerhist_s, bloom_s, slot_s;  // shared addresses of the CTA-wide arrays
+  uint32_t afilt_s, exact_s, kmerhist_s, slot_s;  // shared addresses of the CTA-wide arrays
   uint32_t region_s[3], region_n[3];      // warp blocks: region_n[i] blocks from region_s[i]
+  // -a: every warp keeps the 2-bit codes of its last `rt` tiles (one byte per 32-bit word of bases, one row per
+  // period) so that anchor hits can wait in a queue until 32 of them fill a confirmation pass
+  uint32_t rt;               // tiles in the packed-code ring (2..4)
+  uint32_t prow_stride;      // bytes from one period row to the next (word i of a period at row + 4 + i)
+  uint32_t pring_hole;       // != 0: warp 0's ring, in the unused columns of histogram block 1; 0: inside the warp block
+  uint32_t pring_wstride;    // hole rings: bytes from one warp's ring to the next
+  uint32_t pring_off;        // in-block rings: offset inside the warp block
+  uint32_t hdr_bytes;        // warp block header (barriers, queue, first hits[, ring]); the staged tiles follow
   uint32_t qbase;
   uint32_t grid;
   int ok;                    // 0: not a batch for this kernel

@@ -29,7 +29,9 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <array>
 #include <cstring>
+#include <map>
 #include <mutex>
 
 namespace qb {
@@ -37,24 +39,19 @@ namespace qb {
 constexpr uint32_t kPHist0 = 0x10000u;             // shared address of histogram block 0
 constexpr uint32_t kPBlockStride = 0x10000u;       // block b at kPHist0 + b * 64 KiB (its address has byte 1 == 0)
 constexpr uint32_t kPBlockBytes = kHistRows * 256u;  // 192 rows x 256 B = 48 KiB
-constexpr uint32_t kPBloomBits = 1u << 14;          // -a: one-hash Bloom filter of the 10-mer keys in front of the exact set
-constexpr uint32_t kPBloomMul = 0x9E3779B1u;
-constexpr uint32_t kPPad = 16;                     // readable bytes behind a staged buffer (confirmation loads)
 constexpr uint32_t kPMaxStages = 4;
 constexpr uint32_t kPMaxRpt = 64;                  // reads per tile
 // offsets inside a warp block (multiples of 16)
 constexpr uint32_t kPoBar = 0;                     // kPMaxStages mbarriers
-constexpr uint32_t kPoCount = 32;                  // -a: number of queued anchor hits of the tile
-constexpr uint32_t kPoQueue = 48;                  // -a: kPQueue u16 word indices of anchor hits
-constexpr uint32_t kPQueue = 64;                   //     (more hits in a tile: several rounds of queue + confirm)
-constexpr uint32_t kPoFhit = kPoQueue + kPQueue * 2u;  // -a: first-hit position per read of the tile
+constexpr uint32_t kPoQueue = 32;                  // -a: kPQueue u16 entries: hit bit of the group << 5 | lane
+constexpr uint32_t kPQueue = 64;
+constexpr uint32_t kPoFhit = kPoQueue + kPQueue * 2u;  // -a: first-hit position of every read of the group's tiles
+constexpr uint32_t kPHoleOff = 64;                 // -a: a ring row inside a row of histogram block 1 starts here
+constexpr uint32_t kPHoleRowBytes = 256u - kPHoleOff;
 // one staged buffer: the tile's bytes from the 16-byte boundary below its first byte to the one above its last
-// (tile_bytes is a multiple of 4, not of 16: a tile starts 0, 4, 8 or 12 bytes behind a boundary) + padding
+// (tile_bytes is a multiple of 4, not of 16: a tile starts 0, 4, 8 or 12 bytes behind a boundary)
 __host__ __device__ inline uint32_t pbuf_bytes(uint32_t tile_bytes) {
-  return ((tile_bytes + 15u) & ~15u) + ((tile_bytes & 15u) ? 16u : 0u) + kPPad;
-}
-__host__ __device__ inline uint32_t pblock_hdr(int adapters, uint32_t rpt) {
-  return adapters ? kPoFhit + ((rpt * 4u + 15u) & ~15u) : kPoCount;
+  return ((tile_bytes + 15u) & ~15u) + ((tile_bytes & 15u) ? 16u : 0u);
 }
 
 struct PArgs {
@@ -70,14 +67,6 @@ struct PArgs {
 
 __device__ __forceinline__ uint32_t p_slot_addr(uint32_t e) {
   return kPHist0 + (e >> 7) * kPBlockStride + ((e & 63u) << 2);
-}
-
-// inverted 2-bit codes of 4 bases in bits 7:6 of each byte (see key_bytes, qb_dev.cuh)
-__device__ __forceinline__ uint32_t p_ncodes(uint32_t sw, const KeyConsts &c) {
-  const uint32_t n_cg = lop3<0x6A>(sw, c.m5b, c.x43) + c.a7f;
-  const uint32_t n_g = lop3<0x6A>(sw, c.m1f, c.x07) + c.a3f;
-  const uint32_t n_t = lop3<0x6A>(sw, c.m1f, c.x14) + c.a3f;
-  return lop3<0xE4>(n_cg, n_g & n_t, c.m80);
 }
 
 // rare path: the 4 bases of a word with an out-of-window quality byte, counted one by one in global memory
@@ -99,6 +88,12 @@ static __device__ __noinline__ uint32_t p_exact_word(uint32_t sw, uint32_t qw, u
 
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
   unsigned short v;
@@ -127,6 +122,13 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
   const uint32_t tb = P.tile_bytes, buf = P.buf_bytes, stages = P.stages, nblocks = P.nblocks;
   constexpr bool aligned = kAligned;  // tile_bytes % 16 == 0: every tile starts on a 16-byte boundary (8 x 150 bp)
   const uint32_t last = wp - 32u * (uint32_t)(kS - 1);  // active lanes of the last step (1..32)
+  // Lane <-> word map of a period: word 32 s + lane in step s, the lanes of a step side by side.  (Giving a lane kS
+  // CONSECUTIVE words would save the -a scan four of its five shuffles per period, but then lanes 75 words apart
+  // -- the same positions of two reads -- meet in one atomic: 4 x 150 bp would pay a second wavefront on every
+  // update, 6 x 100 bp five more.  Side by side, the 32 lanes of a step always hold 32 different positions.)
+  const uint32_t w0 = lane;                                    // this lane's word of step 0
+  constexpr uint32_t kWs = 32u;                                // words from one step to the next
+  const uint32_t nact = lane < last ? (uint32_t)kS : (uint32_t)kS - 1u;  // steps in which this lane has a word
 
   // ---- this warp's block ----
   uint32_t wb_s;
@@ -139,15 +141,24 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
     else
       wb_s = P.region_s[2] + (w - P.region_n[1]) * P.wblock;
   }
-  const uint32_t ring_s = wb_s + pblock_hdr(kAd, rpt);  // stage s: bases at ring_s + 2 s buf, quality bytes + buf
-  const uint32_t fhit_s = wb_s + kPoFhit, q_s = wb_s + kPoQueue, qcount_s = wb_s + kPoCount;
-  const uint32_t bloom_s = P.bloom_s;
+  const uint32_t ring_s = wb_s + P.hdr_bytes;  // stage s: bases at ring_s + 2 s buf, quality bytes + buf
+  const uint32_t fhit_s = wb_s + kPoFhit, q_s = wb_s + kPoQueue;
   const uint32_t kmerhist_s = P.kmerhist_s, exact_s = P.exact_s;
+  // packed-code ring of this warp: row r (one period) at pring_s + r * prs, the code byte of word i at + 4 + i
+  const uint32_t pring_s = P.pring_hole ? P.pring_hole + warp * P.pring_wstride : wb_s + P.pring_off;
+  const uint32_t prs = P.prow_stride, rt = P.rt;
 
   // ---- prologue: zero the histograms, load the adapter tables, init barriers ----
   auto clear_counters = [&]() {
     const uint4 z = make_uint4(0, 0, 0, 0);
     for (uint32_t b = 0; b < nblocks; b++) {
+      if (kAd && b == 1u && P.pring_hole) {  // block 1 shares its rows with the packed-code rings: counter columns only
+        for (uint32_t i = tid; i < kHistRows * (kPHoleOff / 16u); i += kPThreads) {
+          const uint32_t r = i / (kPHoleOff / 16u), c = i - r * (kPHoleOff / 16u);
+          *reinterpret_cast<uint4 *>(gen(kPHist0 + kPBlockStride + r * 256u + c * 16u)) = z;
+        }
+        continue;
+      }
       uint4 *h4 = reinterpret_cast<uint4 *>(gen(kPHist0 + b * kPBlockStride));
       for (uint32_t i = tid; i < kPBlockBytes / 16u; i += kPThreads) h4[i] = z;
     }
@@ -158,25 +169,15 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
   };
   clear_counters();
   if (kAd) {
+    // the anchor bitmap with the bits of every word reversed: `word << anchor` then leaves the answer in bit 31,
+    // from where a funnel shift moves it into the lane's hit mask (2 instructions per probe instead of 4)
     uint32_t *af = reinterpret_cast<uint32_t *>(gen(P.afilt_s));
-    for (uint32_t i = tid; i < kAnchorWords * kAnchorCopies; i += kPThreads) af[i] = args.ad.anchor[i / kAnchorCopies];
+    for (uint32_t i = tid; i < kAnchorWords * kAnchorCopies; i += kPThreads) af[i] = __brev(args.ad.anchor[i / kAnchorCopies]);
     uint32_t *ex = reinterpret_cast<uint32_t *>(gen(exact_s));
     if (args.ad.exact)
       for (uint32_t i = tid; i < kExactSlots; i += kPThreads) ex[i] = args.ad.exact[i];
     uint32_t *fh = reinterpret_cast<uint32_t *>(gen(fhit_s));
-    for (uint32_t i = lane; i < rpt; i += 32u) fh[i] = kNoHit;
-    if (lane == 0) *reinterpret_cast<uint32_t *>(gen(qcount_s)) = 0;
-    uint32_t *bl = reinterpret_cast<uint32_t *>(gen(bloom_s));
-    for (uint32_t i = tid; i < kPBloomBits / 32u; i += kPThreads) bl[i] = args.ad.exact ? 0u : 0xFFFFFFFFu;
-    __syncthreads();
-    if (args.ad.exact)
-      for (uint32_t i = tid; i < kExactSlots; i += kPThreads) {
-        const uint32_t k = args.ad.exact[i];
-        if (k != kExactEmpty) {
-          const uint32_t h = (k * kPBloomMul) >> 18;
-          atomicOr(&bl[h >> 5], 1u << (h & 31u));
-        }
-      }
+    for (uint32_t i = lane; i < rt * rpt; i += 32u) fh[i] = kNoHit;
   }
   // the slot table into shared memory: indexing the kernel arguments with a per-thread position is a divergent
   // constant load (one transaction per lane): 20 of them per thread cost ~10 us per launch
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
 #pragma unroll
   for (int s = 0; s < kS; s++)
 #pragma unroll
-    for (int j = 0; j < 4; j++) col[s][j] = p_slot_addr(lds_u8(P.slot_s + (4u * (32u * s + lane) + j) % len));
+    for (int j = 0; j < 4; j++) col[s][j] = p_slot_addr(lds_u8(P.slot_s + (4u * (w0 + kWs * s) + j) % len));
   // Even l: the j-th byte of a word always holds positions of the parity of j, the increments are the two
   // constants.  Odd l: the parity also depends on the read inside the period -> one increment per column.
   uint32_t inc[kOdd ? kS : 1][4];
@@ -214,11 +215,16 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
 #pragma unroll
     for (int s = 0; s < (kOdd ? kS : 1); s++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) inc[s][j] = (((4u * (32u * s + lane) + j) % len) & 1u) ? inc_hi : inc_lo;
+      for (int j = 0; j < 4; j++) inc[s][j] = (((4u * (w0 + kWs * s) + j) % len) & 1u) ? inc_hi : inc_lo;
   }
   const uint32_t afilt_or = P.afilt_s | ((lane >> 2) * 4u);  // this lane's copy of the anchor map (8 copies, 32-byte rows)
   const uint32_t nxt = (lane + 1u) & 31u;
   const uint32_t len_magic = 0xFFFFFFFFu / len + 1u;  // floor(b / len) = umulhi(b, len_magic) for b < 2^24
+  // hit mask of a tile: one bit per (period, step), pushed in from the right -> (pp, s) sits at bit
+  // (ppt - 1 - pp) kS + (kS - 1 - s).  Lanes without a word in the last step never report a hit there.
+  uint32_t hm_valid = (ppt * (uint32_t)kS >= 32u) ? kFull : (1u << (ppt * (uint32_t)kS)) - 1u;
+  for (uint32_t pp = 0; pp < ppt; pp++)
+    for (uint32_t s = nact; s < (uint32_t)kS; s++) hm_valid &= ~(1u << (pp * (uint32_t)kS + ((uint32_t)kS - 1u - s)));
   long long n_invalid = 0;
 
   auto flush = [&]() {  // all warps are behind a barrier
@@ -276,51 +282,82 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
     }
   };
 
-  // ---- -a: confirm the queued anchor hits of this tile (quack.c:210-217) ----
-  // Entry = word index w in the tile: the 7-mer starting at base 4 w passed the filter.  The windows that
-  // contain it start at 4 w - 3 .. 4 w.  One lane per entry: it decodes the 16 bases of words w - 1 .. w + 2
-  // once (aligned loads, the SWAR code of phase A) and tests the four 10-mers against the exact key set.  A
-  // window whose 10 bases lie inside one read lowers that read's first-hit position; a hit that ends on the
-  // last base of its read is dropped (it can only be the first hit if there is no other, and then the
-  // reference counts nothing).
-  auto confirm = [&](uint32_t seq_s, uint32_t qn) {  // qn <= kPQueue
-    __syncwarp();
-    for (uint32_t e0 = 0; e0 < qn; e0 += 32u) {
-      const uint32_t e = e0 + lane;
-      if (e < qn) {
-        const uint32_t b0 = lds_u16(q_s + 2u * e) * 4u;  // tile byte of the anchor's first base
-        const uint32_t n = __umulhi(b0, len_magic), p0 = b0 - n * len;  // its read in the tile, its position
-        const uint32_t A = seq_s + b0;
-        const uint32_t cm = gather_codes(~p_ncodes(lds_u32(A - 4u), kc));  // bases -4..-1 (first word of a tile: unused)
-        const uint32_t c0 = gather_codes(~p_ncodes(lds_u32(A), kc));
-        const uint32_t c1 = gather_codes(~p_ncodes(lds_u32(A + 4u), kc));
-        const uint32_t c2 = gather_codes(~p_ncodes(lds_u32(A + 8u), kc));
-        // codes of bases -4 .. 11, 2 bits each, first base least significant (the gathered codes are top bytes)
-        const uint32_t ctx = __byte_perm(__byte_perm(cm, c0, 0x0073), __byte_perm(c1, c2, 0x0073), 0x5410);
-        // window o starts at base o - 4 (o = 1..4: 3, 2, 1, 0 bases before the anchor): Bloom filter of the keys
-        uint32_t pass = 0;
+  // ---- -a: anchor hits are confirmed per GROUP of up to rt tiles (quack.c:210-217) ----
+  // A lane keeps the hit bits of the group's tiles in one register (hm_acc: the newest tile in the low bits), the
+  // 2-bit codes of the tiles stay in the packed-code ring.  When about 32 hits have come together (or the ring is
+  // full) the hits are expanded into a queue -- entry = bit index << 5 | lane, placed with a warp prefix sum, no
+  // atomics -- and confirmed 32 at a time, one lane per entry: the 16 bases of words w - 1 .. w + 2 come as ONE
+  // 32-bit value out of the ring row (two aligned loads and a funnel shift), the four 10-mers that contain the
+  // anchor are tested against the exact key set.  A window whose 10 bases lie inside one read lowers that read's
+  // first-hit position; a hit that ends on the last base of its read is dropped (it can only be the first hit if
+  // there is no other, and then the reference counts nothing).  Bytes of a ring row outside the period are garbage:
+  // a window that reaches them does not lie inside one read (a period is whole reads).
+  const uint32_t hbits = ppt * (uint32_t)kS;                 // hit bits per tile
+  const uint32_t hbits_magic = 0xFFFFFFFFu / hbits + 1u;     // floor(b / hbits) = umulhi(b, magic), b < 2^16
+  uint32_t hm_acc = 0;                                       // this lane's hit bits of the group
+  uint32_t grp_n = 0, grp_cnt = 0;                           // warp-uniform: tiles in the group, hits in the group
+  auto confirm_pass = [&](uint32_t e0, uint32_t n) {         // queue entries e0 .. e0 + n - 1, n <= 32
+    if (lane < n) {
+      const uint32_t ent = lds_u16(q_s + 2u * (e0 + lane));
+      const uint32_t b = ent >> 5, ln = ent & 31u;
+      const uint32_t jr = __umulhi(b, hbits_magic), bt = b - jr * hbits;  // tile (newest = 0), bit inside the tile
+      const uint32_t pr = bt / (uint32_t)kS, s = (uint32_t)(kS - 1) - (bt - pr * (uint32_t)kS);
+      const uint32_t row = (grp_n - 1u - jr) * ppt + (ppt - 1u - pr), w = 32u * s + ln;
+      const uint32_t a = pring_s + row * prs + 3u + w;  // code byte of word w - 1
+      const uint32_t a4 = a & ~3u;
+      const uint32_t ctx = __funnelshift_r(lds_u32(a4), lds_u32(a4 + 4u), (a & 3u) * 8u);  // bases 4 w - 4 .. 4 w + 11
+      const uint32_t b0 = w * 4u;
+      const uint32_t n_in = __umulhi(b0, len_magic), p0 = b0 - n_in * len;  // the read inside the period, the position
+      uint32_t *fh = shared_ptr<uint32_t>(fhit_s) + (row * P.k + n_in);
 #pragma unroll
-        for (uint32_t o = 1; o <= 4u; o++) {
-          const uint32_t h = (((ctx >> (2u * o)) & 0xFFFFFu) * kPBloomMul) >> 18;
-          pass |= (__funnelshift_r(lds_u32(bloom_s + ((h >> 5) << 2)), 0u, h) & 1u) << o;
-        }
-        if (pass) {  // 8 % of the entries on random bases: exact set, window inside one read, first-hit rule
-#pragma unroll
-          for (uint32_t o = 1; o <= 4u; o++) {
-            const uint32_t oo = 4u - o;  // window starts oo bases before the anchor
-            if ((pass >> o & 1u) && p0 >= oo && p0 - oo + 10u < len) {
-              const uint32_t key = (ctx >> (2u * o)) & 0xFFFFFu;
-              bool member;
-              if (args.ad.exact)
-                member = lds_u32(exact_s + exact_off1(key)) == key || lds_u32(exact_s + exact_off2(key)) == key;
-              else
-                member = (args.ad.bitmap[key >> 5] >> (key & 31u)) & 1u;
-              if (member) atomicMin(shared_ptr<uint32_t>(fhit_s) + n, p0 - oo + 9u);
-            }
-          }
+      for (uint32_t o = 1; o <= 4u; o++) {  // window o starts oo = 4 - o bases before the anchor
+        const uint32_t oo = 4u - o;
+        if (p0 >= oo && p0 - oo + 10u < len) {
+          const uint32_t key = (ctx >> (2u * o)) & 0xFFFFFu;
+          bool member;
+          if (args.ad.exact)
+            member = lds_u32(exact_s + exact_off1(key)) == key || lds_u32(exact_s + exact_off2(key)) == key;
+          else
+            member = (args.ad.bitmap[key >> 5] >> (key & 31u)) & 1u;
+          if (member) atomicMin(fh, p0 - oo + 9u);
         }
       }
     }
+  };
+  auto process_group = [&]() {
+    uint32_t m = hm_acc;
+    while (__any_sync(kFull, m != 0u)) {
+      // where this lane's entries go: exclusive prefix sum of the hit counts over the lanes
+      const uint32_t c = (uint32_t)__popc(m);
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFull, incl, d);
+        if (lane >= (uint32_t)d) incl += v;
+      }
+      const uint32_t total = __shfl_sync(kFull, incl, 31);
+      uint32_t off = incl - c;
+      while (m && off < kPQueue) {  // (a lane whose entries do not fit keeps their bits for the next round)
+        const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+        m &= m - 1u;
+        sts_u16(q_s + 2u * off, b << 5 | lane);
+        off++;
+      }
+      __syncwarp();
+      const uint32_t n = min(total, kPQueue);
+      for (uint32_t e0 = 0; e0 < n; e0 += 32u) confirm_pass(e0, min(32u, n - e0));
+      __syncwarp();
+    }
+    // first hits of the group's reads: kmer_count[p + 1]++ (quack.c:215-216)
+    for (uint32_t h = lane; h < grp_n * rpt; h += 32u) {
+      const uint32_t fa = fhit_s + 4u * h;
+      const uint32_t f = lds_u32(fa);
+      if (f != kNoHit) {
+        red_shared_add<0u>(kmerhist_s + (f + 1u) * 4u, 1u);
+        sts_u32(fa, kNoHit);
+      }
+    }
+    hm_acc = 0, grp_n = 0, grp_cnt = 0;
     __syncwarp();
   };
 
@@ -341,52 +378,57 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
       mbar_wait(wb_s + kPoBar + 8u * st, phase);
       const uint32_t seq_s = ring_s + 2u * st * buf + (aligned ? 0u : (uint32_t)(((size_t)tile * tb) & 15u));
       uint32_t hm = 0;  // -a: this lane's anchor hits of the tile, one bit per (period, step)
+      uint32_t pa = pring_s + grp_n * ppt * prs + 4u + w0;  // -a: this lane's first code byte in the period's ring row
+      uint32_t a0 = seq_s + w0 * 4u;                          // this lane's first word of the period
 
-      for (uint32_t pp = 0; pp < ppt; pp++) {
-        const uint32_t a0 = seq_s + pp * pbytes + lane * 4u;
-        uint32_t sw[kS], qw[kS], K[kS], nc[kS];
+      for (uint32_t pp = 0; pp < ppt; pp++, a0 += pbytes, pa += prs) {
+        uint32_t sw[kS], qw[kS], K[kS], nc[kS], cd[kS];
         uint32_t bad = 0;
 #pragma unroll
         for (int s = 0; s < kS; s++) {
-          const bool act = s < kS - 1 || lane < last;
+          const bool act = (uint32_t)s < nact;
           sw[s] = 0x41414141u;  // lanes without a word: 'A' with the lowest score, not counted
           qw[s] = kc.qsub;
           if (act) {
-            sw[s] = lds_u32(a0 + 128u * s);
-            qw[s] = lds_u32(a0 + buf + 128u * s);
+            sw[s] = lds_u32(a0 + 4u * kWs * s);
+            qw[s] = lds_u32(a0 + buf + 4u * kWs * s);
           }
         }
 #pragma unroll
-        for (int s = 0; s < kS; s++) K[s] = key_bytes(sw[s], qw[s], kc, nc[s], bad);
+        for (int s = 0; s < kS; s++) K[s] = kAd ? key_bytes_c(sw[s], qw[s], kc, nc[s], bad, cd[s]) : key_bytes(sw[s], qw[s], kc, nc[s], bad);
         if (bad & 0xC0C0C0C0u) {  // a quality byte outside the counted window: exact path for those words
 #pragma unroll
           for (int s = 0; s < kS; s++)
             if (word_bad(qw[s], kc.qsub)) {
               K[s] = key_bytes_bad(nc[s]);
-              n_invalid += p_exact_word(sw[s], qw[s], 4u * (32u * s + lane), len, args.a);
+              n_invalid += p_exact_word(sw[s], qw[s], 4u * (w0 + kWs * s), len, args.a);
             }
         }
         if (kAd) {
-          uint32_t gc[kS], r[kS];
-          hm <<= kS;
+          uint32_t gc[kS];
 #pragma unroll
-          for (int s = 0; s < kS; s++) gc[s] = (K[s] & 0x03030303u) * 0x01041040u;  // top byte: the word's 4 codes
+          for (int s = 0; s < kS; s++) gc[s] = cd[s] * 0x01041040u;  // top byte: the word's 4 codes
+          uint32_t nx[kS];  // codes of the word that follows word s
+          {
+            uint32_t r[kS];
 #pragma unroll
-          for (int s = 0; s < kS; s++) r[s] = __shfl_sync(kFull, gc[s], nxt);
+            for (int s = 0; s < kS; s++) r[s] = __shfl_sync(kFull, gc[s], nxt);
+#pragma unroll
+            for (int s = 0; s < kS; s++) nx[s] = lane < 31u ? r[s] : (s + 1 < kS ? r[s + 1] : 0u);
+          }
 #pragma unroll
           for (int s = 0; s < kS; s++) {
-            const bool act = s < kS - 1 || lane < last;
-            const uint32_t nx = lane < 31u ? r[s] : (s + 1 < kS ? r[s + 1] : 0u);  // codes of the next word
-            const uint32_t an = __byte_perm(gc[s], nx, 0x7773);  // bits 13:0 = the 7-mer starting at this word
+            const bool act = (uint32_t)s < nact;
+            const uint32_t an = __byte_perm(gc[s], nx[s], 0x7773);  // bits 13:0 = the 7-mer starting at this word
+            if (act) sts_u8(pa + kWs * s, an);                      // low byte: this word's codes, kept for the confirmation
             const uint32_t fw = lds_u32((an & 0x3FE0u) | afilt_or);
-            // bit (an & 31) of the filter word rotated to bit s of the hit mask
-            const uint32_t rot = __funnelshift_r(fw, fw, an - (uint32_t)s);
-            hm |= rot & ((s < kS - 1 || act) ? (1u << s) : 0u);
+            // the filter words are bit-reversed: bit (an & 31) arrives in bit 31 and is shifted into the hit mask
+            hm = __funnelshift_l(__funnelshift_l(0u, fw, an), hm, 1);
           }
         }
 #pragma unroll
         for (int s = 0; s < kS; s++) {
-          const bool act = s < kS - 1 || lane < last;
+          const bool act = (uint32_t)s < nact;
           if (act) {
             red_shared_add<0u>(__byte_perm(K[s], col[s][0], 0x7604), kOdd ? inc[kOdd ? s : 0][0] : inc_lo);
             red_shared_add<0u>(__byte_perm(K[s], col[s][1], 0x7614), kOdd ? inc[kOdd ? s : 0][1] : inc_hi);
@@ -397,45 +439,17 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
       }
 
       if (kAd) {
-        // queue this lane's anchor hits (bit (ppt - 1 - pp) kS + s <-> word pp wp + 32 s + lane of the tile) and
-        // confirm them, kPQueue at a time; a lane that finds the queue full keeps its bit for the next round
-        bool any = false;
-        while (__any_sync(kFull, hm != 0u)) {
-          any = true;
-          while (hm) {
-            const uint32_t idx = atomicAdd(shared_ptr<uint32_t>(qcount_s), 1u);
-            if (idx >= kPQueue) break;
-            const uint32_t b = (uint32_t)__ffs((int)hm) - 1u;
-            hm &= hm - 1u;
-            const uint32_t pr = b / (uint32_t)kS, s = b - pr * (uint32_t)kS;
-            sts_u16(q_s + 2u * idx, (ppt - 1u - pr) * wp + 32u * s + lane);
-          }
-          __syncwarp();
-          const uint32_t qn = min(lds_u32(qcount_s), kPQueue);
-          confirm(seq_s, qn);
-          if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(qcount_s), "r"(0u) : "memory");
-          __syncwarp();
-        }
-        if (any) {
-          // settle the first hits of the tile's reads: kmer_count[p + 1]++ (quack.c:215-216)
-#pragma unroll
-          for (uint32_t h = 0; h < kPMaxRpt; h += 32u) {  // reads_per_tile <= kPMaxRpt: two predicated rounds, no loop
-            const uint32_t n = h + lane;
-            if (n < rpt) {
-              const uint32_t f = lds_u32(fhit_s + 4u * n);
-              if (f != kNoHit) {
-                red_shared_add<0u>(kmerhist_s + (f + 1u) * 4u, 1u);
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(fhit_s + 4u * n), "r"(kNoHit) : "memory");
-              }
-            }
-          }
-          __syncwarp();
-        }
+        // the tile joins the group; the group is confirmed once it holds about a warp's worth of hits or is full
+        hm &= hm_valid;
+        hm_acc = (hbits >= 32u ? 0u : hm_acc << hbits) | hm;
+        grp_cnt += __reduce_add_sync(kFull, (uint32_t)__popc(hm));
+        if (++grp_n == rt || grp_cnt >= 24u) process_group();
       }
       if (++st == stages) st = 0, phase ^= 1u;
     }
     if (--to_flush == 0u && it + 1u < iters) {  // u16 counters: flush before any bin can wrap
       to_flush = epoch;
+      if (kAd && grp_n) process_group();
       __syncthreads();
       flush();
       __syncthreads();
@@ -443,6 +457,7 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
       __syncthreads();
     }
   }
+  if (kAd && grp_n) process_group();
   __syncthreads();
   flush();
 #pragma unroll
@@ -453,6 +468,21 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
 // ------------------------------------------------------------------------------------------
 // plan: period / tile geometry and shared-memory map
 // ------------------------------------------------------------------------------------------
+
+static void period_slots(const PeriodPlan &p, uint8_t *slot);
+
+// -a: can the packed-code rings live in the rows of histogram block 1?  Only the first kPHoleOff bytes of a row may
+// hold counters then: the counter layout (period_slots) puts the pairs that overflow block 0 into the lowest banks.
+static bool block1_leaves_holes(uint32_t l, uint32_t k, uint32_t wp, uint32_t steps) {
+  PeriodPlan q;
+  memset(&q, 0, sizeof q);
+  q.len = l, q.k = k, q.wp = wp, q.steps = steps, q.nblocks = 2;
+  uint8_t slot[kPeriodMaxLen];
+  period_slots(q, slot);
+  for (uint32_t pos = 0; pos < l; pos++)
+    if ((slot[pos] >> 7) && (slot[pos] & 63u) >= kPHoleOff / 4u) return false;
+  return true;
+}
 
 static PeriodPlan period_plan_w(uint32_t l, uint32_t first_offset, int adapters, int sm_count, uint32_t smem_optin,
                                 uint32_t smem_reserved, uint32_t qbase, uint32_t warps, bool full_tiles) {
@@ -490,7 +520,6 @@ static PeriodPlan period_plan_w(uint32_t l, uint32_t first_offset, int adapters,
     if (!(p.afilt_s = take(1, kAnchorSmemBytes)) || (p.afilt_s & (kAnchorSmemBytes - 1u))) return p;  // 16 KiB-aligned
     if (!(p.exact_s = take(2, kExactSlots * 4u))) return p;
     if (!(p.kmerhist_s = take(2, (l + 1u) * 4u))) return p;
-    if (!(p.bloom_s = take(2, kPBloomBits / 8u))) return p;
   }
   if (!(p.slot_s = take(0, kPeriodMaxLen))) return p;
   uint32_t want = 3, target = 1024u;
@@ -526,14 +555,43 @@ static PeriodPlan period_plan_w(uint32_t l, uint32_t first_offset, int adapters,
       if (ppt * wp > 65535u || ppt * ((wp + 31u) / 32u) > 32u) continue;
       if (full_tiles && ppt * pb < target && (ppt + ppt0) * bk <= kPMaxRpt) break;  // smaller tiles: only in the second round  // u16 queue entries, one hit bit per (period, step)
       for (uint32_t stages = want; stages >= 2u && !p.ok; stages--) {
-        const uint32_t wblock = pblock_hdr(adapters, ppt * bk) + stages * 2u * pbuf_bytes(ppt * pb);
-        uint32_t fit = 0;
-        for (int g = 0; g < 3; g++) fit += (gap[g].b - gap[g].a) / wblock;
-        if (fit < warps) continue;
-        p.k = bk, p.wp = wp, p.steps = (wp + 31u) / 32u;
-        p.ppt = ppt, p.tile_bytes = ppt * pb, p.reads_per_tile = ppt * bk;
-        p.stages = stages, p.wblock = wblock, p.buf_bytes = pbuf_bytes(ppt * pb);
-        p.ok = 1;
+        // -a: packed-code ring of rt tiles (one group of tiles whose anchor hits are confirmed together: as many as
+        // one register holds hit bits for, 4 at most, fewer if memory is short), in the unused columns of histogram
+        // block 1 when they are there (rows of 256 bytes, kPHoleOff of them counters), else inside the warp block
+        const uint32_t hbits = ppt * ((wp + 31u) / 32u);
+        uint32_t rt_max = adapters ? 32u / hbits : 1u;
+        if (rt_max > 4u) rt_max = 4u;
+        if (rt_max < 1u) rt_max = 1u;
+        for (uint32_t rt = rt_max; rt >= 1u && !p.ok; rt--) {
+          for (int holes = (adapters && p.nblocks == 2u) ? 1 : 0; holes >= 0 && !p.ok; holes--) {
+            uint32_t hdr = kPoQueue, prs = 0;
+            if (adapters) {
+              hdr = kPoFhit + ((rt * ppt * bk * 4u + 15u) & ~15u);
+              if (holes) {
+                prs = 256u;
+                if (4u + wp + 8u > kPHoleRowBytes || rt * ppt > kHistRows / warps || l > 128u + 2u * (kPHoleOff / 4u) ||
+                    !block1_leaves_holes(l, bk, wp, (wp + 31u) / 32u))
+                  continue;
+              } else {
+                prs = (4u + wp + 8u + 15u) & ~15u;
+                p.pring_off = hdr;
+                hdr += rt * ppt * prs;
+              }
+            }
+            const uint32_t wblock = hdr + stages * 2u * pbuf_bytes(ppt * pb);
+            uint32_t fit = 0;
+            for (int g = 0; g < 3; g++) fit += (gap[g].b - gap[g].a) / wblock;
+            if (fit < warps) continue;
+            p.k = bk, p.wp = wp, p.steps = (wp + 31u) / 32u;
+            p.ppt = ppt, p.tile_bytes = ppt * pb, p.reads_per_tile = ppt * bk;
+            p.stages = stages, p.wblock = wblock, p.buf_bytes = pbuf_bytes(ppt * pb);
+            p.hdr_bytes = hdr, p.rt = rt, p.prow_stride = prs;
+            p.pring_hole = holes ? kPHist0 + kPBlockStride + kPHoleOff : 0u;
+            p.pring_wstride = holes ? (kHistRows / warps) * 256u : 0u;
+            if (holes) p.pring_off = 0;
+            p.ok = 1;
+          }
+        }
       }
     }
     if (p.ok) break;
@@ -641,10 +699,9 @@ struct SlotSolver {
   }
 };
 
-struct SlotCache {  // the last table solved for each read length
+struct SlotCache {  // every table solved so far, by (read length, reads per period)
   std::mutex mu;
-  uint8_t slot[kPeriodMaxLen + 1][kPeriodMaxLen];
-  uint8_t k[kPeriodMaxLen + 1] = {};  // reads per period the table was solved for (0: none)
+  std::map<uint32_t, std::array<uint8_t, kPeriodMaxLen>> solved;
 };
 
 }  // namespace
@@ -659,8 +716,9 @@ static void period_slots(const PeriodPlan &p, uint8_t *slot) {
   if (getenv("QB_PT_NATURAL")) return;  // tuning hook
   static SlotCache *cache = new SlotCache();
   std::lock_guard<std::mutex> lk(cache->mu);
-  if (cache->k[l] == p.k) {
-    memcpy(slot, cache->slot[l], kPeriodMaxLen);
+  const uint32_t cache_key = l << 8 | p.k;
+  if (auto it = cache->solved.find(cache_key); it != cache->solved.end()) {
+    memcpy(slot, it->second.data(), kPeriodMaxLen);
     return;
   }
   SlotSolver sv;
@@ -702,6 +760,21 @@ static void period_slots(const PeriodPlan &p, uint8_t *slot) {
       if (sac > all) break;
     }
   }
+  // Bank labels are free (a step is conflict-free iff its lanes use DIFFERENT banks): the fullest banks get the
+  // lowest labels, so the pairs that overflow into block 1 sit in its first columns and the rest of every
+  // block-1 row stays free (the -a kernel keeps its packed-code rings there, see block1_leaves_holes).
+  {
+    uint32_t load[32] = {0}, order[32], label[32];
+    for (uint32_t e = 0; e < E; e++) load[best_bank[e] & 31u]++;
+    for (uint32_t b = 0; b < 32u; b++) order[b] = b;
+    for (uint32_t i = 1; i < 32u; i++)  // insertion sort by load, descending, stable
+      for (uint32_t j = i; j > 0 && load[order[j]] > load[order[j - 1]]; j--) {
+        const uint32_t t = order[j];
+        order[j] = order[j - 1], order[j - 1] = t;
+      }
+    for (uint32_t i = 0; i < 32u; i++) label[order[i]] = i;
+    for (uint32_t e = 0; e < E; e++) best_bank[e] = (uint8_t)label[best_bank[e] & 31u];
+  }
   // banks -> columns: the i-th even position of bank b takes column b (i = 0), b + 32 (1), then block 1
   uint32_t cnt[32] = {0};
   bool ok = true;
@@ -717,8 +790,7 @@ static void period_slots(const PeriodPlan &p, uint8_t *slot) {
       const uint32_t blk = pos >> 7, q = pos & 127u;
       slot[pos] = (uint8_t)(blk << 7 | ((q >> 2) + 32u * ((q >> 1) & 1u)));
     }
-  memcpy(cache->slot[l], slot, kPeriodMaxLen);
-  cache->k[l] = (uint8_t)p.k;
+  memcpy(cache->solved[cache_key].data(), slot, kPeriodMaxLen);
 }
 
 template <bool kAd, int kPW, bool kOdd, bool kAligned>
@@ -796,6 +868,15 @@ cudaError_t launch_period(const BatchView &b, const Accum &a, const AdapterSet &
 // B200 (227 KiB of shared memory per block, 1 KiB reserved).  Needs no GPU.  Returns 0 if the kernel takes
 // such batches, -1 otherwise.  info[0..6] = reads per period, words per period, steps, periods per tile,
 // reads per tile, stages, warps; slot[p] = block << 7 | u32 column of position p.
+extern "C" int qb_period_plan_info(uint32_t read_len, int adapters, uint32_t out[16]) {
+  const qb::PeriodPlan p = qb::period_plan(read_len, 0, adapters, 148, 232448u, 1024u, 33u);
+  if (!p.ok) return -1;
+  const uint32_t v[16] = {p.k, p.wp, p.steps, p.ppt, p.reads_per_tile, p.stages, p.warps, p.nblocks, p.wblock, p.hdr_bytes,
+                          p.rt, p.prow_stride, p.pring_hole, p.pring_wstride, p.pring_off, p.buf_bytes};
+  for (int i = 0; i < 16; i++) out[i] = v[i];
+  return 0;
+}
+
 extern "C" int qb_period_layout(uint32_t read_len, int adapters, uint32_t info[7], uint8_t slot[256]) {
   const qb::PeriodPlan p = qb::period_plan(read_len, 0, adapters, 148, 232448u, 1024u, 33u);
   if (!p.ok) return -1;

@@ -85,14 +85,17 @@ def test_period_layout_is_a_valid_counter_map(l, ad):
         assert (blk, col, p & 1) not in seen
         seen.add((blk, col, p & 1))
 
+    def word(s, i):     # the kernel's lane <-> word map
+        return 32 * s + i
+
     def wavefronts(bank_of):
         tot = 0
         for s in range(steps):
             for j in range(4):
                 c = {}
                 for i in range(32):
-                    if 32 * s + i < wp:
-                        b = bank_of((4 * (32 * s + i) + j) % l)
+                    if word(s, i) < wp:
+                        b = bank_of((4 * word(s, i) + j) % l)
                         c[b] = c.get(b, 0) + 1
                 tot += max(c.values())
         return tot

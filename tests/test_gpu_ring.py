@@ -193,10 +193,10 @@ def test_cli_truncated_input_is_reported(mate_files, tmp_path):
     cut = tmp_path / "cut.fq.gz"
     cut.write_bytes(data[: len(data) // 2])
     r = _run(["-u", str(cut)])
-    assert r.returncode == 0 and b"warning" in r.stderr and b"damaged or truncated" in r.stderr
+    # (the cut usually falls inside a record: the reader then sees a record without its quality line first, which the
+    # reference would count with stale quality bytes -- quack.c:203 -- so the two SVGs are not compared here)
+    assert r.returncode == 0 and b"warning" in r.stderr and b"records in front of it" in r.stderr
     assert r.stdout.startswith(b"<svg")
-    if po.have_ref():
-        assert r.stdout == po.ref_svg(["-u", str(cut)])
 
 
 # ------------------------------------------------------------------------------------------ long reads
