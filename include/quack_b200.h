@@ -50,14 +50,17 @@ typedef enum {
 } qb_status;
 
 typedef enum {
-  QB_KERNEL_AUTO = 0,      /* period kernel for batches of back-to-back reads of one length in [32, 256]; else the
-                              fused kernel up to 320 bp, the warp-tile kernel, or simple */
+  QB_KERNEL_AUTO = 0,      /* period kernel for batches of back-to-back reads of one length in [32, 256]; the flat
+                              kernel for other batches of back-to-back reads of 16..320 bp; else the fused kernel up
+                              to 320 bp, the warp-tile kernel, or simple */
   QB_KERNEL_SIMPLE = 1,    /* one warp per read, global atomics: any len_cap, slow */
   QB_KERNEL_FUSED = 2,     /* CTA-wide TMA-staged tiles, joint (base,score) shared-memory histogram (v3) */
   QB_KERNEL_WTILE = 3,     /* autonomous warps, each with its own TMA-staged tile ring (v4; reads <= 192 bp) */
-  QB_KERNEL_PERIOD = 4     /* v5: lanes own fixed positions of a k-read period, one aligned load + PRMT + RED per base;
+  QB_KERNEL_PERIOD = 4,    /* v5: lanes own fixed positions of a k-read period, one aligned load + PRMT + RED per base;
                               uniform-length batches only (an error otherwise), the reads that do not fill a tile
                               go to the AUTO choice among the others */
+  QB_KERNEL_FLAT = 5       /* v6: ragged batches of back-to-back reads of 16..320 bp, lane <-> 16-byte unit, read
+                              boundaries from a bit set per chunk (an error for other batches) */
 } qb_kernel;
 
 typedef struct qb_ctx qb_ctx;       /* one per process; owns devices, streams, accumulators */
@@ -159,6 +162,8 @@ uint64_t qb_launch_count(const qb_ctx *ctx);
 int qb_kernel_counts(const qb_ctx *ctx, uint64_t *n_simple, uint64_t *n_fused);
 /* How many launches took the period kernel (they are also counted in n_fused above). */
 uint64_t qb_period_launch_count(const qb_ctx *ctx);
+/* How many launches took the flat kernel (also counted in n_fused above). */
+uint64_t qb_flat_launch_count(const qb_ctx *ctx);
 /* Bytes queued for host-to-device copy by qb_submit() / qb_submit_from() / qb_accumulate_host() so far: bases +
  * quality bytes of every batch, plus offsets / lengths of the reads that do not take the period kernel (it needs
  * none: the host verified the batch shape).  bench.py reports e2e.h2d_bytes_per_step from this counter. */

@@ -13,7 +13,7 @@ from .build import lib_path
 
 ROW = 97
 COL_CONTENT, COL_LENGTH, COL_KMER = 91, 95, 96
-KERNEL_AUTO, KERNEL_SIMPLE, KERNEL_FUSED, KERNEL_WTILE, KERNEL_PERIOD = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_SIMPLE, KERNEL_FUSED, KERNEL_WTILE, KERNEL_PERIOD, KERNEL_FLAT = 0, 1, 2, 3, 4, 5
 NCCL_ID_BYTES = 128
 
 _u8p = C.POINTER(C.c_uint8)
@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
     L.qb_kernel_counts.argtypes = [vp, _u64p, _u64p]
     L.qb_period_launch_count.argtypes = [vp]
     L.qb_period_launch_count.restype = C.c_uint64
+    L.qb_flat_launch_count.argtypes = [vp]
+    L.qb_flat_launch_count.restype = C.c_uint64
     L.qb_h2d_bytes.argtypes = [vp]
     L.qb_h2d_bytes.restype = C.c_uint64
     L.qb_profile_enable.argtypes = [vp, C.c_int]
@@ -309,6 +311,11 @@ class Context:
     def h2d_bytes(self) -> int:
         """Bytes queued for host-to-device copy by the submit calls so far."""
         return int(lib().qb_h2d_bytes(self.h))
+
+    @property
+    def flat_launch_count(self) -> int:
+        """Launches that took the flat kernel (ragged batches of back-to-back reads)."""
+        return int(lib().qb_flat_launch_count(self.h))
 
     @property
     def period_launch_count(self) -> int:

@@ -111,7 +111,7 @@ struct qb_ctx {
   uint64_t next_slot = 0, submit_seq = 0;
   std::mutex err_mu;
   std::string err;
-  std::atomic<uint64_t> launches{0}, launches_fused{0}, launches_simple{0}, launches_period{0};
+  std::atomic<uint64_t> launches{0}, launches_fused{0}, launches_simple{0}, launches_period{0}, launches_flat{0};
   std::atomic<uint64_t> h2d_bytes{0};  // bytes queued for host-to-device copy by qb_submit*() so far
   // The accumulators hold cur_cap rows, not cfg.len_cap: they start small and grow (grow_accumulators) when a
   // batch announces a longer read, so a context opened for 2^20-bp reads costs nothing until one shows up.
@@ -141,7 +141,7 @@ struct qb_dbatch {
   uint32_t n_reads;
   uint64_t n_bytes;
   uint32_t max_len;
-  uint32_t uniform_len, first_offset;  // see qb::BatchView
+  uint32_t uniform_len, first_offset, contig_min_len;  // see qb::BatchView
 };
 
 namespace {
@@ -195,15 +195,26 @@ qb::Accum accum(const qb_ctx *ctx, const Device &d, int mate) {
   return a;
 }
 
-// Host-side check of the batch shape the period kernel needs: every read has the same length and the reads
-// lie back to back.  Returns that length (0: ragged) -- one vectorisable pass over the two u32 arrays.
-uint32_t detect_uniform(const uint32_t *offset, const uint32_t *length, uint32_t n_reads, uint32_t *first_offset) {
+// Host-side look at the batch shape, one vectorisable pass over the two u32 arrays: do the reads lie back to back
+// (then *contig_min = the shortest read's length, else 0; the flat kernel needs that), and do they all have the same
+// length (returned; 0: ragged -- the period kernel needs that).  *longest = the longest read.
+uint32_t detect_shape(const uint32_t *offset, const uint32_t *length, uint32_t n_reads, uint32_t *first_offset,
+                      uint32_t *contig_min, uint32_t *longest) {
+  *contig_min = 0, *longest = 0, *first_offset = 0;
   if (n_reads == 0) return 0;
   const uint32_t l = length[0], o0 = offset[0];
-  uint32_t diff = 0;
-  for (uint32_t r = 0; r < n_reads; r++) diff |= (length[r] ^ l) | (offset[r] ^ (o0 + r * l));
+  uint32_t diff = 0, gaps = 0, mn = 0xFFFFFFFFu, mx = 0;
+  for (uint32_t r = 0; r < n_reads; r++) {
+    const uint32_t lr = length[r];
+    diff |= lr ^ l;
+    mn = lr < mn ? lr : mn;
+    mx = lr > mx ? lr : mx;
+  }
+  for (uint32_t r = 0; r + 1 < n_reads; r++) gaps |= (offset[r] + length[r]) ^ offset[r + 1];
   *first_offset = o0;
-  return diff ? 0u : l;
+  *longest = mx;
+  *contig_min = gaps ? 0u : mn;
+  return (diff || gaps) ? 0u : l;
 }
 
 // one launch of the v4 / v3 / simple kernel on a batch view
@@ -211,6 +222,23 @@ int launch_other(qb_ctx *ctx, Device &d, const qb::BatchView &v, qb::Accum ac, c
                  cudaStream_t stream) {
   qb::FusedPlan plan{};
   qb::WtilePlan wplan{};
+  if (kernel == QB_KERNEL_AUTO || kernel == QB_KERNEL_FLAT) {
+    // ragged batches of back-to-back reads: the flat kernel (lane <-> 16-byte unit) when the batch has its shape
+    qb::FlatPlan fp{};
+    if (v.contig_min_len >= 16u && !(v.first_offset & 15u) && v.tiles && v.n_bytes < 0xFFFFFF00ull && !getenv("QB_NO_FLAT"))
+      fp = qb::flat_plan(v.max_len && v.max_len < ctx->cur_cap ? v.max_len : ctx->cur_cap, v.contig_min_len, ad.enabled,
+                         d.sm_count, (uint32_t)d.smem_optin, ctx->qbase);
+    if (fp.ok) {
+      ctx->launches++;
+      ctx->launches_fused++;
+      ctx->launches_flat++;
+      const cudaError_t e = qb::launch_flat(v, ac, ad, fp, stream);
+      if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+      return QB_OK;
+    }
+    if (kernel == QB_KERNEL_FLAT)
+      return fail(ctx, QB_ERR_CAPACITY, "the flat kernel needs a batch of back-to-back reads of 16..320 bp that starts on a 16-byte boundary");
+  }
   if (kernel != QB_KERNEL_SIMPLE) {
     // The shared-memory histogram is sized by the longest read of THIS batch (the caller's max_len
     // promise; a longer read is counted as an error and fails qb_finish), not by len_cap: a context
@@ -366,6 +394,10 @@ int launch_batch_locked(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate
     rest.offset += n_main;
     rest.length += n_main;
     rest.n_reads -= n_main;
+    if (n_main) {  // the reads behind the period kernel's tiles: still back to back, one length
+      rest.first_offset = v.first_offset + n_main * v.uniform_len;
+      rest.n_bytes = (uint64_t)rest.n_reads * v.uniform_len;
+    }
     rc = launch_other(ctx, d, rest, ac, ad, kernel, stream);
   }
   if (e1) cudaEventRecord(e1, stream);
@@ -476,6 +508,7 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
         QB_CREATE_CUDA(qb::fused_configure());
         QB_CREATE_CUDA(qb::wtile_configure());
         QB_CREATE_CUDA(qb::period_configure());
+        QB_CREATE_CUDA(qb::flat_configure());
         if (d.id < 256) configured[d.id] = true;
       }
     }
@@ -682,8 +715,13 @@ static int submit_queue(qb_ctx *ctx, int di, int si, int mate, const uint8_t *se
       QB_CUDA(ctx, cudaMemcpyAsync(s.d_qual, qual, n_bytes, cudaMemcpyHostToDevice, s.stream));
     }
     qb::BatchView v{s.d_seq, s.d_qual, s.d_off, s.d_len, n_reads, n_bytes, max_len ? max_len : ctx->cfg.len_cap, s.d_tiles};
-    if (ctx->cfg.kernel == QB_KERNEL_AUTO || ctx->cfg.kernel == QB_KERNEL_PERIOD)
-      v.uniform_len = detect_uniform(offset, length, n_reads, &v.first_offset);
+    if (ctx->cfg.kernel == QB_KERNEL_AUTO || ctx->cfg.kernel == QB_KERNEL_PERIOD || ctx->cfg.kernel == QB_KERNEL_FLAT) {
+      uint32_t longest = 0;
+      v.uniform_len = detect_shape(offset, length, n_reads, &v.first_offset, &v.contig_min_len, &longest);
+      if (longest > v.max_len) v.contig_min_len = 0;  // a longer read than promised: the kernels that check every
+                                                      // read's length take the batch and fail it loudly
+      if (longest && longest < v.max_len) v.max_len = longest;
+    }
     // The period kernel needs no offsets / lengths on the device (the host just verified the batch shape): only
     // those of the reads it leaves to the other kernels (< reads_per_tile at the end of the batch) are copied.
     uint32_t r0 = 0;
@@ -934,6 +972,7 @@ int qb_kernel_counts(const qb_ctx *ctx, uint64_t *n_simple, uint64_t *n_fused) {
 }
 
 uint64_t qb_period_launch_count(const qb_ctx *ctx) { return ctx ? ctx->launches_period.load() : 0; }
+uint64_t qb_flat_launch_count(const qb_ctx *ctx) { return ctx ? ctx->launches_flat.load() : 0; }
 uint64_t qb_h2d_bytes(const qb_ctx *ctx) { return ctx ? ctx->h2d_bytes.load() : 0; }
 
 int qb_profile_enable(qb_ctx *ctx, int max_launches) {
@@ -1037,7 +1076,9 @@ int qb_dbatch_upload(qb_ctx *ctx, int device_index, const uint8_t *seq, const ui
   if (n_reads) {
     QB_CUDA(ctx, cudaMemcpy(b->d_off, offset, (size_t)n_reads * 4, cudaMemcpyHostToDevice));
     QB_CUDA(ctx, cudaMemcpy(b->d_len, length, (size_t)n_reads * 4, cudaMemcpyHostToDevice));
-    b->uniform_len = detect_uniform(offset, length, n_reads, &b->first_offset);
+    uint32_t longest = 0;
+    b->uniform_len = detect_shape(offset, length, n_reads, &b->first_offset, &b->contig_min_len, &longest);
+    if (longest > b->max_len) b->contig_min_len = 0;  // (see submit_queue)
   }
   *out = b;
   return QB_OK;
@@ -1048,7 +1089,12 @@ int qb_dbatch_generate(qb_ctx *ctx, int device_index, uint64_t seed, int mate, u
   if (!ctx || !out || len_min == 0 || len_max < len_min) return QB_ERR_ARG;
   // lengths first (they fix the byte count), then generate in host chunks and upload
   uint64_t total = 0;
-  for (uint32_t r = 0; r < n_reads; r++) total += qb::gen_length(seed, first_read + r, len_min, len_max);
+  uint32_t shortest = 0xFFFFFFFFu;
+  for (uint32_t r = 0; r < n_reads; r++) {
+    const uint32_t l = qb::gen_length(seed, first_read + r, len_min, len_max);
+    total += l;
+    shortest = l < shortest ? l : shortest;
+  }
   qb_dbatch *b = nullptr;
   int rc = dbatch_alloc(ctx, device_index, n_reads, total, &b);
   if (rc) return rc;
@@ -1062,15 +1108,17 @@ int qb_dbatch_generate(qb_ctx *ctx, int device_index, uint64_t seed, int mate, u
     return fail(ctx, QB_ERR_NOMEM, "pinned staging allocation failed");
   }
   uint64_t base = 0;
-  bool uniform = len_min == len_max;  // the generator packs reads back to back
+  bool uniform = len_min == len_max, contiguous = true;  // the generator packs reads back to back
   for (uint32_t r0 = 0; r0 < n_reads && rc == QB_OK; r0 += chunk) {
     const uint32_t n = n_reads - r0 < chunk ? n_reads - r0 : chunk;
     uint64_t nb = 0;
     rc = qb_gen_reads(seed, mate, first_read + r0, n, len_min, len_max, adapter_rate, hs, hq, ho, hl, &nb);
     if (rc) break;
     for (uint32_t i = 0; i < n; i++) ho[i] += (uint32_t)base;
-    uint32_t fo = 0;
-    if (uniform && (detect_uniform(ho, hl, n, &fo) != len_min || fo != (uint32_t)base)) uniform = false;
+    uint32_t fo = 0, cm = 0, lg = 0;
+    const uint32_t ul = detect_shape(ho, hl, n, &fo, &cm, &lg);
+    if (uniform && (ul != len_min || fo != (uint32_t)base)) uniform = false;
+    if (!cm || fo != (uint32_t)base) contiguous = false;  // (the generator packs reads back to back)
     if (cudaMemcpy(b->d_seq + base, hs, nb, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(b->d_qual + base, hq, nb, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(b->d_off + r0, ho, (size_t)n * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -1084,6 +1132,7 @@ int qb_dbatch_generate(qb_ctx *ctx, int device_index, uint64_t seed, int mate, u
     return rc;
   }
   b->uniform_len = uniform && n_reads ? len_min : 0u;
+  b->contig_min_len = contiguous && n_reads ? shortest : 0u;
   b->first_offset = 0;
   *out = b;
   return QB_OK;
@@ -1114,7 +1163,7 @@ int qb_dbatch_run(qb_ctx *ctx, qb_dbatch *b, int mate) {
   Device &d = ctx->dev[b->device_index];
   QB_CUDA(ctx, cudaSetDevice(d.id));
   qb::BatchView v{b->d_seq, b->d_qual, b->d_off, b->d_len, b->n_reads, b->n_bytes, b->max_len, b->d_tiles,
-                  b->uniform_len, b->first_offset};
+                  b->uniform_len, b->first_offset, b->contig_min_len};
   return launch_batch(ctx, d, v, mate, d.main_stream);
 }
 

@@ -82,6 +82,24 @@ __device__ __forceinline__ void bulk_g2s_s(uint32_t dst_s, const void *src, uint
                "l"(src), "r"(bytes), "r"(bar_s)
                : "memory");
 }
+// 16-byte asynchronous copy global -> shared that bypasses L1 and the register file (SASS: LDGSTS.E.BYPASS.128);
+// completion through cp.async.commit_group / wait_group of the issuing thread
+__device__ __forceinline__ void cp_async16(uint32_t dst_s, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_s), "l"(src) : "memory");
+}
+// two of them (bases and quality bytes of a tile) under one predicate, at a compile-time offset from the operands
+template <int kOff>
+__device__ __forceinline__ void cp_async16_pair(bool p, uint32_t dst_a, uint32_t dst_b, const void *src_a, const void *src_b) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.u32 q, %0, 0;\n"
+      "@q cp.async.cg.shared.global [%1+%5], [%3+%5], 16;\n"
+      "@q cp.async.cg.shared.global [%2+%5], [%4+%5], 16;\n"
+      "}\n" ::"r"((uint32_t)p),
+      "r"(dst_a), "r"(dst_b), "l"(src_a), "l"(src_b), "n"(kOff)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));

@@ -57,7 +57,9 @@ struct BatchView {
   uint2 *tiles;            // scratch of n_reads entries: tile descriptors written by the warp-tile kernel's first pass
   uint32_t uniform_len;    // != 0: the HOST verified that every read has this length and that the reads lie back to
                            // back (offset[r] = offset[0] + r * uniform_len); 0: unknown / ragged
-  uint32_t first_offset;   // offset[0] of a uniform batch
+  uint32_t first_offset;   // offset[0] of a uniform / contiguous batch
+  uint32_t contig_min_len; // != 0: the HOST verified that the reads lie back to back (offset[r + 1] = offset[r] +
+                           // length[r]); the value is the shortest read's length.  0: unknown / gaps between reads
 };
 
 struct Accum {
@@ -150,6 +152,23 @@ PeriodPlan period_plan(uint32_t uniform_len, uint32_t first_offset, int adapters
 cudaError_t launch_period(const BatchView &b, const Accum &a, const AdapterSet &ad, const PeriodPlan &plan,
                           cudaStream_t stream, uint32_t *n_main_out);
 cudaError_t period_configure();
+
+// ---- flat kernel geometry (qb_flat.cu; ragged batches of back-to-back reads of 16..320 bp) --------
+struct FlatPlan {
+  uint32_t max_len;          // longest read of the batch (histogram positions 0 .. max_len + 2)
+  uint32_t stride;           // 32-bit columns per histogram row, a multiple of 32
+  uint32_t chunk_bytes;      // byte window that defines a chunk of reads (one warp at a time)
+  uint32_t epoch;            // rounds between two flushes of the u16 counters
+  uint32_t hist_o, lenhist_o, kmerhist_o, afilt_o, exact_o, wblock_o, wblock;  // offsets in dynamic shared memory
+  uint32_t qbase;
+  uint32_t smem_bytes;
+  uint32_t grid;
+  int ok;                    // 0: not a batch for this kernel
+};
+FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters, int sm_count, uint32_t smem_optin,
+                   uint32_t qbase);
+cudaError_t launch_flat(const BatchView &b, const Accum &a, const AdapterSet &ad, const FlatPlan &plan, cudaStream_t stream);
+cudaError_t flat_configure();
 
 FusedPlan fused_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int sm_count,
                      uint32_t smem_optin, uint32_t qbase);

@@ -36,6 +36,19 @@
 
 namespace qb {
 
+// How a warp stages its tiles.  TMA: one 1-D bulk copy per array (cp.async.bulk, SASS UBLKCP) on an mbarrier, issued
+// by one lane -- ~60 warp instructions per tile, the operands go through an elect / R2UR loop each.  cp.async:
+// per-lane 16-byte asynchronous copies (SASS LDGSTS), 3 + 3 warp instructions for the 1200 + 1200 bytes of an
+// 8 x 150 bp tile plus their predicates, completion through the lane's own copy groups -- ~50 per tile.  Measured
+// (profiles/r02/staging_ab.jsonl, 16 M reads of 150 bp): without adapters TMA 0.904 / cp.async 0.889 of the HBM
+// roofline, with -a 0.499 / 0.507: each variant takes its winner.  -DQB_PT_TMA=0|1 forces one for both.
+#ifdef QB_PT_TMA
+template <bool kAd>
+constexpr bool kPTmaFor = QB_PT_TMA != 0;
+#else
+template <bool kAd>
+constexpr bool kPTmaFor = !kAd;
+#endif
 constexpr uint32_t kPHist0 = 0x10000u;             // shared address of histogram block 0
 constexpr uint32_t kPBlockStride = 0x10000u;       // block b at kPHist0 + b * 64 KiB (its address has byte 1 == 0)
 constexpr uint32_t kPBlockBytes = kHistRows * 256u;  // 192 rows x 256 B = 48 KiB
@@ -104,6 +117,7 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 template <bool kAd, int kS, int kPW, bool kOdd, bool kAligned>
 __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_constant__ PArgs args) {
   constexpr uint32_t kPThreads = kPW * 32;
+  constexpr bool kPTma = kPTmaFor<kAd>;
   extern __shared__ __align__(128) uint8_t smem[];
   const PeriodPlan &P = args.plan;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -259,26 +273,67 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
     }
   };
 
-  // Start the bulk copies of tile t into stage s.  The whole warp calls this once it is done with the stage.
-  auto issue = [&](uint32_t s, uint32_t t) {
+  // Start the copies of tile t into stage s (have = false: past the end of the batch -- with cp.async still an
+  // (empty) copy group, so that "all but the newest stages - 1 groups are complete" always means "tile t arrived").
+  // The whole warp calls this once it is done with the stage.
+  auto issue = [&](uint32_t s, uint32_t t, bool have) {
     __syncwarp();  // every lane is done with the buffer's old contents
-    if (lane == 0) {
-      const uint32_t bar_s = wb_s + kPoBar + 8u * s;
-      const uint32_t dst = ring_s + 2u * s * buf;
-      const size_t off = (size_t)t * tb;
-      // the TMA (async proxy) write must be ordered behind the generic-proxy accesses to the buffer
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      if (aligned) {
-        mbar_arrive_expect_tx_s(bar_s, 2u * tb);
-        bulk_g2s_s(dst, args.seq + off, tb, bar_s);
-        bulk_g2s_s(dst + buf, args.qual + off, tb, bar_s);
-      } else {
-        const uint32_t so = (uint32_t)(off & 15u);       // the copy starts at the 16-byte boundary below the tile
-        const uint32_t bytes = (so + tb + 15u) & ~15u;   // (the batch buffers are readable 64 bytes past their end)
-        mbar_arrive_expect_tx_s(bar_s, 2u * bytes);
-        bulk_g2s_s(dst, args.seq + (off - so), bytes, bar_s);
-        bulk_g2s_s(dst + buf, args.qual + (off - so), bytes, bar_s);
+    if (kPTma) {
+      if (have && lane == 0) {
+        const uint32_t bar_s = wb_s + kPoBar + 8u * s;
+        const uint32_t dst = ring_s + 2u * s * buf;
+        const size_t off = (size_t)t * tb;
+        // the TMA (async proxy) write must be ordered behind the generic-proxy accesses to the buffer
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (aligned) {
+          mbar_arrive_expect_tx_s(bar_s, 2u * tb);
+          bulk_g2s_s(dst, args.seq + off, tb, bar_s);
+          bulk_g2s_s(dst + buf, args.qual + off, tb, bar_s);
+        } else {
+          const uint32_t so = (uint32_t)(off & 15u);       // the copy starts at the 16-byte boundary below the tile
+          const uint32_t bytes = (so + tb + 15u) & ~15u;   // (the batch buffers are readable 64 bytes past their end)
+          mbar_arrive_expect_tx_s(bar_s, 2u * bytes);
+          bulk_g2s_s(dst, args.seq + (off - so), bytes, bar_s);
+          bulk_g2s_s(dst + buf, args.qual + (off - so), bytes, bar_s);
+        }
       }
+    } else {
+      if (have) {
+        size_t off = (size_t)t * tb;
+        uint32_t bytes = tb;
+        if (!aligned) {  // from the 16-byte boundary below the tile (the batch buffers are readable 64 bytes past their end)
+          const uint32_t so = (uint32_t)(off & 15u);
+          off -= so;
+          bytes = (so + tb + 15u) & ~15u;
+        }
+        const uint32_t lo = lane * 16u;
+        const uint32_t dst = ring_s + 2u * s * buf + lo;
+        const uint8_t *gs = args.seq + off + lo, *gq = args.qual + off + lo;
+        // round i copies bytes [512 i, 512 i + 512) of both arrays, 16 per lane: one predicate per round, the
+        // addresses are the two pointers above plus immediates
+        cp_async16_pair<0>(lo < bytes, dst, dst + buf, gs, gq);
+        cp_async16_pair<512>(lo + 512u < bytes, dst, dst + buf, gs, gq);
+        cp_async16_pair<1024>(lo + 1024u < bytes, dst, dst + buf, gs, gq);
+        if (bytes > 1536u) {  // (warp-uniform)
+          cp_async16_pair<1536>(lo + 1536u < bytes, dst, dst + buf, gs, gq);
+          cp_async16_pair<2048>(lo + 2048u < bytes, dst, dst + buf, gs, gq);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  };
+  // tile in stage s arrived: the mbarrier's phase flipped / this lane's copy group is complete, then the warp syncs
+  auto arrived = [&](uint32_t s, uint32_t phase) {
+    if (kPTma) {
+      mbar_wait(wb_s + kPoBar + 8u * s, phase);
+    } else {
+      if (stages == 2u)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else if (stages == 3u)
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+      else
+        asm volatile("cp.async.wait_group 3;" ::: "memory");
+      __syncwarp();
     }
   };
 
@@ -362,8 +417,7 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
   };
 
   const uint32_t g = g0 + warp;
-  for (uint32_t s = 0; s + 1u < stages; s++)
-    if (g + s * G < n_tiles) issue(s, g + s * G);
+  for (uint32_t s = 0; s + 1u < stages; s++) issue(s, g + s * G, g + s * G < n_tiles);
 
   uint32_t to_flush = epoch;
   uint32_t tile = g;
@@ -373,9 +427,9 @@ __global__ void __launch_bounds__(kPW * 32, 1) period_kernel(const __grid_consta
       {  // keep stages - 1 tiles in flight: the stage freed by the previous iteration takes tile + (stages - 1) G
         const uint32_t t2 = tile + (stages - 1u) * G;
         const uint32_t s2 = st == 0 ? stages - 1u : st - 1u;
-        if (t2 < n_tiles) issue(s2, t2);
+        issue(s2, t2, t2 < n_tiles);
       }
-      mbar_wait(wb_s + kPoBar + 8u * st, phase);
+      arrived(st, phase);
       const uint32_t seq_s = ring_s + 2u * st * buf + (aligned ? 0u : (uint32_t)(((size_t)tile * tb) & 15u));
       uint32_t hm = 0;  // -a: this lane's anchor hits of the tile, one bit per (period, step)
       uint32_t pa = pring_s + grp_n * ppt * prs + 4u + w0;  // -a: this lane's first code byte in the period's ring row
@@ -552,7 +606,7 @@ static PeriodPlan period_plan_w(uint32_t l, uint32_t first_offset, int adapters,
     uint32_t ppt = ppt0;
     while (ppt * pb < target && (ppt + ppt0) * bk <= kPMaxRpt) ppt += ppt0;
     for (; ppt >= ppt0 && !p.ok; ppt -= ppt0) {
-      if (ppt * wp > 65535u || ppt * ((wp + 31u) / 32u) > 32u) continue;
+      if (ppt * wp > 65535u || ppt * ((wp + 31u) / 32u) > 32u || pbuf_bytes(ppt * pb) > 2560u) continue;
       if (full_tiles && ppt * pb < target && (ppt + ppt0) * bk <= kPMaxRpt) break;  // smaller tiles: only in the second round  // u16 queue entries, one hit bit per (period, step)
       for (uint32_t stages = want; stages >= 2u && !p.ok; stages--) {
         // -a: packed-code ring of rt tiles (one group of tiles whose anchor hits are confirmed together: as many as

@@ -104,6 +104,114 @@ def test_period_rejects_ragged(keys):
         run_gpu(batch, 150, keys, capi.KERNEL_PERIOD)
 
 
+# ---- flat kernel (v6): ragged batches of back-to-back reads of 16..320 bp ----
+FLAT_SHAPES = [(35, 300, 304), (16, 40, 40), (16, 320, 320), (100, 151, 151), (150, 150, 150), (17, 17, 64), (299, 304, 304),
+               (64, 64, 64), (48, 96, 96)]
+
+
+@pytest.mark.parametrize("lmin,lmax,cap", FLAT_SHAPES)
+@pytest.mark.parametrize("ad", [False, True], ids=["noad", "ad"])
+@pytest.mark.parametrize("resident", [False, True], ids=["stream", "resident"])
+def test_flat_ragged(lmin, lmax, cap, ad, resident, table, keys):
+    """Every read-length mix the flat kernel takes: reads that start at every byte phase of a 16-byte unit and of a
+    32-bit word (straddling words), chunk boundaries inside units, planted adapters, N bases."""
+    batch = util.random_batch(7000 + lmin * 400 + lmax, 30011, lmin, lmax, plant=0.3)
+    got = run_gpu(batch, cap, keys if ad else None, capi.KERNEL_FLAT, resident=resident)
+    util.assert_same(got, po.accumulate_batch(*batch, table if ad else None), f"flat {lmin}-{lmax}")
+
+
+@pytest.mark.parametrize("chunk", ["512", "1000", "2048"])
+def test_flat_small_chunks(chunk, monkeypatch, table, keys):
+    """Small byte windows: many chunk boundaries, chunks of one or two reads, reads longer than half a window."""
+    monkeypatch.setenv("QB_FLAT_CHUNK", chunk)
+    for lmin, lmax in ((35, 300), (16, 60), (280, 304)):
+        batch = util.random_batch(int(chunk) + lmin, 20000, lmin, lmax, plant=0.3)
+        got = run_gpu(batch, 304, keys, capi.KERNEL_FLAT, resident=True)
+        util.assert_same(got, po.accumulate_batch(*batch, table), f"flat chunk {chunk} {lmin}-{lmax}")
+
+
+def test_flat_tiny_batches(table, keys):
+    for n in (1, 2, 3, 31, 33, 100):
+        batch = util.random_batch(n, n, 16, 304, plant=0.5)
+        got = run_gpu(batch, 304, keys, capi.KERNEL_FLAT)
+        util.assert_same(got, po.accumulate_batch(*batch, table), f"flat n={n}")
+
+
+def test_flat_all_byte_values_and_score_ranges(table, keys):
+    rng = np.random.default_rng(15)
+    lens = rng.integers(16, 200, size=5000).astype(np.uint32)
+    off = np.zeros(len(lens), dtype=np.uint32)
+    off[1:] = np.cumsum(lens[:-1], dtype=np.uint64).astype(np.uint32)
+    total = int(lens.sum())
+    seq = rng.integers(0, 256, size=total).astype(np.uint8)
+    qual = rng.integers(0, 256, size=total).astype(np.uint8)
+    want = po.accumulate_batch(seq, qual, off, lens, table)
+    got = run_gpu((seq, qual, off, lens), 200, keys, capi.KERNEL_FLAT)
+    util.assert_same(got, want, "flat all bytes")
+    assert got.invalid == want.n_invalid_qual > 0
+    for qlo, qhi in ((0, 90), (31, 71), (44, 49), (60, 62)):
+        batch = util.random_batch(78, 8000, 40, 151, qlo=qlo, qhi=qhi, plant=0.2)
+        util.assert_same(run_gpu(batch, 151, keys, capi.KERNEL_FLAT), po.accumulate_batch(*batch, table), f"flat scores {qlo}-{qhi}")
+
+
+def test_flat_adapter_first_hit_every_position(table, keys):
+    """The first-hit rule with the adapter planted at every position of reads of three lengths, a second adapter
+    further down (only the first may count), hits that end on the last base, windows that would span two reads."""
+    ad = b"AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT"
+    reads = []
+    for l in (30, 61, 150):
+        for at in range(0, l):
+            s = bytearray(b"C" * l)
+            m = min(len(ad), l - at)
+            s[at: at + m] = ad[:m]
+            if at + 51 <= l:
+                s[at + 40: at + 40 + 11] = ad[:11]
+            reads.append((bytes(s), b"I" * l))
+    reads.append((b"CCCCCCCCCCCCGATCGGAAGA", b"I" * 22))       # hit ends on the last base
+    reads.append((b"GATCGGAAGACCCCCC", b"I" * 16))             # a window that starts in the read in front must not count
+    reads.append((b"CCCCCCCCCCCGATCG", b"I" * 16))
+    reads.append((b"GAAGACCCCCCCCCCC", b"I" * 16))
+    batch = util.pack(reads)
+    util.assert_same(run_gpu(batch, 150, keys, capi.KERNEL_FLAT), po.accumulate_batch(*batch, table), "flat first hit")
+    dimers = [(ad[:30] * 5, b"I" * 150)] * 400                 # every anchor hits: the hit queue overflows and is drained in rounds
+    batch = util.pack(dimers)
+    util.assert_same(run_gpu(batch, 150, keys, capi.KERNEL_FLAT), po.accumulate_batch(*batch, table), "flat dimers")
+
+
+def test_flat_u16_flush(monkeypatch, table, keys):
+    monkeypatch.setenv("QB_FUSED_GRID", "2")
+    batch = util.random_batch(32, 300000, 30, 50, plant=0.05)
+    got = run_gpu(batch, 64, keys, capi.KERNEL_FLAT, resident=True)
+    util.assert_same(got, po.accumulate_batch(*batch, table), "flat flush")
+
+
+def test_flat_rejects_other_batches(keys):
+    with pytest.raises(capi.QbError):     # reads shorter than a 16-byte unit
+        run_gpu(util.random_batch(3, 100, 5, 40), 64, keys, capi.KERNEL_FLAT)
+    seq, qual, off, lens = util.random_batch(4, 100, 50, 60)
+    off = off.copy()
+    off[50:] += 7                          # a gap between two reads
+    pad = np.zeros(7, dtype=np.uint8)
+    seq = np.concatenate([seq[: off[50] - 7], pad, seq[off[50] - 7:]])
+    qual = np.concatenate([qual[: off[50] - 7], pad + 40, qual[off[50] - 7:]])
+    with pytest.raises(capi.QbError):
+        run_gpu((seq, qual, off, lens), 64, keys, capi.KERNEL_FLAT)
+    with capi.Context(64, adapter_keys=keys) as ctx:   # AUTO still counts it (fused kernel), bit-exactly
+        ctx.accumulate_host(0, seq, qual, off, lens)
+        got = ctx.finish(0)
+        assert ctx.flat_launch_count == 0
+    util.assert_same(got, po.accumulate_batch(seq, qual, off, lens, util.oracle_table()), "gap batch, auto")
+
+
+def test_auto_takes_the_flat_kernel_for_ragged_batches(table, keys):
+    batch = util.random_batch(5, 50000, 35, 300, plant=0.1)
+    with capi.Context(304, adapter_keys=keys) as ctx:
+        ctx.accumulate_host(0, *batch)
+        got = ctx.finish(0)
+        assert ctx.flat_launch_count >= 1 and ctx.period_launch_count == 0
+    util.assert_same(got, po.accumulate_batch(*batch, table), "auto ragged")
+
+
 WTILE_MAX_LEN = 192   # the warp-tile kernel's shared-memory histogram; longer batches take the fused kernel
 
 
