@@ -227,7 +227,7 @@ int launch_other(qb_ctx *ctx, Device &d, const qb::BatchView &v, qb::Accum ac, c
     qb::FlatPlan fp{};
     if (v.contig_min_len >= 16u && !(v.first_offset & 15u) && v.tiles && v.n_bytes < 0xFFFFFF00ull && !getenv("QB_NO_FLAT"))
       fp = qb::flat_plan(v.max_len && v.max_len < ctx->cur_cap ? v.max_len : ctx->cur_cap, v.contig_min_len, ad.enabled,
-                         d.sm_count, (uint32_t)d.smem_optin, ctx->qbase);
+                         d.sm_count, (uint32_t)d.smem_optin, (uint32_t)d.smem_reserved, ctx->qbase);
     if (fp.ok) {
       ctx->launches++;
       ctx->launches_fused++;

@@ -5,23 +5,21 @@
 // (0.31 / 0.15 of the HBM roofline without / with -a).  Here nothing is per read in the hot loop:
 //   * the batch is cut into CHUNKS of whole reads by byte windows (chunk c = the reads that START in bytes
 //     [c CB, (c + 1) CB); a one-pass index kernel finds each window's first read), one warp per chunk at a time;
-//   * a warp walks its chunk flat, lane <-> aligned 16-byte unit: two coalesced 16-byte vector loads per lane
-//     (512 contiguous bytes of bases and of quality bytes per warp instruction) straight into registers -- no
-//     staging ring, so the shared memory goes to the histogram and 16-24 warps fit;
-//   * which read a unit belongs to comes from a bit set of read starts per chunk (one bit per unit: a popcount of
+//   * a warp walks its chunk flat, lane <-> aligned 32-bit word, 32 consecutive words per step: coalesced loads of
+//     128 contiguous bytes of bases and of quality bytes straight into registers, four steps ahead of their use --
+//     no staging ring, so the shared memory goes to the histogram;
+//   * which read a word belongs to comes from a bit set of read starts per chunk (one bit per word: a popcount of
 //     the bits below the lane's gives the read, two loads its start and the next read's): ~10 instructions per
-//     16 bases instead of a search per word; a word inside the unit switches to the next read by one compare;
+//     step instead of a search;
 //   * histogram: the joint (score, code) x position table of the other kernels (key byte K = score << 2 | code,
 //     u16 counters, even positions in the low half of a 32-bit column, odd ones in the high half) with rows of
-//     `stride` 32-bit columns, a multiple of 32 so that the bank depends on the position only, and one spare column
-//     per 32 (column = pair + pair / 32): lanes are 16 bases = 8 columns apart, which would fall into 4 banks; the
-//     skew spreads 32 lanes of one read over 32 banks;
+//     `stride` 32-bit columns, a multiple of 32 so that the bank depends on the position only;
 //   * a word that straddles two reads is counted as if it belonged to the first one (positions len .. len + 2) and
 //     put right per read boundary afterwards (<= 3 bytes: subtract there, add at positions 0 .. 2 of the next read);
-//   * -a: the 2-bit codes of a unit are packed into one 32-bit value (kept in a per-chunk array for the
-//     confirmation), four 7-mer anchors per unit are probed (the one that starts in the previous unit's last word
-//     with one shuffle), hits are one bit per anchor in a register, expanded with a warp prefix sum at the end of
-//     the chunk and confirmed 32 at a time against the exact key set, one lane per hit (as in qb_period.cu).
+//   * -a: one 7-mer anchor per word is probed as in qb_period.cu (the anchor that starts at the PREVIOUS word: its
+//     codes come from the lane below with one shuffle), the codes of (previous word, word) are kept as one u16 per
+//     word for the confirmation, hits are one bit per step in a register, expanded with a warp prefix sum at the
+//     end of the chunk and confirmed 32 at a time against the exact key set, one lane per hit.
 // Read counts, the length histogram (shared memory) and the first-hit settling are per chunk, lanes over reads.
 //
 // No tensor cores: the path is an integer histogram.
@@ -34,15 +32,15 @@
 namespace qb {
 
 constexpr uint32_t kFMaxReads = 256;   // reads per chunk (reads >= 16 bp, a chunk spans <= 4096 bytes)
-constexpr uint32_t kFMaxIter = 8;      // 32 units of 16 bytes per iteration
+constexpr uint32_t kFMaxSteps = 32;    // 32 words per step: 1024 words = 4096 bytes per chunk at most
 constexpr uint32_t kFQueue = 64;
 // per-warp block (bytes, multiples of 16)
-constexpr uint32_t kFoRoff = 0;                              // u32 roff[-1 .. kFMaxReads + 1]: read starts, chunk-relative
-constexpr uint32_t kFoS = kFoRoff + (kFMaxReads + 4u) * 4u;  // u32 S[9]: bit per unit, set where a new read is current
-constexpr uint32_t kFoSpre = kFoS + 48u;                     // u32 Spre[9]: popcount of the words below
-constexpr uint32_t kFWarpBytesNoAd = kFoSpre + 48u;
-constexpr uint32_t kFoP = kFWarpBytesNoAd;                   // -a: u8 P[4 + words of the chunk + 8]: packed 2-bit codes
-constexpr uint32_t kFoFhit = kFoP + 4u + kFMaxIter * 32u * 4u + 12u;  // -a: u32 fhit[kFMaxReads]
+constexpr uint32_t kFoRoff = 0;                              // u32 roff[-1 .. kFMaxReads + 2]: read starts, chunk-relative
+constexpr uint32_t kFoS = kFoRoff + (kFMaxReads + 4u) * 4u;  // u32 S[34]: bit per word, set where a new read is current
+constexpr uint32_t kFoSpre = kFoS + 144u;                    // u32 Spre[34]: popcount of the words below
+constexpr uint32_t kFWarpBytesNoAd = kFoSpre + 144u;
+constexpr uint32_t kFoP = kFWarpBytesNoAd;                   // -a: u16 P[-1 .. 1026]: codes of (word - 1, word), 2 bits per base
+constexpr uint32_t kFoFhit = kFoP + 16u + kFMaxSteps * 32u * 2u + 16u;  // -a: u32 fhit[kFMaxReads]
 constexpr uint32_t kFoQ = kFoFhit + kFMaxReads * 4u;         // -a: u16 queue[kFQueue]
 constexpr uint32_t kFWarpBytesAd = kFoQ + kFQueue * 2u;
 
@@ -87,8 +85,13 @@ __device__ __forceinline__ uint32_t f_lds_u16(uint32_t addr) {
   asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
   return v;
 }
-// shared address of the 32-bit column that holds positions 2 q and 2 q + 1: one spare column per 32
-__device__ __forceinline__ uint32_t f_col(uint32_t hist_s, uint32_t q) { return hist_s + 4u * (q + (q >> 5)); }
+// shared address of the 32-bit column that holds positions 2 q and 2 q + 1
+__device__ __forceinline__ uint32_t f_col(uint32_t hist_s, uint32_t q) { return hist_s + 4u * q; }
+__device__ __forceinline__ uint32_t ldg_u32(const uint8_t *p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 
 template <bool kAd, int kW>
 __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant__ FArgs args) {
@@ -100,6 +103,10 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
   const uint32_t smem_s = smem_u32(smem);
   auto gen = [&](uint32_t shared_addr) -> uint8_t * { return smem + (shared_addr - smem_s); };
 
+  if (smem_s != P.smem_base) {  // the anchor map must sit at a 16 KiB-aligned shared address: fail loudly, count nothing
+    if (tid == 0) atomicAdd(&args.a.counters[kCntError], 1ull);
+    return;
+  }
   const uint32_t hist_s = smem_s + P.hist_o, lenhist_s = smem_s + P.lenhist_o, kmerhist_s = smem_s + P.kmerhist_o;
   const uint32_t afilt_s = smem_s + P.afilt_o, exact_s = smem_s + P.exact_o;
   const uint32_t wb_s = smem_s + P.wblock_o + warp * P.wblock;
@@ -182,114 +189,121 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
       nr = args.chunk_first[c + 1u] - first;
     }
     if (nr) {  // (warp-uniform)
-      // ---- the chunk's reads: starts relative to the 16-byte boundary below the first one ----
+      // ---- the chunk's reads: starts relative to the 32-bit boundary below the first one ----
       const uint32_t b_start = args.offset[first];
-      const uint32_t ub0 = b_start & ~15u;  // absolute byte of unit 0
+      const uint32_t ub0 = b_start & ~3u;  // absolute byte of word 0
       __syncwarp();
       for (uint32_t i = lane; i <= nr + 1u; i += 32u) {
         const uint32_t gidx = first + i;
-        const uint32_t o = gidx < args.n_reads ? args.offset[gidx] : (gidx == args.n_reads ? args.batch_end : 0xFFFFFFF0u);
+        const uint32_t o = gidx < args.n_reads ? args.offset[gidx] : args.batch_end;
         f_sts_u32(roff_s + 4u * i, gidx <= args.n_reads ? o - ub0 : 0xFFFFFF00u);
       }
       if (lane == 0) f_sts_u32(roff_s - 4u, 0u);
-      if (lane < 9u) f_sts_u32(S_s + 4u * lane, 0u);
+      for (uint32_t i = lane; i < 34u; i += 32u) f_sts_u32(S_s + 4u * i, 0u);
       __syncwarp();
-      for (uint32_t i = lane; i <= nr; i += 32u) {  // bit v: from unit v on, read i is the current one
-        const uint32_t v = (lds_u32(roff_s + 4u * i) + 15u) >> 4;
-        if (v < 9u * 32u) atomicOr(shared_ptr<uint32_t>(S_s) + (v >> 5), 1u << (v & 31u));
+      for (uint32_t i = lane; i <= nr; i += 32u) {  // bit w: from word w on, read i is the current one
+        const uint32_t w = (lds_u32(roff_s + 4u * i) + 3u) >> 2;
+        if (w < 34u * 32u) atomicOr(shared_ptr<uint32_t>(S_s) + (w >> 5), 1u << (w & 31u));
       }
       __syncwarp();
       const uint32_t end_rel = lds_u32(roff_s + 4u * nr);  // start of the read behind the chunk / end of the batch
-      const uint32_t V = (end_rel + 15u) >> 4;             // units whose first byte lies in front of it
-      const uint32_t nit = (V + 31u) >> 5;
+      const uint32_t Wn = (end_rel + 3u) >> 2;             // words whose first byte lies in front of it
+      const uint32_t nst = (Wn + 31u) >> 5;
       const bool last_has_next = first + nr < args.n_reads;  // does the read behind the chunk exist?
-      if (kAd && lane < 9u) {  // popcounts of the words below (read lookup at confirmation time)
-        uint32_t acc = 0;
-        for (uint32_t j = 0; j < lane; j++) acc += (uint32_t)__popc(lds_u32(S_s + 4u * j));
-        f_sts_u32(Spre_s + 4u * lane, acc);
+      if (kAd) {  // popcounts of the words below (read lookup at confirmation time): a warp prefix sum
+        const uint32_t cw = (uint32_t)__popc(lds_u32(S_s + 4u * lane));
+        uint32_t incl = cw;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t vv = __shfl_up_sync(kFull, incl, d);
+          if (lane >= (uint32_t)d) incl += vv;
+        }
+        f_sts_u32(Spre_s + 4u * lane, incl - cw);
+        if (lane == 31) {
+          f_sts_u32(Spre_s + 4u * 32u, incl);
+          f_sts_u32(Spre_s + 4u * 33u, incl + (uint32_t)__popc(lds_u32(S_s + 4u * 32u)));
+        }
       }
       const uint32_t roff0 = lds_u32(roff_s);
 
-      // ---- flat pass: lane <-> 16-byte unit ----
-      const uint8_t *gs = args.seq + ub0 + lane * 16u, *gq = args.qual + ub0 + lane * 16u;
-      uint32_t run = 0;        // reads current in front of this iteration's units
-      uint32_t hm = 0;         // -a: 4 hit bits per iteration, the newest in the low bits
-      uint32_t carry = 0;      // -a: codes of the previous iteration's last unit
-      for (uint32_t it = 0; it < nit; it++, gs += 512, gq += 512) {
-        const uint32_t v = 32u * it + lane;
-        const bool have = v < V;
-        uint4 s4 = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u), q4 = make_uint4(kc.qsub, kc.qsub, kc.qsub, kc.qsub);
-        if (have) {
-          s4 = ldg_u128(gs);
-          q4 = ldg_u128(gq);
+      // ---- flat pass: lane <-> word, groups of four steps whose loads are issued one group ahead ----
+      const uint8_t *gs = args.seq + ub0 + lane * 4u, *gq = args.qual + ub0 + lane * 4u;
+      uint32_t run = 0;        // reads current in front of this step's words
+      uint32_t hm = 0;         // -a: one hit bit per step, the newest in the low bits
+      uint32_t carry = 0;      // -a: codes of the previous step's last word
+      uint32_t ns[4], nq[4];   // the group in flight
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const bool hv = 32u * (uint32_t)u + lane < Wn;
+        ns[u] = hv ? ldg_u32(gs + 128 * u) : 0x41414141u;
+        nq[u] = hv ? ldg_u32(gq + 128 * u) : kc.qsub;
+      }
+      for (uint32_t st0 = 0; st0 < nst; st0 += 4u) {
+        uint32_t cs[4], cq[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) cs[u] = ns[u], cq[u] = nq[u];
+        gs += 512, gq += 512;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {  // (lanes without a word: 'A' with the lowest score, not counted)
+          const bool hv = 32u * (st0 + 4u + (uint32_t)u) + lane < Wn;
+          ns[u] = hv ? ldg_u32(gs + 128 * u) : 0x41414141u;
+          nq[u] = hv ? ldg_u32(gq + 128 * u) : kc.qsub;
         }
-        const uint32_t Sw = lds_u32(S_s + 4u * it);
-        const int r = (int)(run + (uint32_t)__popc(Sw & le_mask)) - 1;  // read of the unit's first byte (-1: the one in front)
-        run += (uint32_t)__popc(Sw);
-        const uint32_t B = 16u * v;
-        const uint32_t rs = lds_u32(roff_s + 4u * (uint32_t)r), rn = lds_u32(roff_s + 4u * (uint32_t)r + 4u);
-        const uint32_t pos0 = B - rs;   // position of the unit's first byte in read r
-        const uint32_t e = rn - B;      // bytes of the unit that belong to read r (>= 16: all)
-        const bool cnt = have && B >= roff0;                       // units in front of the first own read: scan only
-        const bool next_ok = (uint32_t)(r + 1) < nr || last_has_next;  // read r + 1 exists
-        const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w}, qw[4] = {q4.x, q4.y, q4.z, q4.w};
-        uint32_t K[4], nc[4], cd[4], bad = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) K[k] = kAd ? key_bytes_c(sw[k], qw[k], kc, nc[k], bad, cd[k]) : key_bytes(sw[k], qw[k], kc, nc[k], bad);
-        if (bad & 0xC0C0C0C0u) {  // a quality byte outside the counted window: those words byte by byte, exactly
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            if (word_bad(qw[k], kc.qsub)) {
-              K[k] = key_bytes_bad(nc[k]);
-              if (cnt)
+        for (int u = 0; u < 4; u++) {
+          const uint32_t st = st0 + (uint32_t)u;
+          if (st < nst) {  // (warp-uniform)
+            const uint32_t w = 32u * st + lane;
+            const bool have = w < Wn;
+            const uint32_t Sw = lds_u32(S_s + 4u * st);
+            const int r = (int)(run + (uint32_t)__popc(Sw & le_mask)) - 1;  // read of the word's first byte (-1: the one in front)
+            run += (uint32_t)__popc(Sw);
+            const uint32_t B = 4u * w;
+            const uint32_t rs = lds_u32(roff_s + 4u * (uint32_t)r), rn = lds_u32(roff_s + 4u * (uint32_t)r + 4u);
+            const uint32_t pos0 = B - rs;   // position of the word's first byte in read r
+            const uint32_t e = rn - B;      // bytes of the word that belong to read r (>= 4: all)
+            const bool cnt = have && B >= roff0;  // the word in front of the first own read: scan only
+            const uint32_t sw = cs[u], qw = cq[u];
+            uint32_t nc, cd = 0, bad = 0;
+            uint32_t K = kAd ? key_bytes_c(sw, qw, kc, nc, bad, cd) : key_bytes(sw, qw, kc, nc, bad);
+            if (bad & 0xC0C0C0C0u) {  // a quality byte outside the counted window: the word byte by byte, exactly
+              K = key_bytes_bad(nc);
+              if (cnt) {
+                const bool next_ok = (uint32_t)(r + 1) < nr || last_has_next;  // read r + 1 exists
                 for (uint32_t j = 0; j < 4u; j++) {
-                  const uint32_t ob = 4u * k + j;
-                  const bool in_b = ob >= e;
+                  const bool in_b = j >= e;
                   if (in_b && !next_ok) continue;
-                  const uint32_t p = in_b ? ob - e : pos0 + ob;
+                  const uint32_t p = in_b ? j - e : pos0 + j;
                   unsigned long long *row = args.a.rows + (size_t)p * kRow;
-                  atomicAdd(&row[kColContent + base_code((sw[k] >> (8u * j)) & 0xFFu)], 1ull);
-                  const int sc = (int)((qw[k] >> (8u * j)) & 0xFFu) - 33;
+                  atomicAdd(&row[kColContent + base_code((sw >> (8u * j)) & 0xFFu)], 1ull);
+                  const int sc = (int)((qw >> (8u * j)) & 0xFFu) - 33;
                   if (sc >= 0 && sc < 91)
                     atomicAdd(&row[sc], 1ull);
                   else
                     n_invalid++;
                 }
+              }
             }
-        }
-        if (kAd) {
-          // the unit's 16 codes as one value (first base in the low bits), kept for the confirmation
-          const uint32_t g0c = cd[0] * 0x01041040u, g1c = cd[1] * 0x01041040u, g2c = cd[2] * 0x01041040u, g3c = cd[3] * 0x01041040u;
-          const uint32_t P32 = __byte_perm(__byte_perm(g0c, g1c, 0x0073), __byte_perm(g2c, g3c, 0x0073), 0x5410);
-          if (have) f_sts_u32(P_s + 4u + 4u * v, P32);
-          uint32_t prev = __shfl_up_sync(kFull, P32, 1);
-          if (lane == 0) prev = carry;
-          carry = __shfl_sync(kFull, P32, 31);
-          // anchors: the 7-mer that starts at the previous unit's last word, then at words 0, 1, 2 of this unit
-          const uint32_t an[4] = {__funnelshift_r(prev, P32, 24), P32, P32 >> 8, P32 >> 16};
-#pragma unroll
-          for (int t = 0; t < 4; t++) {
-            const uint32_t fw = lds_u32((an[t] & 0x3FE0u) | afilt_or);
-            hm = __funnelshift_l(__funnelshift_l(0u, fw, an[t]), hm, 1);
-          }
-          if (!have) hm &= ~15u;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const bool use_b = 4u * (uint32_t)k >= e;  // the word starts in read r + 1
-          const uint32_t pos = use_b ? 4u * (uint32_t)k - e : pos0 + 4u * (uint32_t)k;
-          const uint32_t q = pos >> 1, t = q & 31u;
-          const bool odd = pos & 1u;
-          const uint32_t A0 = f_col(hist_s, q);
-          const uint32_t A1 = A0 + (t == 31u ? 8u : 4u);
-          const uint32_t A2 = A1 + (t == 30u ? 8u : 4u);
-          const uint32_t X1 = odd ? A1 : A0, X3 = odd ? A2 : A1;
-          const uint32_t i0 = odd ? inc_hi : inc_lo, i1 = odd ? inc_lo : inc_hi;
-          if (cnt && (!use_b || next_ok)) {
-            red_shared_add<0u>(__byte_perm(K[k], 0u, 0x4440) * rowbytes + A0, i0);
-            red_shared_add<0u>(__byte_perm(K[k], 0u, 0x4441) * rowbytes + X1, i1);
-            red_shared_add<0u>(__byte_perm(K[k], 0u, 0x4442) * rowbytes + A1, i0);
-            red_shared_add<0u>((K[k] >> 24) * rowbytes + X3, i1);
+            if (kAd) {
+              const uint32_t gc = cd * 0x01041040u;  // top byte: the word's 4 codes
+              uint32_t prev = __shfl_up_sync(kFull, gc, 1);
+              if (lane == 0) prev = carry;
+              carry = __shfl_sync(kFull, gc, 31);
+              const uint32_t an = __byte_perm(prev, gc, 0x7773);  // bits 13:0 = the 7-mer that starts at the word in front
+              if (have) f_sts_u16(P_s + 16u + 2u * w, an);        // codes of (word - 1, word), kept for the confirmation
+              const uint32_t fw = lds_u32((an & 0x3FE0u) | afilt_or);
+              hm = __funnelshift_l(__funnelshift_l(0u, fw, an), hm, 1);
+              if (!have) hm &= ~1u;
+            }
+            const uint32_t odd = pos0 & 1u;
+            const uint32_t A0 = hist_s + 4u * (pos0 >> 1), Ao = A0 + 4u * odd;
+            const uint32_t i0 = odd ? inc_hi : inc_lo, i1 = odd ? inc_lo : inc_hi;
+            if (cnt) {
+              red_shared_add<0u>(__byte_perm(K, 0u, 0x4440) * rowbytes + A0, i0);
+              red_shared_add<0u>(__byte_perm(K, 0u, 0x4441) * rowbytes + Ao, i1);
+              red_shared_add<4u>(__byte_perm(K, 0u, 0x4442) * rowbytes + A0, i0);
+              red_shared_add<4u>((K >> 24) * rowbytes + Ao, i1);
+            }
           }
         }
       }
@@ -357,20 +371,19 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
             if (e0 + lane < n) {
               const uint32_t ent = f_lds_u16(q_s + 2u * (e0 + lane));
               const uint32_t b = ent >> 5, ln = ent & 31u;
-              const uint32_t it = nit - 1u - (b >> 2), sub = 3u - (b & 3u);
-              const int w = (int)(4u * (32u * it + ln) + sub) - 1;  // chunk-relative word whose 7-mer passed the filter
-              const uint32_t a = P_s + 3u + (uint32_t)w;            // code byte of word w - 1
-              const uint32_t a4 = a & ~3u;
-              const uint32_t ctx = __funnelshift_r(lds_u32(a4), lds_u32(a4 + 4u), (a & 3u) * 8u);  // bases 4 w - 4 .. 4 w + 11
+              const int w = (int)(32u * (nst - 1u - b) + ln) - 1;  // chunk-relative word whose 7-mer passed the filter
+              // codes of words w - 1 .. w + 2 (bases 4 w - 4 .. 4 w + 11): the u16 of word w and of word w + 2
+              const uint32_t ctx = f_lds_u16(P_s + 16u + 2u * (uint32_t)w) | f_lds_u16(P_s + 16u + 2u * (uint32_t)w + 4u) << 16;
               const int ws0 = 4 * w - 3;  // first byte of the first of the four windows
-              // read of that byte (of byte 0 if it lies in front of the chunk's units)
-              const uint32_t vb = (uint32_t)(ws0 < 0 ? 0 : ws0) >> 4;
+              // read of the first byte of the word that holds it (of word 0 if it lies in front of the chunk)
+              const uint32_t vb = (uint32_t)(ws0 < 0 ? 0 : ws0) >> 2;
               int ra = (int)(lds_u32(Spre_s + 4u * (vb >> 5)) + (uint32_t)__popc(lds_u32(S_s + 4u * (vb >> 5)) & (0xFFFFFFFFu >> (31u - (vb & 31u))))) - 1;
               const uint32_t r1 = lds_u32(roff_s + 4u * (uint32_t)ra + 4u), r2 = lds_u32(roff_s + 4u * (uint32_t)ra + 8u);
-              if (ws0 >= 0 && (uint32_t)ws0 >= r1) ra++;  // (the unit's first byte was still in the read in front)
-              const uint32_t s_a = ws0 >= 0 && (uint32_t)ws0 >= r1 ? r1 : lds_u32(roff_s + 4u * (uint32_t)ra);  // start of read ra
-              const uint32_t e_a = ws0 >= 0 && (uint32_t)ws0 >= r1 ? r2 : r1;                                    // start of read ra + 1
-              const uint32_t e_b = lds_u32(roff_s + 4u * (uint32_t)ra + 8u);                                     // start of read ra + 2
+              const bool in_next = ws0 >= 0 && (uint32_t)ws0 >= r1;  // (the word's first byte was still in the read in front)
+              const uint32_t s_a = in_next ? r1 : lds_u32(roff_s + 4u * (uint32_t)ra);  // start of the read of byte ws0
+              const uint32_t e_a = in_next ? r2 : r1;                                    // start of the read behind it
+              if (in_next) ra++;
+              const uint32_t e_b = lds_u32(roff_s + 4u * (uint32_t)ra + 8u);            // and of the one behind that
 #pragma unroll
               for (uint32_t o = 1; o <= 4u; o++) {  // window o starts 4 - o bytes in front of the anchor
                 const int ws = 4 * w - (int)(4u - o);
@@ -429,21 +442,26 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
 // plan and launch
 // ------------------------------------------------------------------------------------------
 
+// warps per CTA: without -a a warp block is 1.4 KiB and the kernel needs 75 registers -> 24 warps; with -a the
+// packed codes, first hits and queue make it 4.5 KiB (and 90 registers) -> 16 warps
 #ifndef QB_FW
-#define QB_FW 16
+#define QB_FW 24
 #endif
-constexpr int kFlatWarps = QB_FW;
+#ifndef QB_FW_AD
+#define QB_FW_AD 16
+#endif
+constexpr int kFlatWarpsNoAd = QB_FW, kFlatWarpsAd = QB_FW_AD;
 
 FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters, int sm_count, uint32_t smem_optin,
-                   uint32_t qbase) {
+                   uint32_t smem_reserved, uint32_t qbase) {
   FlatPlan p;
   memset(&p, 0, sizeof p);
   if (batch_min_len < 16u || batch_max_len < batch_min_len || batch_max_len > 320u) return p;
   p.max_len = batch_max_len;
   p.qbase = qbase;
-  const uint32_t pairs = (batch_max_len + 3u + 1u) / 2u;       // positions 0 .. max_len + 2 (straddling words)
-  const uint32_t ncols = pairs + (pairs >> 5) + 1u;
-  p.stride = (ncols + 31u) & ~31u;
+  const uint32_t pairs = (batch_max_len + 3u + 1u) / 2u + 1u;  // positions 0 .. max_len + 2 (straddling words)
+  p.stride = (pairs + 31u) & ~31u;
+  p.smem_base = smem_reserved;
   uint32_t o = 0;
   auto take = [&](uint32_t bytes) {
     const uint32_t at = o;
@@ -453,19 +471,19 @@ FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters,
   p.hist_o = take(kHistRows * p.stride * 4u);
   p.lenhist_o = take((batch_max_len + 1u) * 4u);
   p.kmerhist_o = take(adapters ? (batch_max_len + 2u) * 4u : 0u);
-  p.afilt_o = take(adapters ? kAnchorSmemBytes : 0u);
-  if (adapters && (p.afilt_o & (kAnchorSmemBytes - 1u))) {  // the probe address is `anchor bits | base`: 16 KiB-aligned
-    o = (p.afilt_o + kAnchorSmemBytes - 1u) & ~(kAnchorSmemBytes - 1u);
+  if (adapters) {  // the probe address is `anchor bits | base`: the SHARED ADDRESS of the map is 16 KiB-aligned
+    o = ((smem_reserved + o + kAnchorSmemBytes - 1u) & ~(kAnchorSmemBytes - 1u)) - smem_reserved;
     p.afilt_o = take(kAnchorSmemBytes);
   }
   p.exact_o = take(adapters ? kExactSlots * 4u : 0u);
   p.wblock = adapters ? kFWarpBytesAd : kFWarpBytesNoAd;
   p.wblock = (p.wblock + 127u) & ~127u;
-  p.wblock_o = take(p.wblock * (uint32_t)kFlatWarps);
+  const uint32_t warps = (uint32_t)(adapters ? kFlatWarpsAd : kFlatWarpsNoAd);
+  p.wblock_o = take(p.wblock * warps);
   p.smem_bytes = o;
   if (p.smem_bytes > smem_optin) return p;
-  // a chunk spans its byte window plus the tail of its last read, in 8 iterations of 512 bytes at most
-  uint32_t cb = kFMaxIter * 512u - ((batch_max_len + 32u + 15u) & ~15u);
+  // a chunk spans its byte window plus the tail of its last read, in 32 steps of 128 bytes at most
+  uint32_t cb = (kFMaxSteps * 128u - batch_max_len - 8u) & ~63u;
   if (const char *e = getenv("QB_FLAT_CHUNK")) {  // tuning hook
     const uint32_t v = (uint32_t)atoi(e);
     if (v >= 512u && v < cb) cb = v;
@@ -473,7 +491,7 @@ FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters,
   p.chunk_bytes = cb;
   const uint32_t reads_per_chunk = cb / batch_min_len + 2u;
   if (reads_per_chunk + 2u > kFMaxReads) return p;
-  p.epoch = 30000u / ((uint32_t)kFlatWarps * reads_per_chunk);
+  p.epoch = 30000u / (warps * reads_per_chunk);
   if (p.epoch == 0) p.epoch = 1;
   p.grid = (uint32_t)sm_count;
   p.ok = 1;
@@ -482,8 +500,8 @@ FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters,
 
 cudaError_t flat_configure() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(flat_kernel<false, kFlatWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
-  return cudaFuncSetAttribute(flat_kernel<true, kFlatWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if ((e = cudaFuncSetAttribute(flat_kernel<false, kFlatWarpsNoAd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+  return cudaFuncSetAttribute(flat_kernel<true, kFlatWarpsAd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
 }
 
 cudaError_t launch_flat(const BatchView &b, const Accum &a, const AdapterSet &ad, const FlatPlan &plan, cudaStream_t stream) {
@@ -508,7 +526,8 @@ cudaError_t launch_flat(const BatchView &b, const Accum &a, const AdapterSet &ad
                                                                   args.n_chunks, chunk_first);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  uint32_t grid = (args.n_chunks + (uint32_t)kFlatWarps - 1u) / (uint32_t)kFlatWarps;
+  const uint32_t warps = (uint32_t)(ad.enabled ? kFlatWarpsAd : kFlatWarpsNoAd);
+  uint32_t grid = (args.n_chunks + warps - 1u) / warps;
   if (grid > plan.grid) grid = plan.grid;
   if (grid == 0) grid = 1;
   if (const char *g = getenv("QB_FUSED_GRID")) {  // test hook: few CTAs exercise the u16 flush path
@@ -516,9 +535,9 @@ cudaError_t launch_flat(const BatchView &b, const Accum &a, const AdapterSet &ad
     if (v >= 1 && v < grid) grid = v;
   }
   if (ad.enabled)
-    flat_kernel<true, kFlatWarps><<<grid, kFlatWarps * 32, plan.smem_bytes, stream>>>(args);
+    flat_kernel<true, kFlatWarpsAd><<<grid, kFlatWarpsAd * 32, plan.smem_bytes, stream>>>(args);
   else
-    flat_kernel<false, kFlatWarps><<<grid, kFlatWarps * 32, plan.smem_bytes, stream>>>(args);
+    flat_kernel<false, kFlatWarpsNoAd><<<grid, kFlatWarpsNoAd * 32, plan.smem_bytes, stream>>>(args);
   return cudaGetLastError();
 }
 

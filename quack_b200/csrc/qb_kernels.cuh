@@ -161,12 +161,13 @@ struct FlatPlan {
   uint32_t epoch;            // rounds between two flushes of the u16 counters
   uint32_t hist_o, lenhist_o, kmerhist_o, afilt_o, exact_o, wblock_o, wblock;  // offsets in dynamic shared memory
   uint32_t qbase;
+  uint32_t smem_base;        // shared address the dynamic shared memory must start at (checked by the kernel)
   uint32_t smem_bytes;
   uint32_t grid;
   int ok;                    // 0: not a batch for this kernel
 };
 FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters, int sm_count, uint32_t smem_optin,
-                   uint32_t qbase);
+                   uint32_t smem_reserved, uint32_t qbase);
 cudaError_t launch_flat(const BatchView &b, const Accum &a, const AdapterSet &ad, const FlatPlan &plan, cudaStream_t stream);
 cudaError_t flat_configure();
 

@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <fcntl.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
@@ -60,9 +61,62 @@ typedef struct {
   long long switch_off;  /* err -6: file offset of the member the serial zlib path continues from */
 } bgzf_pool;
 
+/* ---- multi-member gzip pool ----
+ * An ordinary .gz file may be a concatenation of gzip members (RFC 1952 section 2.2; what `cat a.gz b.gz`, pigz -i,
+ * and the benchmark generator write; gzread() -- the reference, quack.c:187 -- decodes them back to back).  Members
+ * are independent deflate streams, so they can be inflated in parallel once their starts are known.  They are not
+ * marked in any index: the pool SPECULATES.  A scanner looks for byte strings that look like a member header
+ * (1f 8b 08, reserved flag bits clear, a plausible XFL / OS byte); every candidate is inflated by a worker with
+ * zlib's own gzip wrapper (header, CRC32 and ISIZE checked).  The consumer walks the chain in file order: the
+ * member that starts where the previous one ENDED is the next one, whatever the scanner guessed -- a candidate
+ * inside a member's data is simply never asked for (its worker usually fails on the first block), a member whose
+ * header the scanner did not recognise is inflated on demand.  What reaches the framing code is byte for byte
+ * what gzread() would deliver: trailing bytes that start no member end the stream silently, a damaged member
+ * yields the bytes in front of the damage and then -3.
+ * A single-member file has one candidate: one worker streams it through 1 MiB chunks (no parallelism, but the
+ * inflate overlaps the framing and packing of the reader thread). */
+#define MGZ_CHUNK FQR_BUF
+typedef struct mgz_chunk {
+  struct mgz_chunk *next;
+  uint32_t len;
+  uint8_t *data; /* MGZ_CHUNK bytes */
+} mgz_chunk;
+
+typedef struct mgz_pool mgz_pool;
+typedef struct mgz_job {
+  mgz_pool *pool;
+  uint64_t start, end; /* compressed offsets; end valid when done == 1 */
+  int claimed, done;   /* done: 0 running, 1 stream end reached, 2 the file ended inside the member, -3 error */
+  int cancel;          /* the consumer went past this candidate: stop */
+  mgz_chunk *head, *tail;
+} mgz_job;
+
+struct mgz_pool {
+  const uint8_t *map;
+  uint64_t size;
+  int fd;
+  int n_threads;
+  pthread_t *th;
+  pthread_t *extra; /* one thread per member that had to be inflated on demand (rare) */
+  size_t n_extra;
+  pthread_mutex_t mu;
+  pthread_cond_t cv_data, cv_room;
+  mgz_job **job; /* candidates in file order (the nodes never move) */
+  size_t n_jobs, cap_jobs;
+  size_t next_claim;  /* first job no worker has taken yet */
+  uint64_t scan_pos;  /* the scanner has looked at every offset below this */
+  uint64_t expect;    /* compressed offset where the consumer's next member starts */
+  mgz_job *cur;       /* consumer: the job that starts at `expect`, NULL until it is looked up */
+  int stop;
+  uint64_t budget;    /* bytes of inflated data the pool may hold ahead of the consumer */
+  uint64_t held;
+  double inflate_cpu_s;
+};
+
 struct fqr_reader {
   gzFile f;
   bgzf_pool *pool; /* != NULL: BGZF input decoded by the pool, f unused */
+  mgz_pool *mgz;   /* != NULL: gzip members inflated by the pool, f unused */
   char *path;      /* to reopen the file when a BGZF file continues with ordinary gzip members */
   uint8_t *buf;
   size_t begin, end;
@@ -178,7 +232,7 @@ static bgzf_pool *bgzf_pool_open(FILE *fp, int n_threads) {
   bgzf_pool *p = (bgzf_pool *)calloc(1, sizeof *p);
   p->fp = fp;
   p->n_threads = n_threads;
-  p->n_slots = 8 * n_threads;
+  p->n_slots = 64 * n_threads > 1024 ? 1024 : 64 * n_threads; /* up to 64 MiB of text ahead of the framing code */
   p->slot = (bgzf_slot *)calloc((size_t)p->n_slots, sizeof *p->slot);
   for (int i = 0; i < p->n_slots; i++) {
     p->slot[i].cbuf = (uint8_t *)malloc(BGZF_MAX_BLOCK);
@@ -212,6 +266,296 @@ static void bgzf_pool_close(bgzf_pool *p) {
   pthread_cond_destroy(&p->cv_free);
   fclose(p->fp);
   free(p);
+}
+
+/* ---- multi-member gzip pool: implementation ---- */
+
+/* does a gzip member header plausibly start at map[o]?  (RFC 1952: ID1 ID2 CM FLG MTIME[4] XFL OS) */
+static int mgz_header_at(const mgz_pool *p, uint64_t o) {
+  if (o + 18 > p->size) return 0;
+  const uint8_t *h = p->map + o;
+  return h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 0xE0) == 0 && (h[8] == 0 || h[8] == 2 || h[8] == 4) &&
+         (h[9] <= 13 || h[9] == 255);
+}
+
+static mgz_job *mgz_insert_job(mgz_pool *p, size_t at, uint64_t start) { /* mu held */
+  if (p->n_jobs == p->cap_jobs) {
+    p->cap_jobs = p->cap_jobs ? 2 * p->cap_jobs : 64;
+    p->job = (mgz_job **)realloc(p->job, p->cap_jobs * sizeof *p->job);
+  }
+  memmove(&p->job[at + 1], &p->job[at], (p->n_jobs - at) * sizeof *p->job);
+  p->n_jobs++;
+  mgz_job *j = (mgz_job *)calloc(1, sizeof *j);
+  j->pool = p;
+  j->start = start;
+  p->job[at] = j;
+  return j;
+}
+
+/* looks for the next candidate at or behind scan_pos and appends it; 0 if the file holds no more (mu held) */
+static int mgz_scan_next(mgz_pool *p) {
+  uint64_t o = p->scan_pos;
+  while (o + 18 <= p->size) {
+    const uint8_t *hit = (const uint8_t *)memchr(p->map + o, 0x1f, (size_t)(p->size - 17 - o));
+    if (!hit) break;
+    o = (uint64_t)(hit - p->map);
+    if (mgz_header_at(p, o)) {
+      mgz_insert_job(p, p->n_jobs, o);
+      p->scan_pos = o + 18;
+      return 1;
+    }
+    o++;
+  }
+  p->scan_pos = p->size;
+  return 0;
+}
+
+/* inflates one member (zlib's gzip wrapper checks header, CRC32 and ISIZE) into 1 MiB chunks on the job's list */
+static void mgz_inflate_job(mgz_job *j, z_stream *zs) {
+  mgz_pool *p = j->pool;
+  inflateReset2(zs, 15 + 16);
+  zs->avail_in = 0;
+  uint64_t in_pos = j->start;
+  int status = 0;
+  while (status == 0) {
+    mgz_chunk *c = (mgz_chunk *)malloc(sizeof *c);
+    c->data = (uint8_t *)malloc(MGZ_CHUNK);
+    c->next = NULL;
+    zs->next_out = c->data;
+    zs->avail_out = MGZ_CHUNK;
+    while (zs->avail_out && status == 0) {
+      if (zs->avail_in == 0) {
+        const uint64_t left = p->size - in_pos;
+        if (left == 0) { /* the file ends inside the member: gzread() hands out what it has and stops without an
+                            error (Z_BUF_ERROR, "unexpected end of file", is not fatal to it) */
+          status = 2;
+          break;
+        }
+        const uInt n = left > (1u << 30) ? (1u << 30) : (uInt)left;
+        zs->next_in = (Bytef *)(p->map + in_pos);
+        zs->avail_in = n;
+        in_pos += n;
+      }
+      const int rc = inflate(zs, Z_NO_FLUSH);
+      if (rc == Z_STREAM_END)
+        status = 1;
+      else if (rc != Z_OK && rc != Z_BUF_ERROR)
+        status = -3;
+    }
+    c->len = MGZ_CHUNK - zs->avail_out;
+    pthread_mutex_lock(&p->mu);
+    if (c->len) {
+      if (j->tail)
+        j->tail->next = c;
+      else
+        j->head = c;
+      j->tail = c;
+      p->held += c->len;
+    } else {
+      free(c->data);
+      free(c);
+    }
+    if (status) {
+      j->end = in_pos - zs->avail_in;
+      j->done = status;
+    }
+    pthread_cond_broadcast(&p->cv_data);
+    /* a member ahead of the consumer waits here while the pool holds too much; the consumer's own never does */
+    while (!status && p->held >= p->budget && p->cur != j && !p->stop && !j->cancel) pthread_cond_wait(&p->cv_room, &p->mu);
+    if (!status && (p->stop || j->cancel)) {
+      j->done = -3;
+      status = -3;
+      pthread_cond_broadcast(&p->cv_data);
+    }
+    pthread_mutex_unlock(&p->mu);
+  }
+}
+
+static void *mgz_worker(void *arg) {
+  mgz_pool *p = (mgz_pool *)arg;
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  if (inflateInit2(&zs, 15 + 16) != Z_OK) return NULL;
+  double cpu = 0;
+  for (;;) {
+    pthread_mutex_lock(&p->mu);
+    mgz_job *j = NULL;
+    while (!p->stop && !j) {
+      /* candidates the consumer already passed are never claimed */
+      while (p->next_claim < p->n_jobs && (p->job[p->next_claim]->claimed || p->job[p->next_claim]->start < p->expect)) p->next_claim++;
+      if (p->cur && !p->cur->claimed)
+        j = p->cur;
+      else if (p->held >= p->budget)
+        pthread_cond_wait(&p->cv_room, &p->mu); /* speculation is bounded */
+      else if (p->next_claim < p->n_jobs)
+        j = p->job[p->next_claim];
+      else if (!(p->scan_pos < p->size && mgz_scan_next(p)))
+        pthread_cond_wait(&p->cv_room, &p->mu); /* nothing left to look for */
+    }
+    if (p->stop) {
+      pthread_mutex_unlock(&p->mu);
+      break;
+    }
+    j->claimed = 1;
+    pthread_mutex_unlock(&p->mu);
+    const double t0 = now_s();
+    mgz_inflate_job(j, &zs);
+    cpu += now_s() - t0;
+  }
+  inflateEnd(&zs);
+  pthread_mutex_lock(&p->mu);
+  p->inflate_cpu_s += cpu;
+  pthread_mutex_unlock(&p->mu);
+  return NULL;
+}
+
+static void *mgz_one_job(void *arg) { /* a member nobody had scheduled: its own thread */
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  if (inflateInit2(&zs, 15 + 16) == Z_OK) {
+    mgz_inflate_job((mgz_job *)arg, &zs);
+    inflateEnd(&zs);
+  } else {
+    mgz_job *j = (mgz_job *)arg;
+    pthread_mutex_lock(&j->pool->mu);
+    j->done = -3;
+    pthread_cond_broadcast(&j->pool->cv_data);
+    pthread_mutex_unlock(&j->pool->mu);
+  }
+  return NULL;
+}
+
+static void mgz_free_job_chunks(mgz_pool *p, mgz_job *j) { /* mu held */
+  while (j->head) {
+    mgz_chunk *c = j->head;
+    j->head = c->next;
+    p->held -= c->len;
+    free(c->data);
+    free(c);
+  }
+  j->tail = NULL;
+}
+
+static mgz_pool *mgz_pool_open(const char *path, int n_threads) {
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return NULL;
+  struct stat st;
+  if (fstat(fd, &st) != 0 || st.st_size < 18) {
+    close(fd);
+    return NULL;
+  }
+  void *map = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+  if (map == MAP_FAILED) {
+    close(fd);
+    return NULL;
+  }
+  madvise(map, (size_t)st.st_size, MADV_SEQUENTIAL);
+  mgz_pool *p = (mgz_pool *)calloc(1, sizeof *p);
+  p->map = (const uint8_t *)map;
+  p->size = (uint64_t)st.st_size;
+  p->fd = fd;
+  p->budget = (uint64_t)(n_threads + 2) * (96ull << 20);
+  pthread_mutex_init(&p->mu, NULL);
+  pthread_cond_init(&p->cv_data, NULL);
+  pthread_cond_init(&p->cv_room, NULL);
+  p->cur = mgz_insert_job(p, 0, 0);
+  p->scan_pos = 18;
+  p->th = (pthread_t *)calloc((size_t)n_threads, sizeof *p->th);
+  int started = 0;
+  for (int i = 0; i < n_threads; i++)
+    if (pthread_create(&p->th[started], NULL, mgz_worker, p) == 0) started++;
+  p->n_threads = started;
+  return p;
+}
+
+static void mgz_pool_close(mgz_pool *p) {
+  pthread_mutex_lock(&p->mu);
+  p->stop = 1;
+  pthread_cond_broadcast(&p->cv_room);
+  pthread_cond_broadcast(&p->cv_data);
+  pthread_mutex_unlock(&p->mu);
+  for (int i = 0; i < p->n_threads; i++) pthread_join(p->th[i], NULL);
+  for (size_t i = 0; i < p->n_extra; i++) pthread_join(p->extra[i], NULL);
+  for (size_t i = 0; i < p->n_jobs; i++) {
+    mgz_free_job_chunks(p, p->job[i]);
+    free(p->job[i]);
+  }
+  free(p->job);
+  free(p->th);
+  free(p->extra);
+  pthread_mutex_destroy(&p->mu);
+  pthread_cond_destroy(&p->cv_data);
+  pthread_cond_destroy(&p->cv_room);
+  munmap((void *)p->map, (size_t)p->size);
+  close(p->fd);
+  free(p);
+}
+
+/* next chunk of inflated bytes in file order into *buf (buffers are swapped, not copied); 0 ok, -1 end, -3 error */
+static int mgz_next_chunk(mgz_pool *p, uint8_t **buf, size_t *len) {
+  pthread_mutex_lock(&p->mu);
+  for (;;) {
+    if (!p->cur) {
+      /* the member that starts exactly where the last one ended */
+      if (p->expect + 18 > p->size || p->map[p->expect] != 0x1f || p->map[p->expect + 1] != 0x8b) {
+        pthread_mutex_unlock(&p->mu); /* end of file, or trailing bytes that start no member: gzread stops silently */
+        return -1;
+      }
+      size_t i = 0;
+      while (i < p->n_jobs && p->job[i]->start < p->expect) {
+        if (!p->job[i]->cancel) { /* a candidate inside the previous member's data (or a member already delivered) */
+          p->job[i]->cancel = 1;
+          mgz_free_job_chunks(p, p->job[i]);
+        }
+        i++;
+      }
+      if (i < p->n_jobs && p->job[i]->start == p->expect) {
+        p->cur = p->job[i];
+      } else {
+        /* the scanner has not got here yet, or did not take these bytes for a header: the member gets a thread of
+         * its own (the pool's workers may all be waiting for room behind members further down the file) */
+        p->cur = mgz_insert_job(p, i, p->expect);
+        p->cur->claimed = 1;
+        if (p->next_claim > i) p->next_claim = i;
+        if (p->scan_pos < p->expect + 18) p->scan_pos = p->expect + 18;
+        p->extra = (pthread_t *)realloc(p->extra, (p->n_extra + 1) * sizeof *p->extra);
+        if (pthread_create(&p->extra[p->n_extra], NULL, mgz_one_job, p->cur) == 0)
+          p->n_extra++;
+        else
+          p->cur->done = -3;
+      }
+      pthread_cond_broadcast(&p->cv_room);
+    }
+    mgz_job *j = p->cur;
+    if (j->head) {
+      mgz_chunk *c = j->head;
+      j->head = c->next;
+      if (!j->head) j->tail = NULL;
+      p->held -= c->len;
+      uint8_t *old = *buf;
+      *buf = c->data;
+      *len = c->len;
+      pthread_cond_broadcast(&p->cv_room);
+      pthread_mutex_unlock(&p->mu);
+      free(old);
+      free(c);
+      return 0;
+    }
+    if (j->done == 1) {
+      p->expect = j->end;
+      p->cur = NULL;
+      continue;
+    }
+    if (j->done == 2) {
+      pthread_mutex_unlock(&p->mu);
+      return -1;
+    }
+    if (j->done < 0) {
+      pthread_mutex_unlock(&p->mu);
+      return -3;
+    }
+    pthread_cond_wait(&p->cv_data, &p->mu);
+  }
 }
 
 /* 1 if the file starts with a BGZF block header */
@@ -251,12 +595,25 @@ fqr_reader *fqr_open_mt(const char *path, int threads) {
       }
       bgzf_pool_close(pool); /* no thread could be started: gzread path below (closes fp) */
     } else {
+      uint8_t h[3] = {0, 0, 0};
+      const size_t got = fread(h, 1, 3, fp);
       fclose(fp);
+      if (got == 3 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && !getenv("QUACK_NO_MGZ")) {
+        /* ordinary gzip: members inflated in parallel where the file has several (and ahead of the framing code
+         * on a thread of its own where it has one) */
+        mgz_pool *mp = mgz_pool_open(path, threads);
+        if (mp && mp->n_threads > 0) {
+          fqr_reader *r = (fqr_reader *)calloc(1, sizeof *r);
+          r->mgz = mp;
+          r->buf = (uint8_t *)malloc(MGZ_CHUNK);
+          return r;
+        }
+        if (mp) mgz_pool_close(mp);
+      }
     }
   }
   gzFile f = gzopen(path, "r");
   if (!f) return NULL;
-  gzbuffer(f, 1u << 18);
   fqr_reader *r = (fqr_reader *)calloc(1, sizeof *r);
   r->f = f;
   r->buf = (uint8_t *)malloc(FQR_BUF);
@@ -265,12 +622,14 @@ fqr_reader *fqr_open_mt(const char *path, int threads) {
 
 fqr_reader *fqr_open(const char *path) { return fqr_open_mt(path, 0); }
 
-int fqr_decode_threads(const fqr_reader *r) { return r->pool ? r->pool->n_threads : 1; }
+int fqr_decode_threads(const fqr_reader *r) { return r->pool ? r->pool->n_threads : r->mgz ? r->mgz->n_threads : 1; }
 
 void fqr_close(fqr_reader *r) {
   if (!r) return;
   if (r->pool)
     bgzf_pool_close(r->pool);
+  else if (r->mgz)
+    mgz_pool_close(r->mgz);
   else if (r->f)
     gzclose(r->f);
   free(r->path);
@@ -286,8 +645,33 @@ double fqr_inflate_seconds(const fqr_reader *r) { return r->inflate_s; }
 
 /* refill; returns 0 when bytes are available, -1 at end of file, -3 on a stream error */
 static int refill(fqr_reader *r) {
-  if (r->err) return -3;
+  if (r->err) {
+    r->is_eof = 1;
+    return -3;
+  }
   if (r->is_eof) return -1;
+  if (r->mgz) { /* next chunk of the current gzip member, the members in file order */
+    const double t0 = now_s();
+    for (;;) {
+      size_t n = 0;
+      const int rc = mgz_next_chunk(r->mgz, &r->buf, &n);
+      r->begin = 0;
+      r->end = rc ? 0 : n;
+      if (rc) {
+        r->is_eof = 1;
+        r->inflate_s += now_s() - t0;
+        if (rc == -3) {
+          r->err = 1;
+          return -3;
+        }
+        return -1;
+      }
+      if (n) break;
+    }
+    r->bytes_in += r->end;
+    r->inflate_s += now_s() - t0; /* time the framing code waited for the pool */
+    return 0;
+  }
   if (r->pool) { /* next inflated block, in file order; empty blocks (the BGZF end marker) are skipped */
     bgzf_pool *p = r->pool;
     const double t0 = now_s();
@@ -343,21 +727,27 @@ static int refill(fqr_reader *r) {
     r->inflate_s += now_s() - t0; /* time the framing code waited for the pool */
     return 0;
   }
+  /* gzread() in requests of 16 KiB, the size kseq asks for (klib/kseq.h:74,228): a request that runs into damaged
+   * data fails as a whole, so with the reference's request size the bytes in front of the damage that reach the
+   * framing code are the reference's too */
   const double t0 = now_s();
-  const int n = gzread(r->f, r->buf, FQR_BUF);
+  size_t filled = 0;
+  int n = 0;
+  while (filled + 16384 <= FQR_BUF) {
+    n = gzread(r->f, r->buf + filled, 16384);
+    if (n <= 0) break;
+    filled += (size_t)n;
+    if (n < 16384) break;
+  }
   r->inflate_s += now_s() - t0;
   r->begin = 0;
-  if (n <= 0) {
-    r->end = 0;
+  r->end = filled;
+  r->bytes_in += (uint64_t)filled;
+  if (n < 0) r->err = 1; /* reported once the bytes in front of it are consumed */
+  if (filled == 0) {
     r->is_eof = 1;
-    if (n < 0) {
-      r->err = 1;
-      return -3;
-    }
-    return -1;
+    return n < 0 ? -3 : -1;
   }
-  r->end = (size_t)n;
-  r->bytes_in += (uint64_t)n;
   return 0;
 }
 

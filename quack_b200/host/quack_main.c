@@ -107,18 +107,14 @@ struct mate_job {
   int stream_status;
   int decode_threads;
   uint32_t len_cap;
+  fqr_reader *reader; /* opened before the CUDA context exists: its inflate pool works through the start-up */
 };
 
 /* reader thread of one mate: inflate + frame + pack + submit, until the stream ends */
 static void *mate_thread(void *arg) {
   struct mate_job *j = (struct mate_job *)arg;
   const double t0 = now_s();
-  fqr_reader *r = fqr_open(j->path);
-  if (!r) {
-    j->rc = -100;
-    snprintf(j->err, sizeof j->err, "cannot open %s", j->path);
-    return NULL;
-  }
+  fqr_reader *r = j->reader;
   int more = 1;
   while (more) {
     qb_batch b;
@@ -179,6 +175,21 @@ int main(int argc, char **argv) {
     }
   }
 
+  /* The inputs are opened first: a compressed file's inflate pool (fq_reader.c) starts to decode at once and
+   * runs ahead of the framing code by up to a few hundred MiB, so the ~0.5 s the CUDA context, the pinned ring and
+   * the kernel images take to come up are spent inflating instead of waiting. */
+  struct mate_job jobs[2];
+  memset(jobs, 0, sizeof jobs);
+  const int n_mates = paired ? 2 : 1;
+  for (int m = 0; m < n_mates; m++) {
+    jobs[m].path = paired ? (m == 0 ? o.forward : o.reverse) : o.unpaired;
+    jobs[m].reader = fqr_open(jobs[m].path);
+    if (!jobs[m].reader) {
+      fprintf(stderr, "quack: cannot open %s\n", jobs[m].path);
+      return 2;
+    }
+  }
+
   qb_config cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.n_devices = (int)env_long("QB_DEVICES", 1);
@@ -197,14 +208,11 @@ int main(int argc, char **argv) {
   }
   const double t_created = now_s(); /* CUDA start-up, pinned ring, accumulators: a fixed cost per process */
 
-  struct mate_job jobs[2];
   pthread_t th[2];
-  memset(jobs, 0, sizeof jobs);
   for (int m = 0; m < cfg.n_mates; m++) {
     jobs[m].ctx = ctx;
     jobs[m].mate = m;
     jobs[m].len_cap = cfg.len_cap;
-    jobs[m].path = paired ? (m == 0 ? o.forward : o.reverse) : o.unpaired;
     pthread_create(&th[m], NULL, mate_thread, &jobs[m]);
   }
   for (int m = 0; m < cfg.n_mates; m++) pthread_join(th[m], NULL);

@@ -302,17 +302,108 @@ def test_reader_on_a_pipe(kind, tmp_path):
     assert r.stdout.split() == [b"1000", b"-1"]
 
 
-def test_bgzf_is_only_used_for_bgzf(tmp_path):
-    """Plain text and ordinary gzip keep the gzread() path whatever the thread count."""
+def test_pools_are_chosen_by_container(tmp_path):
+    """Plain text keeps the gzread() path whatever the thread count; ordinary gzip takes the member pool, BGZF the
+    block pool; one thread: gzread() for everything, like the reference."""
     p = tmp_path / "a.fq"
     p.write_bytes(b"@a\nACGT\n+\nIIII\n")
     assert capi.decode_throughput(str(p), 8)["threads"] == 1
     g = tmp_path / "a.fq.gz"
     g.write_bytes(gzip.compress(b"@a\nACGT\n+\nIIII\n"))
     d = capi.decode_throughput(str(g), 8)
-    assert d["threads"] == 1 and d["reads"] == 1
+    assert d["threads"] == 8 and d["reads"] == 1
+    assert capi.decode_throughput(str(g), 1)["threads"] == 1
     from quack_b200 import synth
     b = tmp_path / "a.fq.bgz"
     b.write_bytes(synth.bgzf_bytes(b"@a\nACGT\n+\nIIII\n"))
     d = capi.decode_throughput(str(b), 8)
     assert d["threads"] == 8 and d["reads"] == 1 and d["bases"] == 4
+
+
+def _gzip_with_name(data: bytes) -> bytes:
+    """A member with FNAME and FCOMMENT header fields (RFC 1952), as `gzip file` writes them."""
+    import struct
+    import zlib
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    body = co.compress(data) + co.flush()
+    return (b"\x1f\x8b\x08\x18" + struct.pack("<I", 1_700_000_000) + b"\x00\x03" + b"reads.fq\x00" + b"a comment\x00" + body +
+            struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data) & 0xFFFFFFFF))
+
+
+@pytest.mark.parametrize("threads", [2, 8])
+def test_gzip_member_pool_equals_gzread(threads, tmp_path):
+    """Ordinary (multi-member) gzip through the speculative member pool: the same records, the same final status
+    as gzread() -- the reference's decoder (quack.c:187) -- on every shape of file."""
+    blob = _fastq_blob(3000, seed=11)
+    cut = [0, 1000, 1001, 50_000, 50_017, 300_000, len(blob)]
+    members = [gzip.compress(blob[a:b], 1) for a, b in zip(cut, cut[1:])]
+    fake = b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03" + b"ACGT" * 12
+    stored = gzip.compress(b"@s\nACGT" + fake + b"\n+\nIIII" + b"I" * len(fake) + b"\n", 0)   # the fake header verbatim in the file
+    tail_rec = b"@t\nACGTACGT\n+\nIIIIIIII\n"
+    cases = {
+        "one_member": gzip.compress(blob, 6),
+        "many_members": b"".join(members),
+        "empty_members_between": members[0] + gzip.compress(b"") + members[1] + gzip.compress(b"") + b"".join(members[2:]),
+        "trailing_garbage": b"".join(members) + b"garbage that starts no member",
+        "trailing_zeros": b"".join(members) + bytes(100),
+        "header_lookalike_inside_a_member": members[0] + stored + gzip.compress(tail_rec),
+        "truncated_last_member": b"".join(members)[:-40],
+        "truncated_mid": b"".join(members[:4]) + members[4][: len(members[4]) // 2],
+        "with_name_and_comment_fields": members[0] + _gzip_with_name(blob[1000:50_000]),
+        "member_with_exotic_os_byte": members[0] + members[1][:9] + b"\x63" + members[1][10:] + b"".join(members[2:]),
+    }
+    p = tmp_path / "m.fq.gz"
+    for name, data in cases.items():
+        p.write_bytes(data)
+        want = capi.parse_records(str(p), 1)        # gzread path
+        assert po.parse_records(str(p)) == want, name
+        got = capi.parse_records(str(p), threads)
+        assert got == want, (name, len(got[0]), got[1], len(want[0]), want[1])
+        bb, st = capi.read_batches(str(p), 50_000, 400, threads)
+        gb, gst = capi.read_batches(str(p), 50_000, 400, 1)
+        assert st == gst and len(bb) == len(gb), name
+        for x, y in zip(bb, gb):
+            assert all(np.array_equal(u, v) for u, v in zip(x[:4], y[:4])), name
+
+
+def test_damaged_gzip_streams(tmp_path):
+    """A flipped byte inside a member: every decoder stops with -3 (kseq_read()'s stream error).  zlib notices the
+    damage some way behind the flipped byte and the bytes in between inflate to something else than was written, so
+    the records handed out before are NOT a prefix of the true list -- but they are the same for every decoder as far
+    as it gets.  How far depends on the request size against zlib: the gzread() path asks for kseq's 16 KiB at a
+    time and so stops exactly where the reference's reader stops (checked against it when oracle/_ref is there); the
+    pools hand out every byte that inflates in front of the point where zlib gives up, never fewer records."""
+    blob = _fastq_blob(3000, seed=11)
+    cut = [0, 1000, 1001, 50_000, 50_017, 300_000, len(blob)]
+    members = [gzip.compress(blob[a:b], 1) for a, b in zip(cut, cut[1:])]
+    data = b"".join(members[:4]) + members[4][:2000] + bytes([members[4][2000] ^ 0x5A]) + members[4][2001:] + members[5]
+    p = tmp_path / "flip.fq.gz"
+    p.write_bytes(data)
+
+    def complete(recs):
+        return recs[:-1] if recs and recs[-1][1] is None else recs   # (a record cut inside its sequence comes back as FASTA)
+    serial, st = capi.parse_records(str(p), 1)
+    assert st == -3 and len(complete(serial)) > 100
+    if po.have_ref():
+        ref, rst = po.ref_parse_records(str(p), 1 << 26)
+        assert rst == -3 and ref == serial
+    for threads in (2, 8):
+        pool, st = capi.parse_records(str(p), threads)
+        assert st == -3 and len(complete(pool)) >= len(complete(serial))
+        assert complete(pool)[: len(complete(serial))] == complete(serial)
+
+
+def test_gzip_member_pool_big_members(tmp_path):
+    """Members of several MiB (the benchmark generator writes 64 MiB of text per member): chunks cross the pool in
+    order, the speculative workers run ahead of the consumer."""
+    blob = _fastq_blob(40_000, seed=12)      # ~16 MB of text
+    third = len(blob) // 3
+    data = b"".join(gzip.compress(blob[i: i + third + 7], 1) for i in range(0, len(blob), third + 7))
+    p = tmp_path / "big.fq.gz"
+    p.write_bytes(data)
+    want = capi.parse_records(str(p), 1)
+    assert len(want[0]) == 40_000 and want[1] == -1
+    for t in (2, 4, 16):
+        assert capi.parse_records(str(p), t) == want, t
+
+

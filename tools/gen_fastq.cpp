@@ -1,7 +1,8 @@
 // gen_fastq.cpp -- standalone writer of the synthetic benchmark inputs: 4-line FASTQ records
 // '@r<9-digit index>/<mate>', bare '+' line, reads from the deterministic generator of quack_b200/csrc/qb_gen.cpp
 // (the same reads qb_gen_reads() puts into device batches).  Output: plain text, gzip (concatenated members of
-// <= 64 MiB of text each, compressed in parallel: what the reference's gzread handles too), or BGZF (<= 65280-byte
+// 16 MiB of text each -- SURVEY 8d asks for members of at most 64 MiB --, compressed in parallel: what the
+// reference's gzread handles too), or BGZF (<= 65280-byte
 // blocks with the 'BC' size field, reference klib/bgzf.c:63-71).  Links nothing of the library: bench.py's reference
 // arm and the file -> SVG comparison get their inputs from this tool.
 //
@@ -109,8 +110,8 @@ int main(int argc, char **argv) {
     perror(path);
     return 1;
   }
-  // chunks of <= 64 MiB of text (one gzip member each), produced by a pool of threads, written in order
-  const uint64_t per_chunk = (64ull << 20) / (2ull * lmax + 20);
+  // chunks of <= 16 MiB of text (one gzip member each), produced by a pool of threads, written in order
+  const uint64_t per_chunk = (16ull << 20) / (2ull * lmax + 20);
   const uint64_t n_chunks = (n_reads + per_chunk - 1) / per_chunk;
   std::vector<std::string> done(n_chunks);
   std::vector<std::atomic<int>> ready(n_chunks);
