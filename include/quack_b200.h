@@ -55,7 +55,8 @@ typedef enum {
                               to 320 bp, the warp-tile kernel, or simple */
   QB_KERNEL_SIMPLE = 1,    /* one warp per read, global atomics: any len_cap, slow */
   QB_KERNEL_FUSED = 2,     /* CTA-wide TMA-staged tiles, joint (base,score) shared-memory histogram (v3) */
-  QB_KERNEL_WTILE = 3,     /* autonomous warps, each with its own TMA-staged tile ring (v4; reads <= 192 bp) */
+  QB_KERNEL_WTILE = 3,     /* (v4 warp-tile kernel, removed in round 2: slower than v3 wherever both ran; the value is
+                              still accepted and takes the fused kernel) */
   QB_KERNEL_PERIOD = 4,    /* v5: lanes own fixed positions of a k-read period, one aligned load + PRMT + RED per base;
                               uniform-length batches only (an error otherwise), the reads that do not fill a tile
                               go to the AUTO choice among the others */

@@ -221,7 +221,7 @@ uint32_t detect_shape(const uint32_t *offset, const uint32_t *length, uint32_t n
 int launch_other(qb_ctx *ctx, Device &d, const qb::BatchView &v, qb::Accum ac, const qb::AdapterSet &ad, int kernel,
                  cudaStream_t stream) {
   qb::FusedPlan plan{};
-  qb::WtilePlan wplan{};
+  if (kernel == QB_KERNEL_WTILE) kernel = QB_KERNEL_FUSED;  // (the v4 warp-tile kernel is gone: slower than v3 everywhere)
   if (kernel == QB_KERNEL_AUTO || kernel == QB_KERNEL_FLAT) {
     // ragged batches of back-to-back reads: the flat kernel (lane <-> 16-byte unit) when the batch has its shape
     qb::FlatPlan fp{};
@@ -245,17 +245,9 @@ int launch_other(qb_ctx *ctx, Device &d, const qb::BatchView &v, qb::Accum ac, c
     // opened for 65536-bp reads still runs short-read batches on the shared-memory kernels.
     uint32_t eff_cap = ctx->cur_cap;
     if (v.max_len && v.max_len < eff_cap) eff_cap = v.max_len < 11u ? 11u : v.max_len;
-    // AUTO: the v3 kernel measured faster than v4 wherever both fit (profiles/r01c)
-    if (kernel != QB_KERNEL_WTILE)
-      plan = qb::fused_plan(eff_cap, v.max_len, ad.enabled, d.sm_count, (uint32_t)d.smem_optin, ctx->qbase);
-    if (kernel != QB_KERNEL_FUSED && !plan.ok)
-      wplan = qb::wtile_plan(eff_cap, v.max_len, ad.enabled, d.sm_count, (uint32_t)d.smem_optin,
-                             (uint32_t)d.smem_reserved, ctx->qbase);
+    plan = qb::fused_plan(eff_cap, v.max_len, ad.enabled, d.sm_count, (uint32_t)d.smem_optin, ctx->qbase);
     if (plan.ok) {
       kernel = QB_KERNEL_FUSED;
-      ac.len_cap = eff_cap;
-    } else if (wplan.ok) {
-      kernel = QB_KERNEL_WTILE;
       ac.len_cap = eff_cap;
     } else {
       if (kernel != QB_KERNEL_AUTO)
@@ -266,9 +258,8 @@ int launch_other(qb_ctx *ctx, Device &d, const qb::BatchView &v, qb::Accum ac, c
   }
   ctx->launches++;
   (kernel == QB_KERNEL_SIMPLE ? ctx->launches_simple : ctx->launches_fused)++;
-  cudaError_t e = kernel == QB_KERNEL_WTILE   ? qb::launch_wtile(v, ac, ad, wplan, stream)
-                  : kernel == QB_KERNEL_FUSED ? qb::launch_fused(v, ac, ad, plan, stream)
-                                              : qb::launch_simple(v, ac, ad, d.sm_count, stream);
+  cudaError_t e = kernel == QB_KERNEL_FUSED ? qb::launch_fused(v, ac, ad, plan, stream)
+                                            : qb::launch_simple(v, ac, ad, d.sm_count, stream);
   if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   return QB_OK;
 }
@@ -506,7 +497,6 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
       std::lock_guard<std::mutex> lk(cfg_mu);
       if (d.id >= 256 || !configured[d.id]) {
         QB_CREATE_CUDA(qb::fused_configure());
-        QB_CREATE_CUDA(qb::wtile_configure());
         QB_CREATE_CUDA(qb::period_configure());
         QB_CREATE_CUDA(qb::flat_configure());
         if (d.id < 256) configured[d.id] = true;

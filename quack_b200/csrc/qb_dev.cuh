@@ -1,5 +1,5 @@
 // qb_dev.cuh -- device helpers shared by the sm_100a kernels (qb_kernels.cu: simple + fused v3,
-// qb_wtile.cu: warp-tile kernel): base LUT, SWAR key bytes, mbarrier / TMA bulk copy / shared-memory
+// qb_period.cu: period kernel, qb_flat.cu: flat kernel): base LUT, SWAR key bytes, mbarrier / TMA bulk copy / shared-memory
 // access wrappers.  Internal; the public boundary is include/quack_b200.h.
 #pragma once
 

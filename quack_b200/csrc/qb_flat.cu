@@ -372,8 +372,12 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
               const uint32_t ent = f_lds_u16(q_s + 2u * (e0 + lane));
               const uint32_t b = ent >> 5, ln = ent & 31u;
               const int w = (int)(32u * (nst - 1u - b) + ln) - 1;  // chunk-relative word whose 7-mer passed the filter
-              // codes of words w - 1 .. w + 2 (bases 4 w - 4 .. 4 w + 11): the u16 of word w and of word w + 2
-              const uint32_t ctx = f_lds_u16(P_s + 16u + 2u * (uint32_t)w) | f_lds_u16(P_s + 16u + 2u * (uint32_t)w + 4u) << 16;
+              // codes of words w - 1 .. w + 2 (bases 4 w - 4 .. 4 w + 11): the u16 of word w holds (w - 1, w), the high
+              // bytes of the next two hold w + 1 and w + 2.  (Word w + 1 is the word of the lane that saw the hit and
+              // always stored; the u16 of a word behind the chunk was never written -- no window that needs it lies
+              // inside a read of the chunk.)
+              const uint32_t pw = P_s + 16u + 2u * (uint32_t)w;
+              const uint32_t ctx = f_lds_u16(pw) | (f_lds_u16(pw + 2u) & 0xFF00u) << 8 | (f_lds_u16(pw + 4u) & 0xFF00u) << 16;
               const int ws0 = 4 * w - 3;  // first byte of the first of the four windows
               // read of the first byte of the word that holds it (of word 0 if it lies in front of the chunk)
               const uint32_t vb = (uint32_t)(ws0 < 0 ? 0 : ws0) >> 2;

@@ -54,7 +54,7 @@ struct BatchView {
   uint32_t n_reads;
   uint64_t n_bytes;
   uint32_t max_len;        // longest read in the batch (upper bound)
-  uint2 *tiles;            // scratch of n_reads entries: tile descriptors written by the warp-tile kernel's first pass
+  uint2 *tiles;            // scratch of n_reads entries (the flat kernel keeps its chunk index there)
   uint32_t uniform_len;    // != 0: the HOST verified that every read has this length and that the reads lie back to
                            // back (offset[r] = offset[0] + r * uniform_len); 0: unknown / ragged
   uint32_t first_offset;   // offset[0] of a uniform / contiguous batch
@@ -85,32 +85,6 @@ constexpr uint32_t kMaxTileReads = 248;   // reads per tile (8 per consumer warp
 #define QB_CW 15
 #endif
 constexpr int kFusedConsumerWarps = QB_CW;  // + 1 producer warp = 512 threads (up to 128 registers each), 1 CTA per SM
-
-// ---- warp-tile kernel geometry (qb_wtile.cu; computed on the host, see wtile_plan) --------
-#ifndef QB_WW
-#define QB_WW 16
-#endif
-constexpr int kWtileWarps = QB_WW;  // autonomous warps per CTA (one CTA per SM)
-
-struct WtilePlan {
-  uint32_t reads_per_tile;   // R <= 32 whole reads per warp tile
-  uint32_t tile_bytes;       // capacity of one staged byte buffer (seq or qual), multiple of 16
-  uint32_t buf;              // tile_bytes + pad
-  uint32_t wblock;           // bytes of one warp block (barriers, tile headers, queue, 2 stages x 2 buffers)
-  uint32_t smem_base;        // shared address the dynamic shared memory must start at (checked by the kernel)
-  uint32_t smem_bytes;
-  uint32_t tail_s, afilt_s, exact_s, lenhist_s, kmerhist_s;  // shared addresses of the CTA-wide arrays
-  uint32_t region_s[2], region_n[2];                         // warp blocks: region_n[i] blocks from region_s[i]
-  uint32_t qbase;            // score field s = q - qbase
-  uint32_t grid;
-  int ok;                    // 0: the batch does not fit -> another kernel
-};
-
-WtilePlan wtile_plan(uint32_t len_cap, uint32_t batch_max_len, int adapters, int sm_count, uint32_t smem_optin,
-                     uint32_t smem_reserved, uint32_t qbase);
-cudaError_t launch_wtile(const BatchView &b, const Accum &a, const AdapterSet &ad, const WtilePlan &plan,
-                         cudaStream_t stream);
-cudaError_t wtile_configure();  // opt in to the large dynamic shared memory once per device
 
 // ---- period kernel geometry (qb_period.cu; computed on the host, see period_plan) --------
 constexpr uint32_t kPeriodMaxLen = 256;  // two histogram blocks of 128 positions

@@ -1,6 +1,6 @@
 /* render.c -- see render.h.  A restatement, not a copy: tags are emitted by three small printf
  * helpers that take the whole attribute list as one format string, and the panel code is organised
- * around those; what must match the reference is the byte stream, which tests/test_host_render.py
+ * around those; what must match the reference is the byte stream, which tests/test_host_cpu.py
  * compares with the reference binary's output for every CLI combination. */
 #include "render.h"
 

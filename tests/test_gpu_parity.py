@@ -14,9 +14,9 @@ import qb_testutil as util
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [capi.KERNEL_SIMPLE, capi.KERNEL_FUSED, capi.KERNEL_WTILE]
-SMEM_KERNELS = [capi.KERNEL_FUSED, capi.KERNEL_WTILE]
-KNAME = {capi.KERNEL_SIMPLE: "simple", capi.KERNEL_FUSED: "fused", capi.KERNEL_WTILE: "wtile"}
+KERNELS = [capi.KERNEL_SIMPLE, capi.KERNEL_FUSED]
+SMEM_KERNELS = [capi.KERNEL_FUSED]
+KNAME = {capi.KERNEL_SIMPLE: "simple", capi.KERNEL_FUSED: "fused"}
 
 
 @pytest.fixture(scope="module")
@@ -212,13 +212,8 @@ def test_auto_takes_the_flat_kernel_for_ragged_batches(table, keys):
     util.assert_same(got, po.accumulate_batch(*batch, table), "auto ragged")
 
 
-WTILE_MAX_LEN = 192   # the warp-tile kernel's shared-memory histogram; longer batches take the fused kernel
-
-
 def run_gpu(batch, len_cap, keys, kernel, resident=False, **kw):
     seq, qual, off, lens = batch
-    if kernel == capi.KERNEL_WTILE and len(lens) and min(int(lens.max()), len_cap) > WTILE_MAX_LEN:
-        pytest.skip("batch beyond the warp-tile kernel's 192-bp histogram (AUTO picks the fused kernel)")
     with capi.Context(len_cap, adapter_keys=keys, kernel=kernel, **kw) as ctx:
         if resident:
             b = ctx.upload(seq, qual, off, lens, max_len=int(lens.max()) if len(lens) else 0)
@@ -345,7 +340,7 @@ def test_linearity_and_generator_full_size(keys, table):
     properties (running the batch twice doubles every count; per-position content and score sums equal
     the number of reads that long) and against the oracle on the first 100 k reads."""
     n = 2_000_000
-    with capi.Context(150, adapter_keys=keys, kernel=capi.KERNEL_WTILE) as ctx:
+    with capi.Context(150, adapter_keys=keys, kernel=capi.KERNEL_FUSED) as ctx:
         b = ctx.generate(2, 1, 0, n, 150, 150, 0.1)
         b.run(0)
         r1 = ctx.finish(0)

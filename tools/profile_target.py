@@ -16,7 +16,7 @@ lmin = int(sys.argv[3]) if len(sys.argv) > 3 else 150
 lmax = int(sys.argv[4]) if len(sys.argv) > 4 else 150
 launches = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 keys = np.concatenate([capi.adapter_record_keys(r) for r in util.adapter_records()]) if ad else None
-with capi.Context(max(lmax, 11), adapter_keys=keys, kernel=int(os.environ.get("QB_PROFILE_KERNEL", capi.KERNEL_WTILE))) as ctx:
+with capi.Context(max(lmax, 11), adapter_keys=keys, kernel=int(os.environ.get("QB_PROFILE_KERNEL", capi.KERNEL_AUTO))) as ctx:
     b = ctx.generate(2, 1, 0, n, lmin, lmax, 0.1)
     for _ in range(launches):
         b.run(0)

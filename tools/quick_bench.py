@@ -13,10 +13,10 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import qb_testutil as util
 
 HBM = 6545.3
-KN = {capi.KERNEL_SIMPLE: "simple", capi.KERNEL_FUSED: "fused", capi.KERNEL_WTILE: "wtile", capi.KERNEL_PERIOD: "period",
+KN = {capi.KERNEL_SIMPLE: "simple", capi.KERNEL_FUSED: "fused", capi.KERNEL_PERIOD: "period",
       capi.KERNEL_AUTO: "auto", capi.KERNEL_FLAT: "flat"}
 # QB_QUICK_KERNELS=3,2 restricts the sweep (default: wtile, fused, simple)
-KSEL = [int(k) for k in os.environ.get("QB_QUICK_KERNELS", "3,2,1").split(",")]
+KSEL = [int(k) for k in os.environ.get("QB_QUICK_KERNELS", "0,2,1").split(",")]
 
 
 def main():
