@@ -105,7 +105,7 @@ def test_period_rejects_ragged(keys):
 
 
 # ---- flat kernel (v6): ragged batches of back-to-back reads of 16..320 bp ----
-FLAT_SHAPES = [(35, 300, 304), (16, 40, 40), (16, 320, 320), (100, 151, 151), (150, 150, 150), (17, 17, 64), (299, 304, 304),
+FLAT_SHAPES = [(35, 300, 304), (16, 40, 40), (16, 304, 304), (100, 151, 151), (150, 150, 150), (17, 17, 64), (299, 304, 304),
                (64, 64, 64), (48, 96, 96)]
 
 
@@ -128,6 +128,12 @@ def test_flat_small_chunks(chunk, monkeypatch, table, keys):
         batch = util.random_batch(int(chunk) + lmin, 20000, lmin, lmax, plant=0.3)
         got = run_gpu(batch, 304, keys, capi.KERNEL_FLAT, resident=True)
         util.assert_same(got, po.accumulate_batch(*batch, table), f"flat chunk {chunk} {lmin}-{lmax}")
+
+
+def test_flat_longest_reads(table):
+    """Up to 320 bp without -a; with -a the packed codes and first hits take the room of the last 16 positions."""
+    batch = util.random_batch(320, 20000, 16, 320)
+    util.assert_same(run_gpu(batch, 320, None, capi.KERNEL_FLAT), po.accumulate_batch(*batch, None), "flat 16-320")
 
 
 def test_flat_tiny_batches(table, keys):

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Host decode throughput: inflate + framing + packing of one synthetic
-150-bp FASTQ file, no GPU involved.  gzip file through gzread() (the reference's path, quack.c:187) against
-the same reads as a BGZF file through the reader's inflate pool at 1..N threads.  One JSON line per run.
-usage: decode_bench.py [n_reads] [max_threads]"""
+150-bp FASTQ file, no GPU involved.  gzip file (members of 16 MiB of text, written by quack_b200/bin/qb_gen_fastq)
+through gzread() (the reference's path, quack.c:187) against the member pool at 2..N threads, and the same reads as
+a BGZF file through the block pool.  One JSON line per run.   usage: decode_bench.py [n_reads] [max_threads]"""
 import json
 import os
 import sys
@@ -15,9 +15,13 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
 tmax = int(sys.argv[2]) if len(sys.argv) > 2 else (os.cpu_count() or 8)
 with tempfile.TemporaryDirectory() as d:
     gz, bg = os.path.join(d, "s.fq.gz"), os.path.join(d, "s.fq.bgz")
-    text = synth.write_fastq(gz, 2, 1, n, 150, 0.1, gz_level=1)
-    synth.write_fastq(bg, 2, 1, n, 150, 0.1, gz_level=1, bgzf=True)
-    runs = [("gzip/gzread", gz, 1)] + [("bgzf/pool", bg, t) for t in (1, 2, 4, 8, 12, 16, 24, 32) if t <= tmax]
+    import subprocess
+    from quack_b200.build import gen_bin
+    for path, mode in ((gz, "gz"), (bg, "bgzf")):
+        subprocess.run([gen_bin(), path, "2", "1", "0", str(n), "150", "150", "0.1", mode, "1"], check=True)
+    text = n * (14 + 150 + 3 + 150 + 1)
+    ts = [t for t in (2, 4, 8, 12, 16, 24, 32) if t <= tmax]
+    runs = [("gzip/gzread", gz, 1)] + [("gzip/member pool", gz, t) for t in ts] + [("bgzf/pool", bg, t) for t in ts]
     base = None
     for name, path, t in runs:
         best = None
