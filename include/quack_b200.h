@@ -46,7 +46,9 @@ typedef enum {
   QB_ERR_ARG = -3,         /* bad argument */
   QB_ERR_CAPACITY = -4,    /* batch exceeds the ring slot, or a read exceeds len_cap */
   QB_ERR_NOMEM = -5,
-  QB_ERR_LAYOUT = -6       /* offsets not ascending / reads overlap */
+  QB_ERR_LAYOUT = -6,      /* offsets not ascending / reads overlap */
+  QB_ERR_TEXT = -7         /* text path: the FASTQ text is not canonical 4-line records (or a record is longer than the
+                              carry buffer): nothing of that mate's text is reliable, use the host reader instead */
 } qb_status;
 
 typedef enum {
@@ -120,6 +122,28 @@ int qb_accumulate_host(qb_ctx *ctx, int mate, const uint8_t *seq, const uint8_t 
                        const uint32_t *offset, const uint32_t *length, uint64_t n_reads);
 /* Waits for all queued work of every device. */
 int qb_sync(qb_ctx *ctx);
+
+/* ---- text path: the DEVICE frames the records (replaces kseq_read(), klib/kseq.h:177-218, for canonical FASTQ) ----
+ * The host hands over decompressed FASTQ text in chunks cut ANYWHERE (no framing on the host, one host-to-device copy
+ * per chunk); the device finds the line ends, checks that every four lines are a canonical record ('@' line, one
+ * sequence line, '+' line, one quality line of the same length, no '\r'), packs bases and quality bytes and runs
+ * the statistics kernels on them.  A record that straddles two chunks is completed with the next chunk (the chunks
+ * of a mate must be submitted in stream order, from one thread).  Text that is not canonical -- multi-line records,
+ * blank lines, FASTA, garbage in front of the first header, CR LF -- makes qb_finish() of that mate fail with
+ * QB_ERR_TEXT: the caller then counts the stream through qb_acquire/qb_submit and a reader with the full kseq
+ * semantics (host/fq_reader.c).  One device per context. */
+typedef struct {
+  uint8_t *text;              /* pinned host buffer for the chunk */
+  uint64_t cap_bytes;
+  int device_index;
+  int slot;
+} qb_text;
+int qb_text_acquire(qb_ctx *ctx, qb_text *out);
+/* last != 0: the stream ends with this chunk (the caller appends a '\n' if the file does not end with one). */
+int qb_text_submit(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, int last);
+/* After qb_sync()/qb_finish(): records framed so far, and the bytes that were left behind the last complete record
+ * when the stream ended (!= 0: truncated record -- kseq_read() returns -2 there and quack stops, quack.c:193). */
+int qb_text_status(qb_ctx *ctx, int mate, uint64_t *n_reads, uint64_t *tail_bytes);
 
 /* ---- result (what read_fastq() returns, quack.c:222-227) ---- */
 /* Synchronises, sums the per-device accumulators (one NCCL reduce to the first device / rank 0

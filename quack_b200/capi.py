@@ -37,6 +37,10 @@ class QbBatch(C.Structure):
     ]
 
 
+class QbText(C.Structure):
+    _fields_ = [("text", C.POINTER(C.c_uint8)), ("cap_bytes", C.c_uint64), ("device_index", C.c_int), ("slot", C.c_int)]
+
+
 class QbError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"quack_b200 error {code}: {msg}")
@@ -66,6 +70,11 @@ def lib() -> C.CDLL:
     L.qb_submit_from.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_uint32, C.c_uint64, C.c_uint32]
     L.qb_accumulate_host.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_uint64]
     L.qb_sync.argtypes = [vp]
+    L.qb_text_acquire.argtypes = [vp, C.POINTER(QbText)]
+    L.qb_text_submit.argtypes = [vp, C.POINTER(QbText), C.c_int, C.c_uint64, C.c_int]
+    L.qb_text_status.argtypes = [vp, C.c_int, _u64p, _u64p]
+    L.fqr_read_raw.argtypes = [vp, vp, C.c_size_t]
+    L.fqr_read_raw.restype = C.c_long
     L.qb_finish.argtypes = [vp, C.c_int, vp, C.c_uint64, _u64p, _u64p]
     L.qb_reset.argtypes = [vp, C.c_int]
     L.qb_invalid_quality_count.argtypes = [vp, C.c_int, _u64p]
@@ -244,6 +253,35 @@ class Context:
         length = np.ascontiguousarray(length, dtype=np.uint32)
         self._chk(lib().qb_accumulate_host(self.h, mate, seq.ctypes.data, qual.ctypes.data, offset.ctypes.data,
                                            length.ctypes.data, len(offset)))
+
+    def text_accumulate(self, mate: int, text: bytes, cuts=None):
+        """FASTQ text framed on the device (qb_text_submit).  cuts: ascending byte positions where the text is cut
+        into chunks (default: the slot capacity); the last chunk ends the stream."""
+        L = lib()
+        t = QbText()
+        self._chk(L.qb_text_acquire(self._h, C.byref(t)))
+        cap = int(t.cap_bytes)
+        edges = [0]
+        for b in sorted(set(int(c) for c in (cuts or []) if 0 < c < len(text))) + [len(text)]:
+            while b - edges[-1] > cap:
+                edges.append(edges[-1] + cap)
+            if b > edges[-1]:
+                edges.append(b)
+        if len(edges) == 1:
+            edges.append(len(text))
+        for i in range(len(edges) - 1):
+            a, b = edges[i], edges[i + 1]
+            if i:
+                self._chk(L.qb_text_acquire(self._h, C.byref(t)))
+            C.memmove(t.text, text[a:b], b - a)
+            self._chk(L.qb_text_submit(self._h, C.byref(t), mate, b - a, 1 if i == len(edges) - 2 else 0))
+
+    def text_status(self, mate: int = 0):
+        """(records framed, bytes left behind the last complete record); raises QbError(QB_ERR_TEXT) for text the
+        device does not frame."""
+        n, tail = C.c_uint64(0), C.c_uint64(0)
+        self._chk(lib().qb_text_status(self._h, mate, C.byref(n), C.byref(tail)))
+        return int(n.value), int(tail.value)
 
     def sync(self):
         self._chk(lib().qb_sync(self.h))

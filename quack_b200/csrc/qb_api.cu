@@ -78,9 +78,19 @@ struct Slot {
   // Ownership (guarded by qb_ctx::mu).  FREE: nobody uses the buffers.  HELD: a host thread got the slot from
   // qb_acquire()/qb_submit_from() and may write its pinned buffers; no other thread is ever handed it.  PENDING:
   // submitted; copies and the kernel are queued behind `done`, the next owner waits for that event first.
-  enum State { FREE = 0, HELD = 1, PENDING = 2 };
+  // DEFERRED (text path): the device is framing the slot's text; the statistics kernel is launched by the host
+  // once the chunk summary (number of reads, read lengths) has arrived -- flush_deferred() -- and only then the slot
+  // turns PENDING.
+  enum State { FREE = 0, HELD = 1, PENDING = 2, DEFERRED = 3, FLUSHING = 4 };  // FLUSHING: one thread is inside flush_deferred()
   State state = FREE;
   uint64_t seq = 0;  // submit order, so that the oldest pending slot is recycled first
+  // text path (qb_text_acquire / qb_text_submit), allocated at its first use
+  uint8_t *h_text = nullptr, *d_text = nullptr;
+  uint32_t *d_scratch = nullptr;
+  qb::TextSummary *h_sum = nullptr, *d_sum = nullptr;
+  cudaEvent_t framed = nullptr;
+  int text_mate = -1;
+  int text_last = 0;
 };
 
 struct Device {
@@ -99,6 +109,18 @@ struct Device {
   ncclComm_t comm = nullptr;  // in-process communicator (n_devices > 1)
   uint32_t *l2_scratch = nullptr;
   size_t l2_words = 0;
+  // text path: per mate the framing state, two carry buffers that take turns, the event of the last framed chunk
+  struct TextMate {
+    qb::TextState *d_state = nullptr;
+    uint8_t *d_carry[2] = {nullptr, nullptr};
+    int cur = 0;
+    cudaEvent_t last_framed = nullptr;
+    int deferred_slot = -1;
+    int invalid = 0;        // a chunk was not canonical FASTQ (or a record outgrew the carry): use the host reader
+    uint64_t tail_at_end = 0;  // bytes behind the last complete record when the stream ended
+    uint64_t reads = 0;
+  };
+  std::vector<TextMate> text;
 };
 
 }  // namespace
@@ -120,6 +142,7 @@ struct qb_ctx {
   uint32_t cur_cap = 0;
   size_t acc_u64 = 0;  // cur_cap*97 + counters, per mate
   std::atomic<bool> result_valid{false};  // h_result holds the reduced accumulators of every mate (qb_finish)
+  std::mutex text_mu;                     // text path set-up
   qb::AdapterSet ad_host_template{};
   uint32_t n_anchors = 0;     // distinct 7-mer anchors of the adapter set
   double anchor_density = 0;  // n_anchors / 2^14: filter pass rate per probe on random bases
@@ -575,6 +598,17 @@ void qb_destroy(qb_ctx *ctx) {
       cudaFree(s.d_tiles);
       if (s.stream) cudaStreamDestroy(s.stream);
       if (s.done) cudaEventDestroy(s.done);
+      if (s.h_text) cudaFreeHost(s.h_text);
+      cudaFree(s.d_text);
+      cudaFree(s.d_scratch);
+      if (s.h_sum) cudaFreeHost(s.h_sum);
+      cudaFree(s.d_sum);
+      if (s.framed) cudaEventDestroy(s.framed);
+    }
+    for (auto &m : d.text) {
+      cudaFree(m.d_state);
+      cudaFree(m.d_carry[0]);
+      cudaFree(m.d_carry[1]);
     }
     cudaFree(d.acc_all);
     cudaFree(d.reduce_buf);
@@ -593,6 +627,10 @@ void qb_destroy(qb_ctx *ctx) {
   }
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
   delete ctx;
+}
+
+namespace {
+int flush_deferred(qb_ctx *ctx, int si);
 }
 
 // Hands the calling thread a slot nobody else holds: the next FREE slot in round-robin order over devices x ring,
@@ -624,6 +662,17 @@ static int take_slot(qb_ctx *ctx, int *dev_index, int *slot_index) {
         wait_event = true;
       }
       if (di >= 0) break;
+      // nothing free and nothing pending: a chunk of the text path may be waiting for its statistics launch
+      int deferred = -1;
+      for (size_t i = 0; i < ctx->dev[0].slots.size() && !ctx->dev[0].text.empty(); i++)
+        if (ctx->dev[0].slots[i].state == Slot::DEFERRED) deferred = (int)i;
+      if (deferred >= 0) {
+        lk.unlock();
+        const int frc = flush_deferred(ctx, deferred);
+        lk.lock();
+        if (frc) return frc;
+        continue;
+      }
       ctx->cv_slot.wait(lk);
     }
     ctx->dev[di].slots[si].state = Slot::HELD;
@@ -800,8 +849,190 @@ int qb_accumulate_host(qb_ctx *ctx, int mate, const uint8_t *seq, const uint8_t 
   return QB_OK;
 }
 
+// ---------------------------------------------------------------------- text path (device framing)
+
+namespace {
+constexpr uint32_t kTextCarry = 1u << 20;  // a record (4 lines) must fit: reads of up to ~500 kbp
+
+// [carry | chunk] holds at most 2 x batch_bytes of text, so the packed bases (fewer than half of a record's text) fit the slot
+uint32_t text_carry_cap(const qb_ctx *ctx) { return (uint32_t)std::min<uint64_t>(kTextCarry, ctx->cfg.batch_bytes / 2); }
+uint32_t text_cap(const qb_ctx *ctx) {
+  const uint64_t c = 2ull * ctx->cfg.batch_bytes - text_carry_cap(ctx);
+  return (uint32_t)std::min<uint64_t>(c, 0xE0000000ull);
+}
+uint32_t text_nl_cap(const qb_ctx *ctx) { return 4u * ctx->cfg.batch_reads + 16u; }
+
+int text_setup(qb_ctx *ctx) {  // once per context: per-mate state, per-slot text buffers
+  std::lock_guard<std::mutex> lk(ctx->text_mu);
+  Device &d = ctx->dev[0];
+  if (!d.text.empty()) return QB_OK;
+  if (ctx->dev.size() != 1) return fail(ctx, QB_ERR_ARG, "the text path needs a one-device context");
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  std::vector<Device::TextMate> tm(ctx->cfg.n_mates);
+  for (auto &m : tm) {
+    QB_CUDA(ctx, cudaMalloc(&m.d_state, sizeof(qb::TextState)));
+    QB_CUDA(ctx, cudaMemset(m.d_state, 0, sizeof(qb::TextState)));
+    for (int k = 0; k < 2; k++) QB_CUDA(ctx, cudaMalloc(&m.d_carry[k], kTextCarry + 64));
+  }
+  const size_t words = qb::text_scratch_words(text_cap(ctx), text_carry_cap(ctx), text_nl_cap(ctx), ctx->cfg.batch_reads);
+  for (Slot &s : d.slots) {
+    QB_CUDA(ctx, cudaHostAlloc(&s.h_text, (size_t)text_cap(ctx) + 64, cudaHostAllocDefault));
+    QB_CUDA(ctx, cudaMalloc(&s.d_text, (size_t)text_cap(ctx) + 64));
+    QB_CUDA(ctx, cudaMalloc(&s.d_scratch, words * 4));
+    QB_CUDA(ctx, cudaHostAlloc(&s.h_sum, sizeof(qb::TextSummary), cudaHostAllocDefault));
+    QB_CUDA(ctx, cudaMalloc(&s.d_sum, sizeof(qb::TextSummary)));
+    QB_CUDA(ctx, cudaEventCreateWithFlags(&s.framed, cudaEventDisableTiming));
+  }
+  d.text.swap(tm);
+  return QB_OK;
+}
+
+// the chunk of a DEFERRED slot is framed: read its summary, launch the statistics kernel, the slot turns PENDING
+int flush_deferred(qb_ctx *ctx, int si) {
+  Device &d = ctx->dev[0];
+  Slot &s = d.slots[si];
+  {  // any thread may flush any deferred slot (its owner, or one that needs a slot): exactly one of them does
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    while (s.state == Slot::FLUSHING) ctx->cv_slot.wait(lk);
+    if (s.state != Slot::DEFERRED) return QB_OK;
+    s.state = Slot::FLUSHING;
+  }
+  cudaError_t ce = cudaSetDevice(d.id);
+  if (ce == cudaSuccess) ce = cudaEventSynchronize(s.framed);
+  if (ce != cudaSuccess) {
+    {
+      std::lock_guard<std::mutex> lk(ctx->mu);
+      s.state = Slot::FREE;
+      d.text[s.text_mate].invalid = 1;
+    }
+    ctx->cv_slot.notify_all();
+    return fail(ctx, QB_ERR_CUDA, "framing failed: %s", cudaGetErrorString(ce));
+  }
+  const qb::TextSummary sum = *s.h_sum;
+  Device::TextMate &m = d.text[s.text_mate];
+  int rc = QB_OK;
+  if (!sum.valid) {
+    m.invalid = 1;
+  } else {
+    m.reads += sum.n_reads;
+    if (s.text_last) m.tail_at_end = sum.tail_len;
+    if (sum.n_reads) {
+      qb::BatchView v{s.d_seq, s.d_qual, s.d_off, s.d_len, sum.n_reads, sum.n_bytes, sum.max_len, s.d_tiles,
+                      sum.min_len == sum.max_len ? sum.min_len : 0u, 0u, sum.min_len};
+      if (sum.max_len > ctx->cfg.len_cap)
+        rc = fail(ctx, QB_ERR_CAPACITY, "a read of %u bp is longer than len_cap %u", sum.max_len, ctx->cfg.len_cap);
+      else
+        rc = launch_batch(ctx, d, v, s.text_mate, s.stream);
+    }
+  }
+  cudaEventRecord(s.done, s.stream);
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    s.state = Slot::PENDING;
+    s.seq = ++ctx->submit_seq;
+    if (m.deferred_slot == si) m.deferred_slot = -1;
+  }
+  ctx->cv_slot.notify_all();
+  return rc;
+}
+
+int flush_all_deferred(qb_ctx *ctx) {
+  if (ctx->dev.empty() || ctx->dev[0].text.empty()) return QB_OK;
+  Device &d = ctx->dev[0];
+  for (size_t si = 0; si < d.slots.size(); si++) {
+    bool def;
+    {
+      std::lock_guard<std::mutex> lk(ctx->mu);
+      def = d.slots[si].state == Slot::DEFERRED || d.slots[si].state == Slot::FLUSHING;
+    }
+    if (def) {
+      const int rc = flush_deferred(ctx, (int)si);
+      if (rc) return rc;
+    }
+  }
+  return QB_OK;
+}
+}  // namespace
+
+extern "C" int qb_text_acquire(qb_ctx *ctx, qb_text *out) {
+  if (!ctx || !out) return QB_ERR_ARG;
+  int rc = text_setup(ctx);
+  if (rc) return rc;
+  int di, si;
+  if ((rc = take_slot(ctx, &di, &si))) return rc;
+  Slot &s = ctx->dev[di].slots[si];
+  out->text = s.h_text;
+  out->cap_bytes = text_cap(ctx);
+  out->device_index = di;
+  out->slot = si;
+  return QB_OK;
+}
+
+extern "C" int qb_text_submit(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, int last) {
+  int rc = check_mate(ctx, mate);
+  if (rc) return rc;
+  if (!t || t->device_index != 0 || t->slot < 0 || t->slot >= ctx->cfg.ring_depth || ctx->dev[0].text.empty())
+    return fail(ctx, QB_ERR_ARG, "bad text handle");
+  Device &d = ctx->dev[0];
+  Slot &s = d.slots[t->slot];
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (s.state != Slot::HELD || t->text != s.h_text) return fail(ctx, QB_ERR_ARG, "qb_text_submit: the slot is not held by a qb_text_acquire()");
+  }
+  if (n_bytes > text_cap(ctx)) {
+    release_slot(ctx, 0, t->slot);
+    return fail(ctx, QB_ERR_CAPACITY, "text chunk of %llu bytes exceeds the slot (%u)", (unsigned long long)n_bytes, text_cap(ctx));
+  }
+  Device::TextMate &m = d.text[mate];
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  ctx->result_valid = false;
+  if (n_bytes) QB_CUDA(ctx, cudaMemcpyAsync(s.d_text, s.h_text, n_bytes, cudaMemcpyHostToDevice, s.stream));
+  ctx->h2d_bytes += n_bytes;
+  if (m.last_framed) QB_CUDA(ctx, cudaStreamWaitEvent(s.stream, m.last_framed, 0));  // the carry comes from the chunk in front
+  const cudaError_t e = qb::launch_text_frame(s.d_text, (uint32_t)n_bytes, m.d_carry[m.cur], m.d_carry[m.cur ^ 1], text_carry_cap(ctx), m.d_state,
+                                              s.d_scratch, text_nl_cap(ctx), ctx->cfg.batch_reads, s.d_seq, s.d_qual, s.d_off, s.d_len,
+                                              (uint32_t)ctx->cfg.batch_bytes, s.d_sum, s.stream);
+  if (e != cudaSuccess) {
+    release_slot(ctx, 0, t->slot);
+    return fail(ctx, QB_ERR_CUDA, "framing launch failed: %s", cudaGetErrorString(e));
+  }
+  QB_CUDA(ctx, cudaMemcpyAsync(s.h_sum, s.d_sum, sizeof(qb::TextSummary), cudaMemcpyDeviceToHost, s.stream));
+  QB_CUDA(ctx, cudaEventRecord(s.framed, s.stream));
+  m.cur ^= 1;
+  m.last_framed = s.framed;
+  s.text_mate = mate;
+  s.text_last = last;
+  int prev;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    prev = m.deferred_slot;
+    s.state = Slot::DEFERRED;
+    m.deferred_slot = t->slot;
+  }
+  // the chunk in front of this one is framed by now (or soon): its statistics kernel runs while this chunk is copied
+  if (prev >= 0 && (rc = flush_deferred(ctx, prev))) return rc;
+  if (last) return flush_deferred(ctx, t->slot);
+  return QB_OK;
+}
+
+extern "C" int qb_text_status(qb_ctx *ctx, int mate, uint64_t *n_reads, uint64_t *tail_bytes) {
+  int rc = check_mate(ctx, mate);
+  if (rc) return rc;
+  if ((rc = flush_all_deferred(ctx))) return rc;
+  if (ctx->dev[0].text.empty()) return fail(ctx, QB_ERR_ARG, "the text path was not used");
+  const Device::TextMate &m = ctx->dev[0].text[mate];
+  if (n_reads) *n_reads = m.reads;
+  if (tail_bytes) *tail_bytes = m.tail_at_end;
+  return m.invalid ? fail(ctx, QB_ERR_TEXT, "mate %d: the text is not canonical 4-line FASTQ; count it through the host reader", mate)
+                   : QB_OK;
+}
+
 int qb_sync(qb_ctx *ctx) {
   if (!ctx) return QB_ERR_ARG;
+  {
+    const int frc = flush_all_deferred(ctx);
+    if (frc) return frc;
+  }
   uint64_t seen;  // submissions up to this one are covered by the stream synchronisation below
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -831,6 +1062,12 @@ int qb_reset(qb_ctx *ctx, int mate) {
   for (Device &d : ctx->dev) {
     QB_CUDA(ctx, cudaSetDevice(d.id));
     QB_CUDA(ctx, cudaMemset(d.acc[mate], 0, ctx->acc_u64 * 8));
+    if (!d.text.empty()) {  // a new stream starts: no carry, no error from the last one
+      QB_CUDA(ctx, cudaMemset(d.text[mate].d_state, 0, sizeof(qb::TextState)));
+      d.text[mate].invalid = 0;
+      d.text[mate].reads = d.text[mate].tail_at_end = 0;
+      d.text[mate].last_framed = nullptr;
+    }
   }
   ctx->result_valid = false;
   return QB_OK;
@@ -909,6 +1146,8 @@ int qb_finish(qb_ctx *ctx, int mate, uint64_t *rows_out, uint64_t rows_cap, uint
   int rc = check_mate(ctx, mate);
   if (rc) return rc;
   if (!ctx->result_valid && (rc = reduce_all(ctx))) return rc;
+  if (!ctx->dev[0].text.empty() && ctx->dev[0].text[mate].invalid)
+    return fail(ctx, QB_ERR_TEXT, "mate %d: the text is not canonical 4-line FASTQ; count it through the host reader", mate);
 
   const uint32_t cap = ctx->cur_cap;
   unsigned long long *rows = ctx->h_result + (size_t)mate * ctx->acc_u64;

@@ -154,6 +154,19 @@ cudaError_t launch_fused(const BatchView &b, const Accum &a, const AdapterSet &a
                          cudaStream_t stream);
 cudaError_t fused_configure();  // opt in to the large dynamic shared memory once per device
 
+// ---- on-device FASTQ framing (qb_text.cu) ------------------------------------------------
+struct TextState {
+  uint32_t tail_len, broken;
+};
+struct TextSummary {
+  uint32_t n_reads, n_bytes, min_len, max_len, valid, tail_len, n_lines, pad;
+};
+cudaError_t launch_text_frame(const uint8_t *chunk, uint32_t n_chunk, const uint8_t *carry_in, uint8_t *carry_out,
+                              uint32_t carry_cap, TextState *state, uint32_t *scratch, uint32_t nl_cap, uint32_t rec_cap,
+                              uint8_t *seq, uint8_t *qual, uint32_t *offset, uint32_t *length, uint32_t out_cap,
+                              TextSummary *sum_dev, cudaStream_t stream);
+size_t text_scratch_words(uint32_t chunk_cap, uint32_t carry_cap, uint32_t nl_cap, uint32_t rec_cap);
+
 // L2 flush helper for timing (writes `bytes` of scratch)
 cudaError_t launch_l2_flush(uint32_t *scratch, size_t words, cudaStream_t stream);
 

@@ -968,6 +968,27 @@ int fqr_fill(fqr_reader *r, uint8_t *seq, uint8_t *qual, uint32_t *offset, uint3
   return more;
 }
 
+/* Raw decompressed bytes (no framing): what the device-side framing of the text path takes (qb_text_submit). */
+long fqr_read_raw(fqr_reader *r, uint8_t *dst, size_t cap) {
+  size_t n = 0;
+  while (n < cap) {
+    if (r->begin >= r->end) {
+      const int e = refill(r);
+      if (e) {
+        if (e == -3) r->status = -3;
+        else if (r->status == 0) r->status = -1;
+        break;
+      }
+    }
+    size_t k = r->end - r->begin;
+    if (k > cap - n) k = cap - n;
+    memcpy(dst + n, r->buf + r->begin, k);
+    r->begin += k;
+    n += k;
+  }
+  return (long)n;
+}
+
 long fqr_read_adapter_keys(const char *path, uint32_t **keys_out) {
   fqr_reader *r = fqr_open(path);
   if (!r) return -1;

@@ -37,6 +37,10 @@ int fqr_status(const fqr_reader *r); /* 0 while records keep coming, else -1/-2/
  * kseq_read() code; pointers stay valid until the next call; *qual_len == 0 for FASTA records. */
 long fqr_next(fqr_reader *r, const uint8_t **seq, const uint8_t **qual, size_t *qual_len);
 
+/* Up to cap raw decompressed bytes of the stream, no framing (for the device-side framing, qb_text_submit).  Returns
+ * the number of bytes written; fewer than cap: the stream ended (fqr_status() says how: -1 clean, -3 damaged). */
+long fqr_read_raw(fqr_reader *r, uint8_t *dst, size_t cap);
+
 /* bytes of decompressed input consumed so far, and seconds spent inside gzread() -- or, with a BGZF pool,
  * waiting for the pool's next block (host gzip decode, reported separately from the statistics path as
  * BASELINE.json asks) */

@@ -14,12 +14,15 @@
  *                       and grow with the longest read seen, so the limit costs nothing until it is needed)
  *   QB_KERNEL=0|1|2|3   auto | simple | fused | wtile
  *   QB_CLEAN_EXIT=1     free everything before exit (default: _exit after the SVG is flushed)
+ *   QB_DEVICE_FRAMING=1 the DEVICE frames the records (qb_text_submit): the reader threads only inflate.  Canonical
+ *                       4-line FASTQ only; on anything else the run starts over with the host reader.  Regular files.
  *   QB_STATS_JSON=path  write reads/s, bases/s and stage times there (stdout stays the SVG)
  *   QUACK_DECODE_THREADS=n  inflate threads per BGZF input file (default: half of the cores, at most 8)
  */
 #include <pthread.h>
 #include <unistd.h>
 #include <stdio.h>
+#include <sys/stat.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -108,6 +111,8 @@ struct mate_job {
   int decode_threads;
   uint32_t len_cap;
   fqr_reader *reader; /* opened before the CUDA context exists: its inflate pool works through the start-up */
+  int device_framing;
+  uint64_t text_bytes_sent;
 };
 
 /* reader thread of one mate: inflate + frame + pack + submit, until the stream ends */
@@ -116,6 +121,20 @@ static void *mate_thread(void *arg) {
   const double t0 = now_s();
   fqr_reader *r = j->reader;
   int more = 1;
+  if (j->device_framing) { /* raw text to the device, which frames it */
+    int last_byte = '\n';
+    while (more) {
+      qb_text t;
+      if ((j->rc = qb_text_acquire(j->ctx, &t))) break;
+      long n = fqr_read_raw(r, t.text, (size_t)t.cap_bytes - 1);
+      more = fqr_status(r) == 0;
+      if (n > 0) last_byte = t.text[n - 1];
+      if (!more && last_byte != '\n') t.text[n++] = '\n'; /* kseq takes the end of the stream for a line end */
+      j->text_bytes_sent += (uint64_t)n;
+      if ((j->rc = qb_text_submit(j->ctx, &t, j->mate, (uint64_t)n, !more))) break;
+    }
+    more = 0;
+  }
   while (more) {
     qb_batch b;
     if ((j->rc = qb_acquire(j->ctx, &b))) break;
@@ -179,43 +198,75 @@ int main(int argc, char **argv) {
    * runs ahead of the framing code by up to a few hundred MiB, so the ~0.5 s the CUDA context, the pinned ring and
    * the kernel images take to come up are spent inflating instead of waiting. */
   struct mate_job jobs[2];
-  memset(jobs, 0, sizeof jobs);
   const int n_mates = paired ? 2 : 1;
-  for (int m = 0; m < n_mates; m++) {
-    jobs[m].path = paired ? (m == 0 ? o.forward : o.reverse) : o.unpaired;
-    jobs[m].reader = fqr_open(jobs[m].path);
-    if (!jobs[m].reader) {
-      fprintf(stderr, "quack: cannot open %s\n", jobs[m].path);
+  qb_config cfg;
+  qb_ctx *ctx = NULL;
+  double t_created = 0;
+  /* QB_DEVICE_FRAMING=1: first pass with the device framing the text; anything it does not take (not canonical
+   * 4-line FASTQ, a partial record at the end) starts the run over with the host reader, so only for regular files */
+  int device_framing = env_long("QB_DEVICE_FRAMING", 0) != 0;
+  for (int m = 0; m < n_mates && device_framing; m++) {
+    struct stat sb;
+    const char *p = paired ? (m == 0 ? o.forward : o.reverse) : o.unpaired;
+    if (stat(p, &sb) != 0 || !S_ISREG(sb.st_mode)) device_framing = 0;
+  }
+  for (;;) {
+    memset(jobs, 0, sizeof jobs);
+    for (int m = 0; m < n_mates; m++) {
+      jobs[m].path = paired ? (m == 0 ? o.forward : o.reverse) : o.unpaired;
+      jobs[m].reader = fqr_open(jobs[m].path);
+      if (!jobs[m].reader) {
+        fprintf(stderr, "quack: cannot open %s\n", jobs[m].path);
+        return 2;
+      }
+    }
+
+    memset(&cfg, 0, sizeof cfg);
+    cfg.n_devices = device_framing ? 1 : (int)env_long("QB_DEVICES", 1);
+    cfg.len_cap = (uint32_t)env_long("QB_LEN_CAP", 1 << 20);
+    cfg.n_mates = paired ? 2 : 1;
+    cfg.adapters_enabled = adapters;
+    cfg.adapter_keys = keys;
+    cfg.n_adapter_keys = (uint32_t)n_keys;
+    cfg.batch_bytes = (uint64_t)env_long("QB_BATCH_MB", 16) << 20; /* the program is decode-bound: small pinned ring, short start-up */
+    cfg.ring_depth = (int)env_long("QB_RING", 3);
+    cfg.kernel = (int)env_long("QB_KERNEL", QB_KERNEL_AUTO);
+    ctx = NULL;
+    if (qb_create(&cfg, &ctx)) {
+      fprintf(stderr, "quack: %s\n", qb_last_error(NULL));
       return 2;
     }
-  }
+    t_created = now_s(); /* CUDA start-up, pinned ring, accumulators: a fixed cost per process */
 
-  qb_config cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.n_devices = (int)env_long("QB_DEVICES", 1);
-  cfg.len_cap = (uint32_t)env_long("QB_LEN_CAP", 1 << 20);
-  cfg.n_mates = paired ? 2 : 1;
-  cfg.adapters_enabled = adapters;
-  cfg.adapter_keys = keys;
-  cfg.n_adapter_keys = (uint32_t)n_keys;
-  cfg.batch_bytes = (uint64_t)env_long("QB_BATCH_MB", 16) << 20; /* the program is decode-bound: small pinned ring, short start-up */
-  cfg.ring_depth = (int)env_long("QB_RING", 3);
-  cfg.kernel = (int)env_long("QB_KERNEL", QB_KERNEL_AUTO);
-  qb_ctx *ctx = NULL;
-  if (qb_create(&cfg, &ctx)) {
-    fprintf(stderr, "quack: %s\n", qb_last_error(NULL));
-    return 2;
+    pthread_t th[2];
+    for (int m = 0; m < cfg.n_mates; m++) {
+      jobs[m].ctx = ctx;
+      jobs[m].mate = m;
+      jobs[m].len_cap = cfg.len_cap;
+      jobs[m].device_framing = device_framing;
+      pthread_create(&th[m], NULL, mate_thread, &jobs[m]);
+    }
+    for (int m = 0; m < cfg.n_mates; m++) pthread_join(th[m], NULL);
+    if (device_framing) {
+      int again = 0;
+      for (int m = 0; m < cfg.n_mates; m++) {
+        uint64_t tail = 0;
+        if (jobs[m].rc == QB_ERR_TEXT) again = 1;
+        if (!jobs[m].rc) {
+          const int trc = qb_text_status(ctx, m, &jobs[m].reads, &tail);
+          if (trc == QB_ERR_TEXT || (trc == QB_OK && tail != 0) || jobs[m].stream_status != -1) again = 1;
+          else if (trc) jobs[m].rc = trc, snprintf(jobs[m].err, sizeof jobs[m].err, "%s", qb_last_error(ctx));
+        }
+      }
+      if (again) {
+        if (env_long("QB_VERBOSE", 0)) fprintf(stderr, "quack: device framing declined the input; host reader takes it\n");
+        qb_destroy(ctx);
+        device_framing = 0;
+        continue;
+      }
+    }
+    break;
   }
-  const double t_created = now_s(); /* CUDA start-up, pinned ring, accumulators: a fixed cost per process */
-
-  pthread_t th[2];
-  for (int m = 0; m < cfg.n_mates; m++) {
-    jobs[m].ctx = ctx;
-    jobs[m].mate = m;
-    jobs[m].len_cap = cfg.len_cap;
-    pthread_create(&th[m], NULL, mate_thread, &jobs[m]);
-  }
-  for (int m = 0; m < cfg.n_mates; m++) pthread_join(th[m], NULL);
   for (int m = 0; m < cfg.n_mates; m++)
     if (jobs[m].rc) {
       fprintf(stderr, "quack: %s\n", jobs[m].err[0] ? jobs[m].err : "statistics path failed");
@@ -277,6 +328,14 @@ int main(int argc, char **argv) {
       for (int m = 0; m < cfg.n_mates; m++) {
         reads += jobs[m].reads, bases += jobs[m].bases, text += jobs[m].text_bytes;
         if (jobs[m].inflate_s > inflate) inflate = jobs[m].inflate_s;
+      }
+      if (device_framing) { /* the device framed the records */
+        reads = bases = 0;
+        for (int m = 0; m < cfg.n_mates; m++) {
+          reads += data[m].n_reads;
+          for (uint64_t p = 0; p < data[m].max_length; p++) /* length_count sits in the row of the last base */
+            bases += (p + 1) * data[m].rows[p * QB_ROW_U64 + QB_COL_LENGTH];
+        }
       }
       const double stream_s = t_stream - t_start;
       fprintf(f,
