@@ -145,6 +145,23 @@ int qb_text_submit(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, in
  * when the stream ended (!= 0: truncated record -- kseq_read() returns -2 there and quack stops, quack.c:193). */
 int qb_text_status(qb_ctx *ctx, int mate, uint64_t *n_reads, uint64_t *tail_bytes);
 
+/* ---- compressed text path: the DEVICE inflates BGZF blocks (replaces the inflate inside gzread(), quack.c:160,187 ->
+ * klib/kseq.h:74,105, for block-gzipped input; block layout klib/bgzf.c:63-71, trailer 261-266) ----
+ * Same flow as qb_text_submit(), but the buffer from qb_text_acquire() is filled with WHOLE BGZF blocks as they are
+ * in the file: one warp per block inflates them on the device (stored, fixed and dynamic DEFLATE blocks; CRC-32 and
+ * ISIZE of every block are checked there), the text goes straight into the framing kernels, and the host-to-device
+ * copy carries the compressed bytes only.  The blocks of a chunk must hold at most cap_bytes of text: qb_bgzf_fit()
+ * tells how many bytes of a buffer are whole blocks that fit.  A block that does not inflate, a wrong CRC-32 or bytes
+ * that are not BGZF blocks make the mate fail with QB_ERR_TEXT like text that is not canonical: the caller then reads
+ * the file through the host reader, which reports damaged input the way the reference does. */
+int qb_bgzf_submit(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, int last);
+/* n_whole = bytes of buf[0..n_bytes) that are whole BGZF blocks holding at most text_cap_bytes of text together
+ * (n_text).  QB_ERR_TEXT: a block header is not BGZF.  Pure host code. */
+int qb_bgzf_fit(const uint8_t *buf, uint64_t n_bytes, uint64_t text_cap_bytes, uint64_t *n_whole, uint64_t *n_text);
+/* The decoder on its own: inflates whole BGZF blocks (host memory) on device 0 and copies the text back. */
+int qb_bgzf_inflate(qb_ctx *ctx, const uint8_t *comp, uint64_t n_bytes, uint8_t *text_out, uint64_t text_cap_bytes,
+                    uint64_t *n_text_out);
+
 /* ---- result (what read_fastq() returns, quack.c:222-227) ---- */
 /* Synchronises, sums the per-device accumulators (one NCCL reduce to the first device / rank 0
  * when more than one GPU took part), and copies rows[0..max_length) to rows_out in the

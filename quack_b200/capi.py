@@ -73,6 +73,9 @@ def lib() -> C.CDLL:
     L.qb_text_acquire.argtypes = [vp, C.POINTER(QbText)]
     L.qb_text_submit.argtypes = [vp, C.POINTER(QbText), C.c_int, C.c_uint64, C.c_int]
     L.qb_text_status.argtypes = [vp, C.c_int, _u64p, _u64p]
+    L.qb_bgzf_submit.argtypes = [vp, C.POINTER(QbText), C.c_int, C.c_uint64, C.c_int]
+    L.qb_bgzf_fit.argtypes = [vp, C.c_uint64, C.c_uint64, _u64p, _u64p]
+    L.qb_bgzf_inflate.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, _u64p]
     L.fqr_read_raw.argtypes = [vp, vp, C.c_size_t]
     L.fqr_read_raw.restype = C.c_long
     L.qb_finish.argtypes = [vp, C.c_int, vp, C.c_uint64, _u64p, _u64p]
@@ -259,7 +262,7 @@ class Context:
         into chunks (default: the slot capacity); the last chunk ends the stream."""
         L = lib()
         t = QbText()
-        self._chk(L.qb_text_acquire(self._h, C.byref(t)))
+        self._chk(L.qb_text_acquire(self.h, C.byref(t)))
         cap = int(t.cap_bytes)
         edges = [0]
         for b in sorted(set(int(c) for c in (cuts or []) if 0 < c < len(text))) + [len(text)]:
@@ -272,15 +275,45 @@ class Context:
         for i in range(len(edges) - 1):
             a, b = edges[i], edges[i + 1]
             if i:
-                self._chk(L.qb_text_acquire(self._h, C.byref(t)))
+                self._chk(L.qb_text_acquire(self.h, C.byref(t)))
             C.memmove(t.text, text[a:b], b - a)
-            self._chk(L.qb_text_submit(self._h, C.byref(t), mate, b - a, 1 if i == len(edges) - 2 else 0))
+            self._chk(L.qb_text_submit(self.h, C.byref(t), mate, b - a, 1 if i == len(edges) - 2 else 0))
+
+    def bgzf_accumulate(self, mate: int, comp: bytes, max_chunk: int = 0):
+        """A BGZF file's bytes, inflated and framed on the device (qb_bgzf_submit): chunks of whole blocks."""
+        L = lib()
+        t = QbText()
+        pos, first = 0, True
+        while first or pos < len(comp):
+            first = False
+            self._chk(L.qb_text_acquire(self.h, C.byref(t)))
+            cap = int(t.cap_bytes)
+            take = min(len(comp) - pos, max_chunk or cap, cap)
+            buf = comp[pos:pos + take]
+            whole, text = C.c_uint64(0), C.c_uint64(0)
+            rc = L.qb_bgzf_fit(buf, len(buf), cap, C.byref(whole), C.byref(text))
+            n = int(whole.value) if rc == 0 else len(buf)   # (a bad header: let the submit refuse it)
+            if rc == 0 and n == 0 and take < len(comp) - pos and take < cap:
+                n, buf = 0, b""                              # chunk smaller than a block: grow it
+                max_chunk = take * 2
+            C.memmove(t.text, buf, n)
+            last = pos + n >= len(comp) or (rc == 0 and n == 0 and take == len(comp) - pos)
+            self._chk(L.qb_bgzf_submit(self.h, C.byref(t), mate, n, 1 if last else 0))
+            pos += n
+            if last:
+                break
+
+    def bgzf_inflate(self, comp: bytes, text_cap: int) -> bytes:
+        out = (C.c_uint8 * max(text_cap, 1))()
+        n = C.c_uint64(0)
+        self._chk(lib().qb_bgzf_inflate(self.h, comp, len(comp), out, text_cap, C.byref(n)))
+        return C.string_at(out, int(n.value))
 
     def text_status(self, mate: int = 0):
         """(records framed, bytes left behind the last complete record); raises QbError(QB_ERR_TEXT) for text the
         device does not frame."""
         n, tail = C.c_uint64(0), C.c_uint64(0)
-        self._chk(lib().qb_text_status(self._h, mate, C.byref(n), C.byref(tail)))
+        self._chk(lib().qb_text_status(self.h, mate, C.byref(n), C.byref(tail)))
         return int(n.value), int(tail.value)
 
     def sync(self):

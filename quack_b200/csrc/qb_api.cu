@@ -89,6 +89,10 @@ struct Slot {
   uint32_t *d_scratch = nullptr;
   qb::TextSummary *h_sum = nullptr, *d_sum = nullptr;
   cudaEvent_t framed = nullptr;
+  // compressed input of the text path (qb_bgzf_submit), allocated at its first use
+  uint8_t *d_comp = nullptr;
+  qb::BgzfBlock *h_blk = nullptr, *d_blk = nullptr;
+  uint32_t *d_blk_status = nullptr, *d_bad = nullptr;
   int text_mate = -1;
   int text_last = 0;
 };
@@ -602,6 +606,10 @@ void qb_destroy(qb_ctx *ctx) {
       cudaFree(s.d_text);
       cudaFree(s.d_scratch);
       if (s.h_sum) cudaFreeHost(s.h_sum);
+      if (s.h_blk) cudaFreeHost(s.h_blk);
+      cudaFree(s.d_comp);
+      cudaFree(s.d_blk);
+      cudaFree(s.d_blk_status);
       cudaFree(s.d_sum);
       if (s.framed) cudaEventDestroy(s.framed);
     }
@@ -968,7 +976,67 @@ extern "C" int qb_text_acquire(qb_ctx *ctx, qb_text *out) {
   return QB_OK;
 }
 
-extern "C" int qb_text_submit(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, int last) {
+namespace {
+constexpr uint32_t kMaxBgzfBlocks = 1u << 16;  // per chunk
+
+int bgzf_setup(qb_ctx *ctx) {  // once per context: per-slot buffers for compressed bytes and block tables
+  std::lock_guard<std::mutex> lk(ctx->text_mu);
+  Device &d = ctx->dev[0];
+  if (d.slots[0].d_comp) return QB_OK;
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  for (Slot &s : d.slots) {
+    QB_CUDA(ctx, cudaHostAlloc(&s.h_blk, sizeof(qb::BgzfBlock) * kMaxBgzfBlocks, cudaHostAllocDefault));
+    QB_CUDA(ctx, cudaMalloc(&s.d_blk, sizeof(qb::BgzfBlock) * kMaxBgzfBlocks));
+    QB_CUDA(ctx, cudaMalloc(&s.d_blk_status, 4 * kMaxBgzfBlocks + 4));
+    s.d_bad = s.d_blk_status + kMaxBgzfBlocks;
+  }
+  for (size_t i = d.slots.size(); i-- > 0;) {  // (slot 0 last: its d_comp is the "set up" mark)
+    QB_CUDA(ctx, cudaMalloc(&d.slots[i].d_comp, (size_t)text_cap(ctx) + 64));
+    QB_CUDA(ctx, cudaMemset(d.slots[i].d_comp + text_cap(ctx), 0, 64));
+  }
+  return QB_OK;
+}
+
+// Walks the BGZF blocks at buf[0 .. n) (header: klib/bgzf.c:63-71; trailer CRC32 | ISIZE: 261-266): whole blocks only,
+// as many as fit text_cap bytes of text / max_blocks.  Returns false for anything that is not a BGZF block header.
+bool bgzf_walk(const uint8_t *buf, uint64_t n, uint64_t text_cap_bytes, uint32_t max_blocks, qb::BgzfBlock *out, uint32_t *n_blocks,
+               uint64_t *n_whole, uint64_t *n_text) {
+  uint64_t pos = 0, text = 0;
+  uint32_t nb = 0;
+  while (pos + 18 <= n && nb < max_blocks) {
+    const uint8_t *h = buf + pos;
+    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || h[3] != 4) return false;  // gzip member with FEXTRA only
+    const uint32_t xlen = h[10] | (uint32_t)h[11] << 8;
+    if (pos + 12 + xlen > n) break;
+    int bsize = -1;
+    for (uint32_t q = 12; q + 4 <= 12 + xlen;) {
+      const uint32_t slen = h[q + 2] | (uint32_t)h[q + 3] << 8;
+      if (h[q] == 'B' && h[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) bsize = h[q + 4] | (int)h[q + 5] << 8;
+      q += 4 + slen;
+    }
+    if (bsize < 0) return false;
+    const uint32_t total = (uint32_t)bsize + 1u;
+    if (total < 12 + xlen + 8) return false;
+    if (pos + total > n) break;
+    const uint8_t *tr = h + total - 8;
+    const uint32_t crc = tr[0] | (uint32_t)tr[1] << 8 | (uint32_t)tr[2] << 16 | (uint32_t)tr[3] << 24;
+    const uint32_t isize = tr[4] | (uint32_t)tr[5] << 8 | (uint32_t)tr[6] << 16 | (uint32_t)tr[7] << 24;
+    if (isize > 65536u) return false;
+    if (text + isize > text_cap_bytes) break;
+    if (out) out[nb] = qb::BgzfBlock{(uint32_t)(pos + 12 + xlen), total - 12 - xlen - 8, (uint32_t)text, isize, crc};
+    nb++;
+    text += isize;
+    pos += total;
+  }
+  *n_blocks = nb;
+  *n_whole = pos;
+  *n_text = text;
+  return true;
+}
+
+}  // namespace
+
+static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, int last, bool bgzf) {
   int rc = check_mate(ctx, mate);
   if (rc) return rc;
   if (!t || t->device_index != 0 || t->slot < 0 || t->slot >= ctx->cfg.ring_depth || ctx->dev[0].text.empty())
@@ -986,10 +1054,40 @@ extern "C" int qb_text_submit(qb_ctx *ctx, const qb_text *t, int mate, uint64_t 
   Device::TextMate &m = d.text[mate];
   QB_CUDA(ctx, cudaSetDevice(d.id));
   ctx->result_valid = false;
-  if (n_bytes) QB_CUDA(ctx, cudaMemcpyAsync(s.d_text, s.h_text, n_bytes, cudaMemcpyHostToDevice, s.stream));
+  uint64_t n_text = n_bytes;
+  if (bgzf) {
+    if ((rc = bgzf_setup(ctx))) {
+      release_slot(ctx, 0, t->slot);
+      return rc;
+    }
+    uint32_t nb = 0;
+    uint64_t whole = 0;
+    const bool ok = bgzf_walk(s.h_text, n_bytes, text_cap(ctx), kMaxBgzfBlocks, s.h_blk, &nb, &whole, &n_text);
+    if (!ok || whole != n_bytes) {
+      release_slot(ctx, 0, t->slot);
+      if (!ok) {
+        m.invalid = 1;
+        return fail(ctx, QB_ERR_TEXT, "mate %d: not a sequence of BGZF blocks", mate);
+      }
+      return fail(ctx, QB_ERR_ARG, "qb_bgzf_submit: %llu of %llu bytes are whole blocks that fit the slot (see qb_bgzf_fit)",
+                  (unsigned long long)whole, (unsigned long long)n_bytes);
+    }
+    if (n_bytes) QB_CUDA(ctx, cudaMemcpyAsync(s.d_comp, s.h_text, n_bytes, cudaMemcpyHostToDevice, s.stream));
+    if (nb) QB_CUDA(ctx, cudaMemcpyAsync(s.d_blk, s.h_blk, sizeof(qb::BgzfBlock) * nb, cudaMemcpyHostToDevice, s.stream));
+    cudaError_t e = qb::launch_inflate_bgzf(s.d_comp, s.d_blk, nb, s.d_text, s.d_bad, s.d_blk_status, s.stream);
+    if (e == cudaSuccess && m.last_framed) e = cudaStreamWaitEvent(s.stream, m.last_framed, 0);
+    if (e == cudaSuccess) e = qb::launch_inflate_merge(s.d_bad, m.d_state, s.stream);
+    if (e != cudaSuccess) {
+      release_slot(ctx, 0, t->slot);
+      return fail(ctx, QB_ERR_CUDA, "inflate launch failed: %s", cudaGetErrorString(e));
+    }
+    ctx->launches += nb ? 1 : 0;
+  } else {
+    if (n_bytes) QB_CUDA(ctx, cudaMemcpyAsync(s.d_text, s.h_text, n_bytes, cudaMemcpyHostToDevice, s.stream));
+    if (m.last_framed) QB_CUDA(ctx, cudaStreamWaitEvent(s.stream, m.last_framed, 0));  // the carry comes from the chunk in front
+  }
   ctx->h2d_bytes += n_bytes;
-  if (m.last_framed) QB_CUDA(ctx, cudaStreamWaitEvent(s.stream, m.last_framed, 0));  // the carry comes from the chunk in front
-  const cudaError_t e = qb::launch_text_frame(s.d_text, (uint32_t)n_bytes, m.d_carry[m.cur], m.d_carry[m.cur ^ 1], text_carry_cap(ctx), m.d_state,
+  const cudaError_t e = qb::launch_text_frame(s.d_text, (uint32_t)n_text, m.d_carry[m.cur], m.d_carry[m.cur ^ 1], text_carry_cap(ctx), m.d_state,
                                               s.d_scratch, text_nl_cap(ctx), ctx->cfg.batch_reads, s.d_seq, s.d_qual, s.d_off, s.d_len,
                                               (uint32_t)ctx->cfg.batch_bytes, s.d_sum, s.stream);
   if (e != cudaSuccess) {
@@ -1012,6 +1110,60 @@ extern "C" int qb_text_submit(qb_ctx *ctx, const qb_text *t, int mate, uint64_t 
   // the chunk in front of this one is framed by now (or soon): its statistics kernel runs while this chunk is copied
   if (prev >= 0 && (rc = flush_deferred(ctx, prev))) return rc;
   if (last) return flush_deferred(ctx, t->slot);
+  return QB_OK;
+}
+
+extern "C" int qb_text_submit(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, int last) {
+  return text_submit_common(ctx, t, mate, n_bytes, last, false);
+}
+
+extern "C" int qb_bgzf_submit(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, int last) {
+  return text_submit_common(ctx, t, mate, n_bytes, last, true);
+}
+
+extern "C" int qb_bgzf_fit(const uint8_t *buf, uint64_t n_bytes, uint64_t text_cap_bytes, uint64_t *n_whole, uint64_t *n_text) {
+  uint32_t nb = 0;
+  uint64_t whole = 0, text = 0;
+  if (!buf && n_bytes) return QB_ERR_ARG;
+  if (!bgzf_walk(buf, n_bytes, text_cap_bytes, kMaxBgzfBlocks, nullptr, &nb, &whole, &text)) return QB_ERR_TEXT;
+  if (n_whole) *n_whole = whole;
+  if (n_text) *n_text = text;
+  return QB_OK;
+}
+
+// Inflates whole BGZF blocks on the device and copies the text back: the decoder on its own (tests, other callers).
+extern "C" int qb_bgzf_inflate(qb_ctx *ctx, const uint8_t *comp, uint64_t n_bytes, uint8_t *text_out, uint64_t text_cap_bytes,
+                               uint64_t *n_text_out) {
+  if (!ctx || (!comp && n_bytes) || !n_text_out) return QB_ERR_ARG;
+  Device &d = ctx->dev[0];
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  std::vector<qb::BgzfBlock> blocks(kMaxBgzfBlocks);
+  uint32_t nb = 0;
+  uint64_t whole = 0, n_text = 0;
+  if (!bgzf_walk(comp, n_bytes, text_cap_bytes, kMaxBgzfBlocks, blocks.data(), &nb, &whole, &n_text) || whole != n_bytes)
+    return fail(ctx, QB_ERR_TEXT, "not a sequence of whole BGZF blocks that fit %llu bytes of text", (unsigned long long)text_cap_bytes);
+  uint8_t *d_comp = nullptr, *d_text = nullptr;
+  qb::BgzfBlock *d_blk = nullptr;
+  uint32_t *d_status = nullptr;
+  cudaError_t e = cudaMalloc(&d_comp, n_bytes + 64);
+  if (e == cudaSuccess) e = cudaMalloc(&d_text, n_text + 64);
+  if (e == cudaSuccess) e = cudaMalloc(&d_blk, sizeof(qb::BgzfBlock) * (nb + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_status, 4 * (size_t)nb + 8);
+  if (e == cudaSuccess) e = cudaMemset(d_comp + n_bytes, 0, 64);
+  if (e == cudaSuccess && n_bytes) e = cudaMemcpy(d_comp, comp, n_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && nb) e = cudaMemcpy(d_blk, blocks.data(), sizeof(qb::BgzfBlock) * nb, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = qb::launch_inflate_bgzf(d_comp, d_blk, nb, d_text, d_status + nb, d_status, d.main_stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d.main_stream);
+  std::vector<uint32_t> status(nb + 1, 0);
+  if (e == cudaSuccess) e = cudaMemcpy(status.data(), d_status, 4 * (size_t)(nb + 1), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && n_text) e = cudaMemcpy(text_out, d_text, n_text, cudaMemcpyDeviceToHost);
+  cudaFree(d_comp), cudaFree(d_text), cudaFree(d_blk), cudaFree(d_status);
+  if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "qb_bgzf_inflate: %s", cudaGetErrorString(e));
+  ctx->launches += nb ? 1 : 0;
+  *n_text_out = n_text;
+  if (status[nb])
+    for (uint32_t i = 0; i < nb; i++)
+      if (status[i]) return fail(ctx, QB_ERR_TEXT, "BGZF block %u does not inflate (check %u)", i, status[i]);
   return QB_OK;
 }
 

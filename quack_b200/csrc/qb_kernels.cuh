@@ -167,6 +167,16 @@ cudaError_t launch_text_frame(const uint8_t *chunk, uint32_t n_chunk, const uint
                               TextSummary *sum_dev, cudaStream_t stream);
 size_t text_scratch_words(uint32_t chunk_cap, uint32_t carry_cap, uint32_t nl_cap, uint32_t rec_cap);
 
+// ---- on-device inflate of BGZF blocks (qb_inflate.cu) --------------------------------------
+struct BgzfBlock {
+  uint32_t in_off, in_len;    // the raw DEFLATE stream of the block inside the chunk's compressed bytes
+  uint32_t out_off, out_len;  // where its text goes (prefix sums of ISIZE) and ISIZE
+  uint32_t crc;               // CRC-32 of the text, from the block trailer
+};
+cudaError_t launch_inflate_bgzf(const uint8_t *comp, const BgzfBlock *blocks, uint32_t n_blocks, uint8_t *text, uint32_t *bad,
+                                uint32_t *status, cudaStream_t stream);
+cudaError_t launch_inflate_merge(const uint32_t *bad, TextState *state, cudaStream_t stream);
+
 // L2 flush helper for timing (writes `bytes` of scratch)
 cudaError_t launch_l2_flush(uint32_t *scratch, size_t words, cudaStream_t stream);
 

@@ -16,12 +16,15 @@
  *   QB_CLEAN_EXIT=1     free everything before exit (default: _exit after the SVG is flushed)
  *   QB_DEVICE_FRAMING=1 the DEVICE frames the records (qb_text_submit): the reader threads only inflate.  Canonical
  *                       4-line FASTQ only; on anything else the run starts over with the host reader.  Regular files.
+ *   QB_DEVICE_INFLATE=1 BGZF files: the device also inflates (qb_bgzf_submit): the host only reads the file.  Falls back
+ *                       the same way (not BGZF -> device framing; damaged or odd input -> host reader).
  *   QB_STATS_JSON=path  write reads/s, bases/s and stage times there (stdout stays the SVG)
  *   QUACK_DECODE_THREADS=n  inflate threads per BGZF input file (default: half of the cores, at most 8)
  */
 #include <pthread.h>
 #include <unistd.h>
 #include <stdio.h>
+#include <fcntl.h>
 #include <sys/stat.h>
 #include <stdlib.h>
 #include <string.h>
@@ -111,9 +114,46 @@ struct mate_job {
   int decode_threads;
   uint32_t len_cap;
   fqr_reader *reader; /* opened before the CUDA context exists: its inflate pool works through the start-up */
-  int device_framing;
+  int device_framing; /* 1: the device frames the text; 2: it also inflates the BGZF blocks */
   uint64_t text_bytes_sent;
 };
+
+/* BGZF file, block bytes straight to the device: no inflate, no framing on the host */
+static void stream_bgzf_blocks(struct mate_job *j) {
+  const int fd = open(j->path, O_RDONLY);
+  struct stat sb;
+  if (fd < 0 || fstat(fd, &sb) != 0) {
+    j->rc = QB_ERR_TEXT;
+    if (fd >= 0) close(fd);
+    return;
+  }
+  off_t off = 0;
+  for (;;) {
+    qb_text t;
+    if ((j->rc = qb_text_acquire(j->ctx, &t))) break;
+    ssize_t got = 0;
+    while ((uint64_t)got < t.cap_bytes) { /* (pread returns at most 2 GiB - 4 KiB per call) */
+      const ssize_t k = pread(fd, t.text + got, (size_t)(t.cap_bytes - (uint64_t)got), off + got);
+      if (k <= 0) break;
+      got += k;
+    }
+    uint64_t whole = 0, text = 0;
+    const int frc = qb_bgzf_fit(t.text, (uint64_t)got, t.cap_bytes, &whole, &text);
+    const int at_end = off + (off_t)whole >= sb.st_size;
+    if (frc || (whole == 0 && !at_end)) { /* not BGZF, or a block cut short: the host reader decides what that means */
+      qb_bgzf_submit(j->ctx, &t, j->mate, 0, 1);
+      j->rc = QB_ERR_TEXT;
+      break;
+    }
+    j->text_bytes += text;
+    j->text_bytes_sent += whole;
+    if ((j->rc = qb_bgzf_submit(j->ctx, &t, j->mate, whole, at_end))) break;
+    off += (off_t)whole;
+    if (at_end) break;
+  }
+  close(fd);
+  j->stream_status = -1;
+}
 
 /* reader thread of one mate: inflate + frame + pack + submit, until the stream ends */
 static void *mate_thread(void *arg) {
@@ -121,6 +161,12 @@ static void *mate_thread(void *arg) {
   const double t0 = now_s();
   fqr_reader *r = j->reader;
   int more = 1;
+  if (j->device_framing == 2) {
+    stream_bgzf_blocks(j);
+    if (j->rc > -100 && j->rc != 0 && !j->err[0]) snprintf(j->err, sizeof j->err, "%s", qb_last_error(j->ctx));
+    j->wall_s = now_s() - t0;
+    return NULL;
+  }
   if (j->device_framing) { /* raw text to the device, which frames it */
     int last_byte = '\n';
     while (more) {
@@ -204,18 +250,25 @@ int main(int argc, char **argv) {
   double t_created = 0;
   /* QB_DEVICE_FRAMING=1: first pass with the device framing the text; anything it does not take (not canonical
    * 4-line FASTQ, a partial record at the end) starts the run over with the host reader, so only for regular files */
-  int device_framing = env_long("QB_DEVICE_FRAMING", 0) != 0;
+  int device_framing = env_long("QB_DEVICE_INFLATE", 0) != 0 ? 2 : env_long("QB_DEVICE_FRAMING", 0) != 0;
   for (int m = 0; m < n_mates && device_framing; m++) {
     struct stat sb;
     const char *p = paired ? (m == 0 ? o.forward : o.reverse) : o.unpaired;
     if (stat(p, &sb) != 0 || !S_ISREG(sb.st_mode)) device_framing = 0;
+    if (device_framing == 2) { /* BGZF? (klib/bgzf.c:63-71: gzip member with a 6-byte 'BC' extra field) */
+      unsigned char h[16] = {0};
+      FILE *f = fopen(p, "rb");
+      const size_t n = f ? fread(h, 1, sizeof h, f) : 0;
+      if (f) fclose(f);
+      if (n < 16 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || h[3] != 4 || h[12] != 'B' || h[13] != 'C') device_framing = 1;
+    }
   }
   for (;;) {
     memset(jobs, 0, sizeof jobs);
     for (int m = 0; m < n_mates; m++) {
       jobs[m].path = paired ? (m == 0 ? o.forward : o.reverse) : o.unpaired;
-      jobs[m].reader = fqr_open(jobs[m].path);
-      if (!jobs[m].reader) {
+      jobs[m].reader = device_framing == 2 ? NULL : fqr_open(jobs[m].path);
+      if (!jobs[m].reader && device_framing != 2) {
         fprintf(stderr, "quack: cannot open %s\n", jobs[m].path);
         return 2;
       }
@@ -254,7 +307,7 @@ int main(int argc, char **argv) {
         if (jobs[m].rc == QB_ERR_TEXT) again = 1;
         if (!jobs[m].rc) {
           const int trc = qb_text_status(ctx, m, &jobs[m].reads, &tail);
-          if (trc == QB_ERR_TEXT || (trc == QB_OK && tail != 0) || jobs[m].stream_status != -1) again = 1;
+          if (trc == QB_ERR_TEXT || trc == QB_ERR_ARG || (trc == QB_OK && tail != 0) || jobs[m].stream_status != -1) again = 1;
           else if (trc) jobs[m].rc = trc, snprintf(jobs[m].err, sizeof jobs[m].err, "%s", qb_last_error(ctx));
         }
       }
@@ -308,6 +361,12 @@ int main(int argc, char **argv) {
       return 2;
     }
   }
+  uint64_t framed_reads = 0, framed_bases = 0; /* (before qr_transform() turns the counts into fractions) */
+  for (int m = 0; m < cfg.n_mates; m++) {
+    framed_reads += data[m].n_reads;
+    for (uint64_t p = 0; p < data[m].max_length; p++) /* length_count sits in the row of the last base */
+      framed_bases += (p + 1) * data[m].rows[p * QB_ROW_U64 + QB_COL_LENGTH];
+  }
   const double t_finish = now_s();
 
   qr_begin_document(paired, adapters, o.name, stdout);
@@ -329,14 +388,7 @@ int main(int argc, char **argv) {
         reads += jobs[m].reads, bases += jobs[m].bases, text += jobs[m].text_bytes;
         if (jobs[m].inflate_s > inflate) inflate = jobs[m].inflate_s;
       }
-      if (device_framing) { /* the device framed the records */
-        reads = bases = 0;
-        for (int m = 0; m < cfg.n_mates; m++) {
-          reads += data[m].n_reads;
-          for (uint64_t p = 0; p < data[m].max_length; p++) /* length_count sits in the row of the last base */
-            bases += (p + 1) * data[m].rows[p * QB_ROW_U64 + QB_COL_LENGTH];
-        }
-      }
+      if (device_framing) reads = framed_reads, bases = framed_bases; /* the device framed the records */
       const double stream_s = t_stream - t_start;
       fprintf(f,
               "{\"reads\": %llu, \"bases\": %llu, \"text_bytes\": %llu, \"devices\": %d, \"launches\": %llu, "

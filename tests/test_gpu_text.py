@@ -40,7 +40,7 @@ def _run_text(text, cuts, adapters=True, len_cap=320, batch_bytes=1 << 20, ring=
         ctx.text_accumulate(0, text, cuts)
         n, tail = ctx.text_status(0)
         res = ctx.finish(0)
-        return res, n, tail, ctx.launch_count()
+        return res, n, tail, ctx.launch_count
 
 
 @pytest.mark.parametrize("shape", [(150, 150), (35, 300), (1, 40), (100, 100)], ids=lambda s: f"{s[0]}-{s[1]}")
