@@ -184,13 +184,14 @@ def e2e_file(pairs: int = 2_000_000):
             svg_ref = r.stdout
             out["reference"] = {"seconds": dt, "value": 2 * pairs / dt, "cores": 1, "input": "multi-member gzip",
                                 "program": "oracle/_ref/quack (unmodified reference, single-threaded)"}
-        for mode in ("gz", "bgzf"):
+        # third arm: the same BGZF files with the DEVICE inflating and framing (qb_bgzf_submit): the host only reads the file
+        for mode, fmode, extra_env in (("gz", "gz", {}), ("bgzf", "bgzf", {}), ("bgzf_device_inflate", "bgzf", {"QB_DEVICE_INFLATE": "1"})):
             js = os.path.join(tmp, "stats.json")
             best = None
             for _ in range(2):
-                env = dict(os.environ, QB_STATS_JSON=js)
+                env = dict(os.environ, QB_STATS_JSON=js, **extra_env)
                 t0 = time.perf_counter()
-                r = subprocess.run([QUACK_BIN, "-1", files[(mode, 1)], "-2", files[(mode, 2)], *common],
+                r = subprocess.run([QUACK_BIN, "-1", files[(fmode, 1)], "-2", files[(fmode, 2)], *common],
                                    stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
                 dt = time.perf_counter() - t0
                 if r.returncode != 0:
@@ -198,7 +199,8 @@ def e2e_file(pairs: int = 2_000_000):
                 if best is None or dt < best[0]:
                     best = (dt, r.stdout, json.load(open(js)))
             dt, svg, st = best
-            rec = {"seconds": dt, "value": 2 * pairs / dt, "input": "multi-member gzip" if mode == "gz" else "BGZF",
+            rec = {"seconds": dt, "value": 2 * pairs / dt,
+                   "input": {"gz": "multi-member gzip", "bgzf": "BGZF", "bgzf_device_inflate": "BGZF, inflated and framed on the device"}[mode],
                    "create_s": st["create_s"], "stream_s": st["stream_s"], "finish_s": st["finish_s"],
                    "render_s": st["render_s"],
                    # host gzip decode, broken out: inflate runs in a pool per file (QUACK_DECODE_THREADS), ahead of the
@@ -513,6 +515,20 @@ def bench_ours(args):
         other["config1_5_150bp_no_adapters"] = kernel_only(READ_LEN, READ_LEN, READ_LEN, False, 10_000_000)
         other["config4_ragged_35_300_no_adapters"] = kernel_only(35, 300, 304, False, 5_000_000)
         other["config4_ragged_35_300_adapters"] = kernel_only(35, 300, 304, True, 5_000_000)
+        try:    # the inflate kernel of the compressed-input path (qb_bgzf_submit): one warp per BGZF block; not an HBM-bound
+            # kernel (a serial bit stream per block: instruction-issue bound), so throughput only, no roofline fraction
+            with tempfile.TemporaryDirectory(dir=scratch_dir(2_000_000 * 400)) as tmp:
+                pth = os.path.join(tmp, "inflate.fq.gz")
+                gen_fastq(pth, 1, 0, 2_000_000, "bgzf")
+                comp = open(pth, "rb").read()
+            with capi.Context(READ_LEN, device_ids=[local_rank]) as c2:
+                ms, n_text, n_blocks = c2.bgzf_inflate_bench(comp, 5)
+            other["bgzf_inflate_150bp_level1"] = {"blocks_per_launch": n_blocks, "kernel_ms_mean": ms, "text_GBps": n_text / ms / 1e6,
+                                                  "compressed_GBps": len(comp) / ms / 1e6, "reads_per_s": 2_000_000 / ms * 1e3,
+                                                  "bound": "issue"}
+            del comp
+        except Exception as ex:
+            other["bgzf_inflate_150bp_level1"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {

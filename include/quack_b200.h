@@ -161,6 +161,10 @@ int qb_bgzf_fit(const uint8_t *buf, uint64_t n_bytes, uint64_t text_cap_bytes, u
 /* The decoder on its own: inflates whole BGZF blocks (host memory) on device 0 and copies the text back. */
 int qb_bgzf_inflate(qb_ctx *ctx, const uint8_t *comp, uint64_t n_bytes, uint8_t *text_out, uint64_t text_cap_bytes,
                     uint64_t *n_text_out);
+/* Diagnostics: the inflate kernel alone over all blocks of a buffer (< 3.7 GB of text), device-resident, CUDA-event
+ * time per launch. */
+int qb_bgzf_inflate_bench(qb_ctx *ctx, const uint8_t *comp, uint64_t n_bytes, int iters, float *ms_per_launch,
+                          uint64_t *n_text_out, uint32_t *n_blocks_out);
 
 /* ---- result (what read_fastq() returns, quack.c:222-227) ---- */
 /* Synchronises, sums the per-device accumulators (one NCCL reduce to the first device / rank 0

@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
     L.qb_bgzf_submit.argtypes = [vp, C.POINTER(QbText), C.c_int, C.c_uint64, C.c_int]
     L.qb_bgzf_fit.argtypes = [vp, C.c_uint64, C.c_uint64, _u64p, _u64p]
     L.qb_bgzf_inflate.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, _u64p]
+    L.qb_bgzf_inflate_bench.argtypes = [vp, vp, C.c_uint64, C.c_int, C.POINTER(C.c_float), _u64p, _u32p]
     L.fqr_read_raw.argtypes = [vp, vp, C.c_size_t]
     L.fqr_read_raw.restype = C.c_long
     L.qb_finish.argtypes = [vp, C.c_int, vp, C.c_uint64, _u64p, _u64p]
@@ -308,6 +309,12 @@ class Context:
         n = C.c_uint64(0)
         self._chk(lib().qb_bgzf_inflate(self.h, comp, len(comp), out, text_cap, C.byref(n)))
         return C.string_at(out, int(n.value))
+
+    def bgzf_inflate_bench(self, comp: bytes, iters: int = 5):
+        """(ms per launch, text bytes, blocks) of the inflate kernel alone."""
+        ms, n, nb = C.c_float(0), C.c_uint64(0), C.c_uint32(0)
+        self._chk(lib().qb_bgzf_inflate_bench(self.h, comp, len(comp), iters, C.byref(ms), C.byref(n), C.byref(nb)))
+        return float(ms.value), int(n.value), int(nb.value)
 
     def text_status(self, mate: int = 0):
         """(records framed, bytes left behind the last complete record); raises QbError(QB_ERR_TEXT) for text the

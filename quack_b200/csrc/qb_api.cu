@@ -1131,6 +1131,63 @@ extern "C" int qb_bgzf_fit(const uint8_t *buf, uint64_t n_bytes, uint64_t text_c
   return QB_OK;
 }
 
+// Diagnostics: the inflate kernel alone on device-resident blocks, timed with CUDA events (ms per launch).
+extern "C" int qb_bgzf_inflate_bench(qb_ctx *ctx, const uint8_t *comp, uint64_t n_bytes, int iters, float *ms_per_launch,
+                                     uint64_t *n_text_out, uint32_t *n_blocks_out) {
+  if (!ctx || !comp || iters < 1 || !ms_per_launch) return QB_ERR_ARG;
+  Device &d = ctx->dev[0];
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  std::vector<qb::BgzfBlock> blocks;
+  uint64_t pos = 0, n_text = 0;
+  while (pos < n_bytes) {  // every block of the buffer, however many
+    std::vector<qb::BgzfBlock> part(kMaxBgzfBlocks);
+    uint32_t nb = 0;
+    uint64_t whole = 0, text = 0;
+    if (!bgzf_walk(comp + pos, n_bytes - pos, 0xF0000000ull - n_text, kMaxBgzfBlocks, part.data(), &nb, &whole, &text) || whole == 0)
+      return fail(ctx, QB_ERR_TEXT, "not a sequence of whole BGZF blocks");
+    for (uint32_t i = 0; i < nb; i++) {
+      part[i].in_off += (uint32_t)pos;
+      part[i].out_off += (uint32_t)n_text;
+      blocks.push_back(part[i]);
+    }
+    pos += whole;
+    n_text += text;
+  }
+  const uint32_t nb = (uint32_t)blocks.size();
+  uint8_t *d_comp = nullptr, *d_text = nullptr;
+  qb::BgzfBlock *d_blk = nullptr;
+  uint32_t *d_status = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e = cudaMalloc(&d_comp, n_bytes + 64);
+  if (e == cudaSuccess) e = cudaMalloc(&d_text, n_text + 64);
+  if (e == cudaSuccess) e = cudaMalloc(&d_blk, sizeof(qb::BgzfBlock) * (nb + 1));
+  if (e == cudaSuccess) e = cudaMalloc(&d_status, 4 * (size_t)nb + 8);
+  if (e == cudaSuccess) e = cudaMemset(d_comp + n_bytes, 0, 64);
+  if (e == cudaSuccess) e = cudaMemcpy(d_comp, comp, n_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_blk, blocks.data(), sizeof(qb::BgzfBlock) * nb, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  for (int w = 0; w < 2 && e == cudaSuccess; w++) e = qb::launch_inflate_bgzf(d_comp, d_blk, nb, d_text, d_status + nb, d_status, d.main_stream);
+  if (e == cudaSuccess) e = cudaEventRecord(e0, d.main_stream);
+  for (int i = 0; i < iters && e == cudaSuccess; i++) e = qb::launch_inflate_bgzf(d_comp, d_blk, nb, d_text, d_status + nb, d_status, d.main_stream);
+  if (e == cudaSuccess) e = cudaEventRecord(e1, d.main_stream);
+  if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+  float ms = 0;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+  uint32_t bad = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&bad, d_status + nb, 4, cudaMemcpyDeviceToHost);
+  cudaFree(d_comp), cudaFree(d_text), cudaFree(d_blk), cudaFree(d_status);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "qb_bgzf_inflate_bench: %s", cudaGetErrorString(e));
+  if (bad) return fail(ctx, QB_ERR_TEXT, "a block does not inflate");
+  ctx->launches += (uint64_t)iters + 2;
+  *ms_per_launch = ms / (float)iters;
+  if (n_text_out) *n_text_out = n_text;
+  if (n_blocks_out) *n_blocks_out = nb;
+  return QB_OK;
+}
+
 // Inflates whole BGZF blocks on the device and copies the text back: the decoder on its own (tests, other callers).
 extern "C" int qb_bgzf_inflate(qb_ctx *ctx, const uint8_t *comp, uint64_t n_bytes, uint8_t *text_out, uint64_t text_cap_bytes,
                                uint64_t *n_text_out) {

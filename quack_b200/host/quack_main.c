@@ -128,9 +128,11 @@ static void stream_bgzf_blocks(struct mate_job *j) {
     return;
   }
   off_t off = 0;
+  double t_acq = 0, t_read = 0, t_sub = 0, t0 = now_s(), t1;
   for (;;) {
     qb_text t;
     if ((j->rc = qb_text_acquire(j->ctx, &t))) break;
+    t1 = now_s(), t_acq += t1 - t0, t0 = t1;
     ssize_t got = 0;
     while ((uint64_t)got < t.cap_bytes) { /* (pread returns at most 2 GiB - 4 KiB per call) */
       const ssize_t k = pread(fd, t.text + got, (size_t)(t.cap_bytes - (uint64_t)got), off + got);
@@ -147,11 +149,15 @@ static void stream_bgzf_blocks(struct mate_job *j) {
     }
     j->text_bytes += text;
     j->text_bytes_sent += whole;
+    t1 = now_s(), t_read += t1 - t0, t0 = t1;
     if ((j->rc = qb_bgzf_submit(j->ctx, &t, j->mate, whole, at_end))) break;
+    t1 = now_s(), t_sub += t1 - t0, t0 = t1;
     off += (off_t)whole;
     if (at_end) break;
   }
   close(fd);
+  if (getenv("QB_VERBOSE") && atoi(getenv("QB_VERBOSE")) > 1)
+    fprintf(stderr, "quack: mate %d: waiting for a slot %.3f s, reading the file %.3f s, submitting %.3f s\n", j->mate, t_acq, t_read, t_sub);
   j->stream_status = -1;
 }
 
@@ -282,7 +288,8 @@ int main(int argc, char **argv) {
     cfg.adapter_keys = keys;
     cfg.n_adapter_keys = (uint32_t)n_keys;
     cfg.batch_bytes = (uint64_t)env_long("QB_BATCH_MB", 16) << 20; /* the program is decode-bound: small pinned ring, short start-up */
-    cfg.ring_depth = (int)env_long("QB_RING", 3);
+    /* device inflate: the reader threads only copy file bytes, so more chunks in flight per mate keep the GPU busy */
+    cfg.ring_depth = (int)env_long("QB_RING", device_framing == 2 ? 6 : 3);
     cfg.kernel = (int)env_long("QB_KERNEL", QB_KERNEL_AUTO);
     ctx = NULL;
     if (qb_create(&cfg, &ctx)) {
