@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <shared_mutex>
@@ -470,8 +471,19 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
   if (cfg.batch_reads == 0) cfg.batch_reads = (uint32_t)(cfg.batch_bytes / 32 + 1);
   if (cfg.ring_depth == 0) cfg.ring_depth = 3;
   if (cfg.ring_depth < 1) return fail(nullptr, QB_ERR_ARG, "ring_depth must be >= 1");
+  // QB_CREATE_TIMING=1: where the start-up goes (stderr)
+  const bool timing = getenv("QB_CREATE_TIMING") && atoi(getenv("QB_CREATE_TIMING")) > 0;
+  auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tlast = tnow();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    const double t = tnow();
+    fprintf(stderr, "qb_create: %-28s %8.1f ms\n", what, (t - tlast) * 1e3);
+    tlast = t;
+  };
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
+  lap("cudaGetDeviceCount");
   if (ce != cudaSuccess || ndev == 0)
     return fail(nullptr, QB_ERR_CUDA, "no usable CUDA device (%s); quack_b200 has no CPU fallback",
                 ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
@@ -515,6 +527,8 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
       return QB_ERR_ARG;
     }
     QB_CREATE_CUDA(cudaSetDevice(d.id));
+    QB_CREATE_CUDA(cudaFree(nullptr));
+    lap("context (cudaSetDevice)");
     QB_CREATE_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.id));
     QB_CREATE_CUDA(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.id));
     QB_CREATE_CUDA(cudaDeviceGetAttribute(&d.smem_reserved, cudaDevAttrReservedSharedMemoryPerBlock, d.id));
@@ -524,8 +538,11 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
       std::lock_guard<std::mutex> lk(cfg_mu);
       if (d.id >= 256 || !configured[d.id]) {
         QB_CREATE_CUDA(qb::fused_configure());
+        lap("fused_configure");
         QB_CREATE_CUDA(qb::period_configure());
+        lap("period_configure");
         QB_CREATE_CUDA(qb::flat_configure());
+        lap("flat_configure");
         if (d.id < 256) configured[d.id] = true;
       }
     }
@@ -540,12 +557,14 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
         QB_CREATE_CUDA(cudaMemcpy(d.d_exact, exact.data(), exact.size() * 4, cudaMemcpyHostToDevice));
       }
     }
+    lap("adapter images");
     d.slots.resize(cfg.ring_depth);
     for (Slot &s : d.slots) {
       QB_CREATE_CUDA(cudaHostAlloc(&s.h_seq, pad_bytes(cfg.batch_bytes), cudaHostAllocDefault));
       QB_CREATE_CUDA(cudaHostAlloc(&s.h_qual, pad_bytes(cfg.batch_bytes), cudaHostAllocDefault));
       QB_CREATE_CUDA(cudaHostAlloc(&s.h_off, pad_reads(cfg.batch_reads) * 4, cudaHostAllocDefault));
       QB_CREATE_CUDA(cudaHostAlloc(&s.h_len, pad_reads(cfg.batch_reads) * 4, cudaHostAllocDefault));
+      lap("slot: pinned host buffers");
       QB_CREATE_CUDA(cudaMalloc(&s.d_seq, pad_bytes(cfg.batch_bytes)));
       QB_CREATE_CUDA(cudaMalloc(&s.d_qual, pad_bytes(cfg.batch_bytes)));
       QB_CREATE_CUDA(cudaMalloc(&s.d_off, pad_reads(cfg.batch_reads) * 4));
@@ -557,14 +576,17 @@ int qb_create(const qb_config *cfg_in, qb_ctx **out) {
       QB_CREATE_CUDA(cudaMemset(s.d_len, 0, pad_reads(cfg.batch_reads) * 4));
       QB_CREATE_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
       QB_CREATE_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+      lap("slot: device buffers");
     }
     QB_CREATE_CUDA(cudaDeviceSynchronize());
+    lap("synchronize");
   }
   if (alloc_accumulators(ctx, grown_cap(ctx, cfg.len_cap < 512u ? cfg.len_cap : 512u)) != QB_OK) {
     g_create_error = ctx->err;
     qb_destroy(ctx);
     return QB_ERR_CUDA;
   }
+  lap("accumulators");
   if (cfg.n_devices > 1) {
     std::vector<ncclComm_t> comms(cfg.n_devices);
     std::vector<int> ids(cfg.n_devices);

@@ -235,6 +235,9 @@ int main(int argc, char **argv) {
     exit(1);
   }
   const double t_start = now_s();
+  /* one GPU is used unless QB_DEVICES says otherwise: on a multi-GPU node the driver then initialises only that one
+   * (cuInit time grows with the number of visible devices) */
+  if (env_long("QB_DEVICES", 1) == 1) setenv("CUDA_VISIBLE_DEVICES", "0", 0);
 
   uint32_t *keys = NULL;
   long n_keys = 0;
