@@ -203,7 +203,8 @@ int fail(qb_ctx *ctx, int code, const char *fmt, ...) {
       return fail(ctx, QB_ERR_NCCL, "%s failed: %s (%s:%d)", #call, nccl_api()->GetErrorString(r__), __FILE__, __LINE__); \
   } while (0)
 
-inline size_t pad_bytes(uint64_t n) { return (size_t)((n + 15) & ~15ull) + 64; }
+// (the flat kernel's unpredicated loads read up to 511 bytes behind the last read: qb_flat.cu)
+inline size_t pad_bytes(uint64_t n) { return (size_t)((n + 15) & ~15ull) + 1088; }
 inline size_t pad_reads(uint32_t n) { return ((size_t)n + 3 & ~(size_t)3) + 16; }
 
 qb::AdapterSet adapter_set(const qb_ctx *ctx, const Device &d) {

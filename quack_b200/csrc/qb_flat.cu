@@ -232,22 +232,18 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
       uint32_t hm = 0;         // -a: one hit bit per step, the newest in the low bits
       uint32_t carry = 0;      // -a: codes of the previous step's last word
       uint32_t ns[4], nq[4];   // the group in flight
+      // (Loads are not predicated: a group reads up to 511 bytes behind the chunk's last word -- the next chunk's
+      // bytes, or the padding behind the batch buffers (qb_api.cu: pad_bytes); such words are never counted.)
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const bool hv = 32u * (uint32_t)u + lane < Wn;
-        ns[u] = hv ? ldg_u32(gs + 128 * u) : 0x41414141u;
-        nq[u] = hv ? ldg_u32(gq + 128 * u) : kc.qsub;
-      }
+      for (int u = 0; u < 4; u++) ns[u] = ldg_u32(gs + 128 * u), nq[u] = ldg_u32(gq + 128 * u);
       for (uint32_t st0 = 0; st0 < nst; st0 += 4u) {
         uint32_t cs[4], cq[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) cs[u] = ns[u], cq[u] = nq[u];
         gs += 512, gq += 512;
+        if (st0 + 4u < nst) {  // (warp-uniform)
 #pragma unroll
-        for (int u = 0; u < 4; u++) {  // (lanes without a word: 'A' with the lowest score, not counted)
-          const bool hv = 32u * (st0 + 4u + (uint32_t)u) + lane < Wn;
-          ns[u] = hv ? ldg_u32(gs + 128 * u) : 0x41414141u;
-          nq[u] = hv ? ldg_u32(gq + 128 * u) : kc.qsub;
+          for (int u = 0; u < 4; u++) ns[u] = ldg_u32(gs + 128 * u), nq[u] = ldg_u32(gq + 128 * u);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -259,16 +255,16 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
             const int r = (int)(run + (uint32_t)__popc(Sw & le_mask)) - 1;  // read of the word's first byte (-1: the one in front)
             run += (uint32_t)__popc(Sw);
             const uint32_t B = 4u * w;
-            const uint32_t rs = lds_u32(roff_s + 4u * (uint32_t)r), rn = lds_u32(roff_s + 4u * (uint32_t)r + 4u);
+            const uint32_t rs = lds_u32(roff_s + 4u * (uint32_t)r);
             const uint32_t pos0 = B - rs;   // position of the word's first byte in read r
-            const uint32_t e = rn - B;      // bytes of the word that belong to read r (>= 4: all)
             const bool cnt = have && B >= roff0;  // the word in front of the first own read: scan only
             const uint32_t sw = cs[u], qw = cq[u];
             uint32_t nc, cd = 0, bad = 0;
             uint32_t K = kAd ? key_bytes_c(sw, qw, kc, nc, bad, cd) : key_bytes(sw, qw, kc, nc, bad);
-            if (bad & 0xC0C0C0C0u) {  // a quality byte outside the counted window: the word byte by byte, exactly
+            if ((bad & 0xC0C0C0C0u) && cnt) {  // a quality byte outside the counted window: the word byte by byte, exactly
               K = key_bytes_bad(nc);
-              if (cnt) {
+              {
+                const uint32_t e = lds_u32(roff_s + 4u * (uint32_t)r + 4u) - B;  // bytes of the word that belong to read r (>= 4: all)
                 const bool next_ok = (uint32_t)(r + 1) < nr || last_has_next;  // read r + 1 exists
                 for (uint32_t j = 0; j < 4u; j++) {
                   const bool in_b = j >= e;
