@@ -182,6 +182,7 @@ int qb_invalid_quality_count(qb_ctx *ctx, int mate, uint64_t *out);
 /* ---- multi-process multi-GPU (one process per GPU, e.g. under torchrun) ---- */
 #define QB_NCCL_ID_BYTES 128
 int qb_nccl_unique_id(uint8_t id_out[QB_NCCL_ID_BYTES]);             /* call on rank 0, broadcast */
+/* Every rank's context must have been created with the same len_cap, n_mates and adapters_enabled. */
 int qb_comm_init_rank(qb_ctx *ctx, int n_ranks, int rank, const uint8_t id[QB_NCCL_ID_BYTES]);
 
 /* ---- device-resident batches (config 5: kernel-only sweep; bench.py `value`) ---- */

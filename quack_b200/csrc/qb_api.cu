@@ -1336,8 +1336,9 @@ static int reduce_all(qb_ctx *ctx) {
   if (rc) return rc;
   NcclApi *nc = nccl_api();
   Device &root = ctx->dev[0];
-  if (ctx->rank_comm && ctx->n_ranks > 1) {
-    // the ranks may have grown their accumulators differently: agree on the largest row count first
+  if (ctx->rank_comm && ctx->n_ranks > 1 && ctx->cur_cap < ctx->cfg.len_cap) {
+    // the ranks may have grown their accumulators differently: agree on the largest row count first.  (Not needed
+    // once the rows cover len_cap -- every rank is created with the same len_cap --, e.g. for len_cap <= 512.)
     QB_CUDA(ctx, cudaSetDevice(root.id));
     unsigned long long cap = ctx->cur_cap;
     QB_CUDA(ctx, cudaMemcpyAsync(root.d_scalar, &cap, 8, cudaMemcpyHostToDevice, root.main_stream));
