@@ -57,17 +57,54 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks and throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled while the timed region runs.  In-process NVML (nvidia-ml-py) every few
+    milliseconds: spawning nvidia-smi next to a 10 ms timed region perturbs it (its NVML start-up takes driver locks;
+    measured: +0.1-0.2 ms per 2 ms step).  nvidia-smi -lms stays as the fallback when NVML cannot be loaded."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.stop_flag = threading.Event()
+        self.nvml, self.handle, self.samples, self.mask, self.max_mhz = None, None, [], 0, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                pr = torch.cuda.get_device_properties(gpu_index)
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.handle = pynvml, h
+        except Exception:
+            self.nvml = None
+
+    def _reasons(self):
+        n = self.nvml
+        for f in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+            if hasattr(n, f):
+                return int(getattr(n, f)(self.handle))
+        return 0
 
     def run(self):
+        if self.nvml is not None:
+            while not self.stop_flag.is_set():
+                try:
+                    self.samples.append(float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+                    self.mask |= self._reasons()
+                except Exception:
+                    pass
+                self.stop_flag.wait(0.004)
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
@@ -77,9 +114,14 @@ class ClockSampler(threading.Thread):
             pass
 
     def stop(self):
+        self.stop_flag.set()
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
+        if self.nvml is not None:
+            return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": [name for name, bit in self.REASONS if self.mask & bit], "samples": len(self.samples),
+                    "source": "nvml"}
         sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = []
@@ -88,7 +130,7 @@ class ClockSampler(threading.Thread):
             if any(len(r) >= 8 and r[col].lower().startswith("active") for r in self.rows):
                 reasons.append(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------- inputs on disk

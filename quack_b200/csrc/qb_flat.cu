@@ -181,21 +181,46 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
     }
   };
 
+  // Software pipeline over the rounds, so that a chunk never starts with a chain of dependent global loads:
+  // chunk_first[] is read two rounds ahead, the chunk's first 32 read starts one round ahead (at the start of the round
+  // in front), its first group of words at the end of that round's flat pass (behind them: the per-read phases).
+  auto load_cf = [&](uint32_t cc, uint32_t &f0, uint32_t &f1) {
+    f0 = f1 = 0;
+    if (cc < n_chunks) f0 = args.chunk_first[cc], f1 = args.chunk_first[cc + 1u];
+  };
+  auto load_off = [&](uint32_t f0) -> uint32_t {  // start of read f0 + lane (the end of the batch behind the last read)
+    const uint32_t gidx = f0 + lane;
+    return gidx < args.n_reads ? args.offset[gidx] : args.batch_end;
+  };
+  uint32_t cf0, cf1, nf0, nf1;
+  load_cf(g0, cf0, cf1);
+  load_cf(g0 + G, nf0, nf1);
+  uint32_t coff = load_off(cf0);
+  uint32_t ns[4], nq[4];  // the group of four steps in flight
+  bool have_grp = false;  // ns / nq hold the first group of this round's chunk
   for (uint32_t round = 0; round < rounds; round++) {
     const uint32_t c = round * G + g0;
-    uint32_t first = 0, nr = 0;
-    if (c < n_chunks) {
-      first = args.chunk_first[c];
-      nr = args.chunk_first[c + 1u] - first;
-    }
+    const uint32_t first = cf0, nr = cf1 - cf0;
+    uint32_t ff0, ff1;
+    load_cf(c + 2u * G, ff0, ff1);
+    const uint32_t noff = load_off(nf0);
+    auto issue_next_group = [&]() {
+      have_grp = nf1 != nf0;  // (warp-uniform)
+      if (have_grp) {
+        const uint32_t ub0n = __shfl_sync(kFull, noff, 0) & ~3u;
+        const uint8_t *ps = args.seq + ub0n + lane * 4u, *pq = args.qual + ub0n + lane * 4u;
+#pragma unroll
+        for (int u = 0; u < 4; u++) ns[u] = ldg_u32(ps + 128 * u), nq[u] = ldg_u32(pq + 128 * u);
+      }
+    };
     if (nr) {  // (warp-uniform)
       // ---- the chunk's reads: starts relative to the 32-bit boundary below the first one ----
-      const uint32_t b_start = args.offset[first];
+      const uint32_t b_start = __shfl_sync(kFull, coff, 0);
       const uint32_t ub0 = b_start & ~3u;  // absolute byte of word 0
       __syncwarp();
       for (uint32_t i = lane; i <= nr + 1u; i += 32u) {
         const uint32_t gidx = first + i;
-        const uint32_t o = gidx < args.n_reads ? args.offset[gidx] : args.batch_end;
+        const uint32_t o = i < 32u ? coff : gidx < args.n_reads ? args.offset[gidx] : args.batch_end;
         f_sts_u32(roff_s + 4u * i, gidx <= args.n_reads ? o - ub0 : 0xFFFFFF00u);
       }
       if (lane == 0) f_sts_u32(roff_s - 4u, 0u);
@@ -206,6 +231,12 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
         if (w < 34u * 32u) atomicOr(shared_ptr<uint32_t>(S_s) + (w >> 5), 1u << (w & 31u));
       }
       __syncwarp();
+      // the words that straddle the first 32 read boundaries, for the fix-up behind the flat pass
+      uint32_t bsw = 0, bqw = 0;
+      if (lane < nr) {
+        const uint32_t sb = lds_u32(roff_s + 4u * (lane + 1u));
+        if (sb & 3u) bsw = ldg_u32(args.seq + ub0 + (sb & ~3u)), bqw = ldg_u32(args.qual + ub0 + (sb & ~3u));
+      }
       const uint32_t end_rel = lds_u32(roff_s + 4u * nr);  // start of the read behind the chunk / end of the batch
       const uint32_t Wn = (end_rel + 3u) >> 2;             // words whose first byte lies in front of it
       const uint32_t nst = (Wn + 31u) >> 5;
@@ -231,11 +262,12 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
       uint32_t run = 0;        // reads current in front of this step's words
       uint32_t hm = 0;         // -a: one hit bit per step, the newest in the low bits
       uint32_t carry = 0;      // -a: codes of the previous step's last word
-      uint32_t ns[4], nq[4];   // the group in flight
       // (Loads are not predicated: a group reads up to 511 bytes behind the chunk's last word -- the next chunk's
       // bytes, or the padding behind the batch buffers (qb_api.cu: pad_bytes); such words are never counted.)
+      if (!have_grp) {
 #pragma unroll
-      for (int u = 0; u < 4; u++) ns[u] = ldg_u32(gs + 128 * u), nq[u] = ldg_u32(gq + 128 * u);
+        for (int u = 0; u < 4; u++) ns[u] = ldg_u32(gs + 128 * u), nq[u] = ldg_u32(gq + 128 * u);
+      }
       for (uint32_t st0 = 0; st0 < nst; st0 += 4u) {
         uint32_t cs[4], cq[4];
 #pragma unroll
@@ -304,6 +336,7 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
         }
       }
       __syncwarp();
+      issue_next_group();
 
       // ---- per read boundary: the word that straddles it was counted for the read in front ----
       for (uint32_t i0 = 1; i0 <= nr; i0 += 32u) {
@@ -312,8 +345,8 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
           const uint32_t s = lds_u32(roff_s + 4u * i), m = s & 3u;
           if (m) {
             const uint32_t wbyte = s - m;
-            const uint32_t swd = __ldg(reinterpret_cast<const uint32_t *>(args.seq + ub0 + wbyte));
-            const uint32_t qwd = __ldg(reinterpret_cast<const uint32_t *>(args.qual + ub0 + wbyte));
+            const uint32_t swd = i0 == 1u ? bsw : ldg_u32(args.seq + ub0 + wbyte);
+            const uint32_t qwd = i0 == 1u ? bqw : ldg_u32(args.qual + ub0 + wbyte);
             if (!word_bad(qwd, kc.qsub)) {
               uint32_t ncx, badx = 0;
               const uint32_t Kw = key_bytes(swd, qwd, kc, ncx, badx);
@@ -418,7 +451,10 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
         }
         __syncwarp();
       }
+    } else {
+      issue_next_group();
     }
+    cf0 = nf0, cf1 = nf1, nf0 = ff0, nf1 = ff1, coff = noff;
     if (--to_flush == 0u && round + 1u < rounds) {  // u16 counters: flush before any bin can wrap
       to_flush = P.epoch;
       __syncthreads();

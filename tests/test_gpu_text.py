@@ -181,3 +181,32 @@ def test_cli_device_framing_same_svg(tmp_path, golden_dir):
         a = _cli(["-u", p, "-a", util.ADAPTER_FA], {})
         b = _cli(["-u", p, "-a", util.ADAPTER_FA], {"QB_DEVICE_FRAMING": "1", "QB_VERBOSE": "1"})
         assert a.returncode == b.returncode and a.stdout == b.stdout, name
+
+
+TRICKY = {   # the streams of tests/test_host_cpu.py::test_reader_tricky_streams
+    "only_garbage": b"no header here\n\n",
+    "header_at_eof": b"@",
+    "no_final_newline": b"@a\nACGT\n+\nIIII",
+    "crlf": b"@a x\r\nACGT\r\n+\r\nIIII\r\n@b\r\nAC\r\n+\r\nII\r\n",
+    "multi_line": b"@a\nAC\nGT\nAC\n+a\nII\nII\nII\n@b\nA\n+\nI\n",
+    "qual_starts_with_at": b"@a\nACGT\n+\n@III\n@b\nAC\n+\n@@\n",
+    "truncated_qual": b"@a\nACGTACGT\n+\nIII\n",
+    "qual_too_long": b"@a\nACGT\n+\nIIIIII\n@b\nAC\n+\nII\n",
+    "fasta_then_fastq": b">f\nACGT\n@a\nAC\n+\nII\n",
+    "lone_cr_line": b"@a\n\r\nAC\n+\nIII\n",
+    "plus_line_with_name": b"@a\nACGTACGTACGTA\n+a again\nIIIIIIIIIIIII\n@b\nACGTACGTACGTAC\n+\nIIIIIIIIIIIIII\n",
+    "trailing_blank_lines": b"@a\nACGTACGTACGT\n+\nIIIIIIIIIIII\n\n\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(TRICKY))
+def test_cli_device_framing_on_tricky_streams_equals_host_reader(name, tmp_path):
+    """Whatever the device makes of a stream -- frames it, or refuses and lets the host reader take it -- the program's
+    output is the one the kseq-exact host reader gives (which tests/test_host_cpu.py pins to the reference parse)."""
+    good = _text_of(*util.random_batch(4, 40, 30, 60))
+    for i, data in enumerate((TRICKY[name], good + TRICKY[name])):
+        p = tmp_path / f"{name}_{i}.fq"
+        p.write_bytes(data)
+        a = _cli(["-u", str(p), "-a", util.ADAPTER_FA], {})
+        b = _cli(["-u", str(p), "-a", util.ADAPTER_FA], {"QB_DEVICE_FRAMING": "1"})
+        assert (a.returncode, a.stdout) == (b.returncode, b.stdout), (name, i, a.stderr, b.stderr)
