@@ -31,18 +31,21 @@
 
 namespace qb {
 
-constexpr uint32_t kFMaxReads = 256;   // reads per chunk (reads >= 16 bp, a chunk spans <= 4096 bytes)
 constexpr uint32_t kFMaxSteps = 32;    // 32 words per step: 1024 words = 4096 bytes per chunk at most
 constexpr uint32_t kFQueue = 64;
-// per-warp block (bytes, multiples of 16)
-constexpr uint32_t kFoRoff = 0;                              // u32 roff[-1 .. kFMaxReads + 2]: read starts, chunk-relative
-constexpr uint32_t kFoS = kFoRoff + (kFMaxReads + 4u) * 4u;  // u32 S[34]: bit per word, set where a new read is current
-constexpr uint32_t kFoSpre = kFoS + 144u;                    // u32 Spre[34]: popcount of the words below
-constexpr uint32_t kFWarpBytesNoAd = kFoSpre + 144u;
-constexpr uint32_t kFoP = kFWarpBytesNoAd;                   // -a: u16 P[-1 .. 1026]: codes of (word - 1, word), 2 bits per base
-constexpr uint32_t kFoFhit = kFoP + 16u + kFMaxSteps * 32u * 2u + 16u;  // -a: u32 fhit[kFMaxReads]
-constexpr uint32_t kFoQ = kFoFhit + kFMaxReads * 4u;         // -a: u16 queue[kFQueue]
-constexpr uint32_t kFWarpBytesAd = kFoQ + kFQueue * 2u;
+// Per-warp block (bytes), for chunks of at most kMR reads: 256 covers reads >= 16 bp (a chunk spans <= 4096 bytes),
+// 128 reads >= 32 bp -- the smaller block lets the -a variant run 20 warps instead of 16.
+template <uint32_t kMR>
+struct FLay {
+  static constexpr uint32_t oRoff = 0;                            // u32 roff[-1 .. kMR + 2]: read starts, chunk-relative
+  static constexpr uint32_t oS = oRoff + (kMR + 4u) * 4u;         // u32 S[34]: bit per word, set where a new read is current
+  static constexpr uint32_t oSpre = oS + 144u;                    // u32 Spre[34]: popcount of the words below
+  static constexpr uint32_t bytesNoAd = oSpre + 144u;
+  static constexpr uint32_t oP = bytesNoAd;                       // -a: u16 P[-1 .. 1026]: codes of (word - 1, word), 2 bits per base
+  static constexpr uint32_t oFhit = oP + 16u + kFMaxSteps * 32u * 2u + 16u;  // -a: u32 fhit[kMR]
+  static constexpr uint32_t oQ = oFhit + kMR * 4u;                // -a: u16 queue[kFQueue]
+  static constexpr uint32_t bytesAd = oQ + kFQueue * 2u;
+};
 
 struct FArgs {
   const uint8_t *seq, *qual;   // byte 0 of the batch buffers (16-byte aligned)
@@ -93,7 +96,7 @@ __device__ __forceinline__ uint32_t ldg_u32(const uint8_t *p) {
   return v;
 }
 
-template <bool kAd, int kW>
+template <bool kAd, int kW, uint32_t kMR>
 __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant__ FArgs args) {
   constexpr uint32_t kThreads = kW * 32;
   constexpr uint32_t kFull = 0xffffffffu;
@@ -110,8 +113,9 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
   const uint32_t hist_s = smem_s + P.hist_o, lenhist_s = smem_s + P.lenhist_o, kmerhist_s = smem_s + P.kmerhist_o;
   const uint32_t afilt_s = smem_s + P.afilt_o, exact_s = smem_s + P.exact_o;
   const uint32_t wb_s = smem_s + P.wblock_o + warp * P.wblock;
-  const uint32_t roff_s = wb_s + kFoRoff + 4u;  // roff[i] at roff_s + 4 i, i = -1 .. nr + 1
-  const uint32_t S_s = wb_s + kFoS, Spre_s = wb_s + kFoSpre, P_s = wb_s + kFoP, fhit_s = wb_s + kFoFhit, q_s = wb_s + kFoQ;
+  using L = FLay<kMR>;
+  const uint32_t roff_s = wb_s + L::oRoff + 4u;  // roff[i] at roff_s + 4 i, i = -1 .. nr + 1
+  const uint32_t S_s = wb_s + L::oS, Spre_s = wb_s + L::oSpre, P_s = wb_s + L::oP, fhit_s = wb_s + L::oFhit, q_s = wb_s + L::oQ;
   const uint32_t rowbytes = P.stride * 4u, max_len = P.max_len;
 
   auto clear_counters = [&]() {
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
     if (args.ad.exact)
       for (uint32_t i = tid; i < kExactSlots; i += kThreads) ex[i] = args.ad.exact[i];
     uint32_t *fh = reinterpret_cast<uint32_t *>(gen(fhit_s));
-    for (uint32_t i = lane; i < kFMaxReads; i += 32u) fh[i] = kNoHit;
+    for (uint32_t i = lane; i < kMR; i += 32u) fh[i] = kNoHit;
   }
   __syncthreads();
 
@@ -478,15 +482,13 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
 // plan and launch
 // ------------------------------------------------------------------------------------------
 
-// warps per CTA: without -a a warp block is 1.4 KiB and the kernel needs 75 registers -> 24 warps; with -a the
-// packed codes, first hits and queue make it 4.5 KiB (and 90 registers) -> 16 warps
+// warps per CTA: without -a a warp block is 1.4 KiB and the kernel needs 68 registers -> 24 warps; with -a the packed
+// codes, first hits and queue make it 4.5 KiB -> 16 warps, or 3.5 KiB -> 20 warps when every read has >= 32 bp
+// (chunks of <= 128 reads).  The -a variant is latency-bound (issue slots 59 % busy at 16 warps): warps matter.
 #ifndef QB_FW
 #define QB_FW 24
 #endif
-#ifndef QB_FW_AD
-#define QB_FW_AD 16
-#endif
-constexpr int kFlatWarpsNoAd = QB_FW, kFlatWarpsAd = QB_FW_AD;
+constexpr int kFlatWarpsNoAd = QB_FW, kFlatWarpsAd = 16, kFlatWarpsAdShort = 20;
 
 FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters, int sm_count, uint32_t smem_optin,
                    uint32_t smem_reserved, uint32_t qbase) {
@@ -512,12 +514,6 @@ FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters,
     p.afilt_o = take(kAnchorSmemBytes);
   }
   p.exact_o = take(adapters ? kExactSlots * 4u : 0u);
-  p.wblock = adapters ? kFWarpBytesAd : kFWarpBytesNoAd;
-  p.wblock = (p.wblock + 127u) & ~127u;
-  const uint32_t warps = (uint32_t)(adapters ? kFlatWarpsAd : kFlatWarpsNoAd);
-  p.wblock_o = take(p.wblock * warps);
-  p.smem_bytes = o;
-  if (p.smem_bytes > smem_optin) return p;
   // a chunk spans its byte window plus the tail of its last read, in 32 steps of 128 bytes at most
   uint32_t cb = (kFMaxSteps * 128u - batch_max_len - 8u) & ~63u;
   if (const char *e = getenv("QB_FLAT_CHUNK")) {  // tuning hook
@@ -526,7 +522,25 @@ FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters,
   }
   p.chunk_bytes = cb;
   const uint32_t reads_per_chunk = cb / batch_min_len + 2u;
-  if (reads_per_chunk + 2u > kFMaxReads) return p;
+  if (reads_per_chunk + 2u > 256u) return p;
+  p.max_reads = reads_per_chunk + 2u <= 128u && !getenv("QB_FLAT_MR256") ? 128u : 256u;
+  uint32_t warps = (uint32_t)kFlatWarpsNoAd;
+  if (adapters) warps = p.max_reads == 128u ? (uint32_t)kFlatWarpsAdShort : (uint32_t)kFlatWarpsAd;
+  p.warps = warps;
+  p.wblock = adapters ? (p.max_reads == 128u ? FLay<128>::bytesAd : FLay<256>::bytesAd)
+                      : (p.max_reads == 128u ? FLay<128>::bytesNoAd : FLay<256>::bytesNoAd);
+  p.wblock = (p.wblock + 127u) & ~127u;
+  p.wblock_o = take(p.wblock * warps);
+  p.smem_bytes = o;
+  if (p.smem_bytes > smem_optin) {  // (the 20-warp -a variant does not fit every max_len: 16 warps then)
+    if (!(adapters && p.max_reads == 128u)) return p;
+    o = p.wblock_o;
+    p.max_reads = 256u, p.warps = warps = (uint32_t)kFlatWarpsAd;
+    p.wblock = (FLay<256>::bytesAd + 127u) & ~127u;
+    p.wblock_o = take(p.wblock * warps);
+    p.smem_bytes = o;
+    if (p.smem_bytes > smem_optin) return p;
+  }
   p.epoch = 30000u / (warps * reads_per_chunk);
   if (p.epoch == 0) p.epoch = 1;
   p.grid = (uint32_t)sm_count;
@@ -536,8 +550,10 @@ FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters,
 
 cudaError_t flat_configure() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(flat_kernel<false, kFlatWarpsNoAd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
-  return cudaFuncSetAttribute(flat_kernel<true, kFlatWarpsAd>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if ((e = cudaFuncSetAttribute(flat_kernel<false, kFlatWarpsNoAd, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+  if ((e = cudaFuncSetAttribute(flat_kernel<false, kFlatWarpsNoAd, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+  if ((e = cudaFuncSetAttribute(flat_kernel<true, kFlatWarpsAdShort, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+  return cudaFuncSetAttribute(flat_kernel<true, kFlatWarpsAd, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
 }
 
 cudaError_t launch_flat(const BatchView &b, const Accum &a, const AdapterSet &ad, const FlatPlan &plan, cudaStream_t stream) {
@@ -562,7 +578,7 @@ cudaError_t launch_flat(const BatchView &b, const Accum &a, const AdapterSet &ad
                                                                   args.n_chunks, chunk_first);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const uint32_t warps = (uint32_t)(ad.enabled ? kFlatWarpsAd : kFlatWarpsNoAd);
+  const uint32_t warps = plan.warps;
   uint32_t grid = (args.n_chunks + warps - 1u) / warps;
   if (grid > plan.grid) grid = plan.grid;
   if (grid == 0) grid = 1;
@@ -570,10 +586,14 @@ cudaError_t launch_flat(const BatchView &b, const Accum &a, const AdapterSet &ad
     const uint32_t v = (uint32_t)atoi(g);
     if (v >= 1 && v < grid) grid = v;
   }
-  if (ad.enabled)
-    flat_kernel<true, kFlatWarpsAd><<<grid, kFlatWarpsAd * 32, plan.smem_bytes, stream>>>(args);
+  if (ad.enabled && plan.max_reads == 128u)
+    flat_kernel<true, kFlatWarpsAdShort, 128><<<grid, kFlatWarpsAdShort * 32, plan.smem_bytes, stream>>>(args);
+  else if (ad.enabled)
+    flat_kernel<true, kFlatWarpsAd, 256><<<grid, kFlatWarpsAd * 32, plan.smem_bytes, stream>>>(args);
+  else if (plan.max_reads == 128u)
+    flat_kernel<false, kFlatWarpsNoAd, 128><<<grid, kFlatWarpsNoAd * 32, plan.smem_bytes, stream>>>(args);
   else
-    flat_kernel<false, kFlatWarpsNoAd><<<grid, kFlatWarpsNoAd * 32, plan.smem_bytes, stream>>>(args);
+    flat_kernel<false, kFlatWarpsNoAd, 256><<<grid, kFlatWarpsNoAd * 32, plan.smem_bytes, stream>>>(args);
   return cudaGetLastError();
 }
 

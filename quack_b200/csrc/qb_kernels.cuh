@@ -138,6 +138,7 @@ struct FlatPlan {
   uint32_t smem_base;        // shared address the dynamic shared memory must start at (checked by the kernel)
   uint32_t smem_bytes;
   uint32_t grid;
+  uint32_t warps, max_reads; // warps per CTA; reads per chunk the warp blocks are sized for (128 or 256)
   int ok;                    // 0: not a batch for this kernel
 };
 FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters, int sm_count, uint32_t smem_optin,
