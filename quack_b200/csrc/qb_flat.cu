@@ -31,15 +31,17 @@
 
 namespace qb {
 
-constexpr uint32_t kFMaxSteps = 32;    // 32 words per step: 1024 words = 4096 bytes per chunk at most
+constexpr uint32_t kFMaxSteps = 32;    // 32 words per step: 1024 words = 4096 bytes per chunk at most (-a: one hit bit per step)
+constexpr uint32_t kFLongSteps = 64;   // without -a a chunk may span 8192 bytes: half as many chunk set-ups per byte
 constexpr uint32_t kFQueue = 64;
 // Per-warp block (bytes), for chunks of at most kMR reads: 256 covers reads >= 16 bp (a chunk spans <= 4096 bytes),
 // 128 reads >= 32 bp -- the smaller block lets the -a variant run 20 warps instead of 16.
-template <uint32_t kMR>
+template <uint32_t kMR, uint32_t kMS = kFMaxSteps>
 struct FLay {
+  static constexpr uint32_t sWords = kMS + 2u;                    // words of the bit set S (one bit per word of the chunk)
   static constexpr uint32_t oRoff = 0;                            // u32 roff[-1 .. kMR + 2]: read starts, chunk-relative
-  static constexpr uint32_t oS = oRoff + (kMR + 4u) * 4u;         // u32 S[34]: bit per word, set where a new read is current
-  static constexpr uint32_t oSpre = oS + 144u;                    // u32 Spre[34]: popcount of the words below
+  static constexpr uint32_t oS = oRoff + (kMR + 4u) * 4u;         // u32 S[kMS + 2]: bit per word, set where a new read is current
+  static constexpr uint32_t oSpre = oS + ((sWords * 4u + 15u) & ~15u);  // u32 Spre[34] (-a): popcount of the words below
   static constexpr uint32_t bytesNoAd = oSpre + 144u;
   static constexpr uint32_t oP = bytesNoAd;                       // -a: u16 P[-1 .. 1026]: codes of (word - 1, word), 2 bits per base
   static constexpr uint32_t oFhit = oP + 16u + kFMaxSteps * 32u * 2u + 16u;  // -a: u32 fhit[kMR]
@@ -96,7 +98,7 @@ __device__ __forceinline__ uint32_t ldg_u32(const uint8_t *p) {
   return v;
 }
 
-template <bool kAd, int kW, uint32_t kMR>
+template <bool kAd, int kW, uint32_t kMR, uint32_t kMS>
 __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant__ FArgs args) {
   constexpr uint32_t kThreads = kW * 32;
   constexpr uint32_t kFull = 0xffffffffu;
@@ -113,7 +115,8 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
   const uint32_t hist_s = smem_s + P.hist_o, lenhist_s = smem_s + P.lenhist_o, kmerhist_s = smem_s + P.kmerhist_o;
   const uint32_t afilt_s = smem_s + P.afilt_o, exact_s = smem_s + P.exact_o;
   const uint32_t wb_s = smem_s + P.wblock_o + warp * P.wblock;
-  using L = FLay<kMR>;
+  using L = FLay<kMR, kMS>;
+  static_assert(!kAd || kMS == kFMaxSteps, "the -a path keeps one hit bit per step in a 32-bit register");
   const uint32_t roff_s = wb_s + L::oRoff + 4u;  // roff[i] at roff_s + 4 i, i = -1 .. nr + 1
   const uint32_t S_s = wb_s + L::oS, Spre_s = wb_s + L::oSpre, P_s = wb_s + L::oP, fhit_s = wb_s + L::oFhit, q_s = wb_s + L::oQ;
   const uint32_t rowbytes = P.stride * 4u, max_len = P.max_len;
@@ -228,11 +231,11 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
         f_sts_u32(roff_s + 4u * i, gidx <= args.n_reads ? o - ub0 : 0xFFFFFF00u);
       }
       if (lane == 0) f_sts_u32(roff_s - 4u, 0u);
-      for (uint32_t i = lane; i < 34u; i += 32u) f_sts_u32(S_s + 4u * i, 0u);
+      for (uint32_t i = lane; i < L::sWords; i += 32u) f_sts_u32(S_s + 4u * i, 0u);
       __syncwarp();
       for (uint32_t i = lane; i <= nr; i += 32u) {  // bit w: from word w on, read i is the current one
         const uint32_t w = (lds_u32(roff_s + 4u * i) + 3u) >> 2;
-        if (w < 34u * 32u) atomicOr(shared_ptr<uint32_t>(S_s) + (w >> 5), 1u << (w & 31u));
+        if (w < L::sWords * 32u) atomicOr(shared_ptr<uint32_t>(S_s) + (w >> 5), 1u << (w & 31u));
       }
       __syncwarp();
       // the words that straddle the first 32 read boundaries, for the fix-up behind the flat pass
@@ -515,7 +518,11 @@ FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters,
   }
   p.exact_o = take(adapters ? kExactSlots * 4u : 0u);
   // a chunk spans its byte window plus the tail of its last read, in 32 steps of 128 bytes at most
-  uint32_t cb = (kFMaxSteps * 128u - batch_max_len - 8u) & ~63u;
+  // (without -a: 64 steps when the reads are long enough for <= 256 of them per chunk)
+  p.max_steps = kFMaxSteps;
+  if (!adapters && (kFLongSteps * 128u - batch_max_len - 8u) / batch_min_len + 4u <= 256u && !getenv("QB_FLAT_STEPS32"))
+    p.max_steps = kFLongSteps;
+  uint32_t cb = (p.max_steps * 128u - batch_max_len - 8u) & ~63u;
   if (const char *e = getenv("QB_FLAT_CHUNK")) {  // tuning hook
     const uint32_t v = (uint32_t)atoi(e);
     if (v >= 512u && v < cb) cb = v;
@@ -528,7 +535,9 @@ FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters,
   if (adapters) warps = p.max_reads == 128u ? (uint32_t)kFlatWarpsAdShort : (uint32_t)kFlatWarpsAd;
   p.warps = warps;
   p.wblock = adapters ? (p.max_reads == 128u ? FLay<128>::bytesAd : FLay<256>::bytesAd)
-                      : (p.max_reads == 128u ? FLay<128>::bytesNoAd : FLay<256>::bytesNoAd);
+             : p.max_steps == kFLongSteps ? FLay<256, kFLongSteps>::bytesNoAd
+                                          : (p.max_reads == 128u ? FLay<128>::bytesNoAd : FLay<256>::bytesNoAd);
+  if (p.max_steps == kFLongSteps) p.max_reads = 256u;
   p.wblock = (p.wblock + 127u) & ~127u;
   p.wblock_o = take(p.wblock * warps);
   p.smem_bytes = o;
@@ -550,10 +559,11 @@ FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters,
 
 cudaError_t flat_configure() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(flat_kernel<false, kFlatWarpsNoAd, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
-  if ((e = cudaFuncSetAttribute(flat_kernel<false, kFlatWarpsNoAd, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
-  if ((e = cudaFuncSetAttribute(flat_kernel<true, kFlatWarpsAdShort, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
-  return cudaFuncSetAttribute(flat_kernel<true, kFlatWarpsAd, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+  if ((e = cudaFuncSetAttribute(flat_kernel<false, kFlatWarpsNoAd, 256, kFLongSteps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+  if ((e = cudaFuncSetAttribute(flat_kernel<false, kFlatWarpsNoAd, 128, kFMaxSteps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+  if ((e = cudaFuncSetAttribute(flat_kernel<false, kFlatWarpsNoAd, 256, kFMaxSteps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+  if ((e = cudaFuncSetAttribute(flat_kernel<true, kFlatWarpsAdShort, 128, kFMaxSteps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448))) return e;
+  return cudaFuncSetAttribute(flat_kernel<true, kFlatWarpsAd, 256, kFMaxSteps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
 }
 
 cudaError_t launch_flat(const BatchView &b, const Accum &a, const AdapterSet &ad, const FlatPlan &plan, cudaStream_t stream) {
@@ -587,13 +597,15 @@ cudaError_t launch_flat(const BatchView &b, const Accum &a, const AdapterSet &ad
     if (v >= 1 && v < grid) grid = v;
   }
   if (ad.enabled && plan.max_reads == 128u)
-    flat_kernel<true, kFlatWarpsAdShort, 128><<<grid, kFlatWarpsAdShort * 32, plan.smem_bytes, stream>>>(args);
+    flat_kernel<true, kFlatWarpsAdShort, 128, kFMaxSteps><<<grid, kFlatWarpsAdShort * 32, plan.smem_bytes, stream>>>(args);
   else if (ad.enabled)
-    flat_kernel<true, kFlatWarpsAd, 256><<<grid, kFlatWarpsAd * 32, plan.smem_bytes, stream>>>(args);
+    flat_kernel<true, kFlatWarpsAd, 256, kFMaxSteps><<<grid, kFlatWarpsAd * 32, plan.smem_bytes, stream>>>(args);
+  else if (plan.max_steps == kFLongSteps)
+    flat_kernel<false, kFlatWarpsNoAd, 256, kFLongSteps><<<grid, kFlatWarpsNoAd * 32, plan.smem_bytes, stream>>>(args);
   else if (plan.max_reads == 128u)
-    flat_kernel<false, kFlatWarpsNoAd, 128><<<grid, kFlatWarpsNoAd * 32, plan.smem_bytes, stream>>>(args);
+    flat_kernel<false, kFlatWarpsNoAd, 128, kFMaxSteps><<<grid, kFlatWarpsNoAd * 32, plan.smem_bytes, stream>>>(args);
   else
-    flat_kernel<false, kFlatWarpsNoAd, 256><<<grid, kFlatWarpsNoAd * 32, plan.smem_bytes, stream>>>(args);
+    flat_kernel<false, kFlatWarpsNoAd, 256, kFMaxSteps><<<grid, kFlatWarpsNoAd * 32, plan.smem_bytes, stream>>>(args);
   return cudaGetLastError();
 }
 

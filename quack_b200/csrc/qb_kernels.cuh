@@ -139,6 +139,7 @@ struct FlatPlan {
   uint32_t smem_bytes;
   uint32_t grid;
   uint32_t warps, max_reads; // warps per CTA; reads per chunk the warp blocks are sized for (128 or 256)
+  uint32_t max_steps;        // 32-word steps per chunk at most (32; 64 without -a for reads long enough)
   int ok;                    // 0: not a batch for this kernel
 };
 FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters, int sm_count, uint32_t smem_optin,
