@@ -176,6 +176,15 @@ int qb_finish(qb_ctx *ctx, int mate, uint64_t *rows_out, uint64_t rows_cap, uint
               uint64_t *n_reads);
 /* Zeroes the accumulators of one mate (all devices) so a context can be reused. */
 int qb_reset(qb_ctx *ctx, int mate);
+/* ---- opt-in side outputs that the reference does NOT compute (no reference oracle; never part of the SVG) ----
+ * qb_extras_enable(): before the first batch; every batch then takes a second, small kernel pass.
+ * qb_extras_finish(): n_count[p] = reads whose base p is 'N' or 'n' (the main result keeps folding N into A like
+ * lookup[] does, quack.c:150); qual_sum[p] = sum of (q - 33) over the reads at position p (derived from the heatmap
+ * rows); mean_hist[m], m = 0..93 = reads whose mean quality floor(sum(q - 33) / l) is m (q clamped to [33, 126]).
+ * n_count and qual_sum hold rows_cap entries (>= max_length); any of the three pointers may be NULL.  With
+ * qb_comm_init_rank() rank 0 receives the sums. */
+int qb_extras_enable(qb_ctx *ctx);
+int qb_extras_finish(qb_ctx *ctx, int mate, uint64_t *n_count, uint64_t *qual_sum, uint64_t rows_cap, uint64_t *mean_hist);
 /* Diagnostics: quality bytes outside [33,123] seen (undefined behaviour in the reference). */
 int qb_invalid_quality_count(qb_ctx *ctx, int mate, uint64_t *out);
 

@@ -62,6 +62,7 @@ def lib() -> C.CDLL:
                                           C.c_void_p, C.c_uint64, C.c_void_p]
         L.qo_read_fastq.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(_Stats)]
         L.qo_transform.argtypes = [C.POINTER(_Stats), _u64p]
+        L.qo_extras.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, _u64p, _u64p, C.c_uint64, _u64p]
         L.qo_reader_open.argtypes = [C.c_char_p]
         L.qo_reader_open.restype = C.c_void_p
         L.qo_reader_next.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
@@ -147,6 +148,19 @@ def accumulate_batch(seq, qual, offset, length, table: AdapterTable | None) -> R
     if rc:
         raise MemoryError
     return _take(st)
+
+
+def extras(seq, qual, offset, length, rows: int):
+    """PARITY UNPINNED side outputs (qo_extras): (n_count[rows], qual_sum[rows], mean_hist[94])."""
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    qual = np.ascontiguousarray(qual, dtype=np.uint8)
+    offset = np.ascontiguousarray(offset, dtype=np.uint32)
+    length = np.ascontiguousarray(length, dtype=np.uint32)
+    n_count, qual_sum, mean = (np.zeros(rows, dtype=np.uint64), np.zeros(rows, dtype=np.uint64),
+                               np.zeros(94, dtype=np.uint64))
+    lib().qo_extras(seq.ctypes.data, qual.ctypes.data, offset.ctypes.data, length.ctypes.data, len(offset),
+                    n_count.ctypes.data_as(_u64p), qual_sum.ctypes.data_as(_u64p), rows, mean.ctypes.data_as(_u64p))
+    return n_count, qual_sum, mean
 
 
 def read_fastq(path: str, table: AdapterTable | None) -> Result:

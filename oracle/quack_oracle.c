@@ -335,3 +335,28 @@ void qo_transform(qo_stats *st, uint64_t *original_max_length) {
     row[QO_COL_KMER] = (uint64_t)ceil(100 * (float)row[QO_COL_KMER] / (float)st->n_reads);
   }
 }
+
+/* ------------------------------------------------------------------ extras (PARITY UNPINNED)
+ * The side outputs north_star names and the reference does not compute: there is no
+ * reference line, golden vector or fixture for them, so this restatement only pins the CUDA path against an
+ * independent scalar definition:
+ *   n_count[p]   reads whose base p is 'N' or 'n'
+ *   qual_sum[p]  sum over the reads of (q - 33) at position p, for quality bytes in the heatmap's range [33, 123]
+ *                (what sum_s s * scores[p][s] over the rows of quack.c:203-204 gives)
+ *   mean_hist[m] reads with floor(sum_p clamp(q, 33, 126) - 33) / l) == m, m = 0..93 */
+void qo_extras(const uint8_t *seq, const uint8_t *qual, const uint32_t *offset, const uint32_t *length, uint64_t n_reads,
+               uint64_t *n_count, uint64_t *qual_sum, uint64_t rows, uint64_t *mean_hist) {
+  for (uint64_t r = 0; r < n_reads; r++) {
+    const uint8_t *s = seq + offset[r], *q = qual + offset[r];
+    const uint32_t l = length[r];
+    if (l == 0 || l > rows) continue;
+    uint64_t sum = 0;
+    for (uint32_t p = 0; p < l; p++) {
+      if (s[p] == 'N' || s[p] == 'n') n_count[p]++;
+      if (q[p] >= 33 && q[p] <= 123) qual_sum[p] += (uint64_t)(q[p] - 33);
+      const unsigned c = q[p] < 33 ? 33u : q[p] > 126 ? 126u : q[p];
+      sum += c - 33u;
+    }
+    mean_hist[sum / l]++;
+  }
+}

@@ -88,6 +88,10 @@ int qo_read_fastq(const char *path, const uint8_t *table, qo_stats *st);
  * checked against KAT-F of SURVEY.md Appendix B. */
 void qo_transform(qo_stats *st, uint64_t *original_max_length);
 
+/* Side outputs the reference does not compute (PARITY UNPINNED: no reference oracle exists). */
+void qo_extras(const uint8_t *seq, const uint8_t *qual, const uint32_t *offset, const uint32_t *length, uint64_t n_reads,
+               uint64_t *n_count, uint64_t *qual_sum, uint64_t rows, uint64_t *mean_hist);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,8 @@ def lib() -> C.CDLL:
     L.qb_bgzf_submit.argtypes = [vp, C.POINTER(QbText), C.c_int, C.c_uint64, C.c_int]
     L.qb_bgzf_fit.argtypes = [vp, C.c_uint64, C.c_uint64, _u64p, _u64p]
     L.qb_bgzf_inflate.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, _u64p]
+    L.qb_extras_enable.argtypes = [vp]
+    L.qb_extras_finish.argtypes = [vp, C.c_int, _u64p, _u64p, C.c_uint64, _u64p]
     L.qb_bgzf_inflate_bench.argtypes = [vp, vp, C.c_uint64, C.c_int, C.POINTER(C.c_float), _u64p, _u32p]
     L.fqr_read_raw.argtypes = [vp, vp, C.c_size_t]
     L.fqr_read_raw.restype = C.c_long
@@ -315,6 +317,18 @@ class Context:
         ms, n, nb = C.c_float(0), C.c_uint64(0), C.c_uint32(0)
         self._chk(lib().qb_bgzf_inflate_bench(self.h, comp, len(comp), iters, C.byref(ms), C.byref(n), C.byref(nb)))
         return float(ms.value), int(n.value), int(nb.value)
+
+    def extras_enable(self):
+        self._chk(lib().qb_extras_enable(self.h))
+
+    def extras_finish(self, mate: int = 0):
+        """(n_count[max_length], qual_sum[max_length], mean_hist[94]): side outputs without a reference oracle."""
+        ml = self.finish(mate).max_length
+        n_count, qual_sum, mean = (np.zeros(max(ml, 1), dtype=np.uint64), np.zeros(max(ml, 1), dtype=np.uint64),
+                                   np.zeros(94, dtype=np.uint64))
+        self._chk(lib().qb_extras_finish(self.h, mate, n_count.ctypes.data_as(_u64p), qual_sum.ctypes.data_as(_u64p),
+                                         max(ml, 1), mean.ctypes.data_as(_u64p)))
+        return n_count[:ml], qual_sum[:ml], mean
 
     def text_status(self, mate: int = 0):
         """(records framed, bytes left behind the last complete record); raises QbError(QB_ERR_TEXT) for text the

@@ -126,6 +126,9 @@ struct Device {
     uint64_t reads = 0;
   };
   std::vector<TextMate> text;
+  // opt-in side outputs (qb_extras_enable): per mate [len_cap N counts | 94 mean-quality bins]
+  std::vector<unsigned long long *> ext;
+  unsigned long long *ext_reduce = nullptr;
 };
 
 }  // namespace
@@ -148,6 +151,7 @@ struct qb_ctx {
   size_t acc_u64 = 0;  // cur_cap*97 + counters, per mate
   std::atomic<bool> result_valid{false};  // h_result holds the reduced accumulators of every mate (qb_finish)
   std::mutex text_mu;                     // text path set-up
+  std::atomic<bool> extras{false};        // qb_extras_enable(): every batch also takes the extras pass
   qb::AdapterSet ad_host_template{};
   uint32_t n_anchors = 0;     // distinct 7-mer anchors of the adapter set
   double anchor_density = 0;  // n_anchors / 2^14: filter pass rate per probe on random bases
@@ -421,6 +425,11 @@ int launch_batch_locked(qb_ctx *ctx, Device &d, const qb::BatchView &v, int mate
     rc = launch_other(ctx, d, rest, ac, ad, kernel, stream);
   }
   if (e1) cudaEventRecord(e1, stream);
+  if (rc == QB_OK && ctx->extras.load()) {
+    const cudaError_t e = qb::launch_extras(v, ctx->cfg.len_cap, d.ext[mate], d.ext[mate] + ctx->cfg.len_cap, d.sm_count, stream);
+    if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "extras kernel launch failed: %s", cudaGetErrorString(e));
+    ctx->launches++;
+  }
   return rc;
 }
 
@@ -613,6 +622,8 @@ void qb_destroy(qb_ctx *ctx) {
     cudaSetDevice(d.id);
     cudaDeviceSynchronize();
     if (d.comm) nccl_api()->CommDestroy(d.comm);
+    for (unsigned long long *x : d.ext) cudaFree(x);
+    cudaFree(d.ext_reduce);
     for (Slot &s : d.slots) {
       if (s.h_seq) cudaFreeHost(s.h_seq);
       if (s.h_qual) cudaFreeHost(s.h_qual);
@@ -1294,6 +1305,7 @@ int qb_reset(qb_ctx *ctx, int mate) {
   for (Device &d : ctx->dev) {
     QB_CUDA(ctx, cudaSetDevice(d.id));
     QB_CUDA(ctx, cudaMemset(d.acc[mate], 0, ctx->acc_u64 * 8));
+    if (ctx->extras.load()) QB_CUDA(ctx, cudaMemset(d.ext[mate], 0, ((size_t)ctx->cfg.len_cap + qb::kExtrasMeanBins) * 8));
     if (!d.text.empty()) {  // a new stream starts: no carry, no error from the last one
       QB_CUDA(ctx, cudaMemset(d.text[mate].d_state, 0, sizeof(qb::TextState)));
       d.text[mate].invalid = 0;
@@ -1403,6 +1415,63 @@ int qb_finish(qb_ctx *ctx, int mate, uint64_t *rows_out, uint64_t rows_cap, uint
     if (ml > rows_cap) return fail(ctx, QB_ERR_CAPACITY, "rows_out holds %llu rows, need %llu",
                                    (unsigned long long)rows_cap, (unsigned long long)ml);
     memcpy(rows_out, rows, (size_t)ml * qb::kRow * 8);
+  }
+  return QB_OK;
+}
+
+// ---- opt-in side outputs (no reference oracle: SURVEY.md section 0.1) ----
+int qb_extras_enable(qb_ctx *ctx) {
+  if (!ctx) return QB_ERR_ARG;
+  if (ctx->extras.load()) return QB_OK;
+  if (ctx->submit_seq != 0 || ctx->launches.load() != 0)
+    return fail(ctx, QB_ERR_ARG, "qb_extras_enable must be called before the first batch is submitted");
+  const size_t n = (size_t)ctx->cfg.len_cap + qb::kExtrasMeanBins;
+  for (Device &d : ctx->dev) {
+    QB_CUDA(ctx, cudaSetDevice(d.id));
+    d.ext.assign(ctx->cfg.n_mates, nullptr);
+    for (int m = 0; m < ctx->cfg.n_mates; m++) {
+      QB_CUDA(ctx, cudaMalloc(&d.ext[m], n * 8));
+      QB_CUDA(ctx, cudaMemset(d.ext[m], 0, n * 8));
+    }
+    QB_CUDA(ctx, cudaMalloc(&d.ext_reduce, n * 8));
+  }
+  ctx->extras.store(true);
+  return QB_OK;
+}
+
+int qb_extras_finish(qb_ctx *ctx, int mate, uint64_t *n_count, uint64_t *qual_sum, uint64_t rows_cap, uint64_t *mean_hist) {
+  int rc = check_mate(ctx, mate);
+  if (rc) return rc;
+  if (!ctx->extras.load()) return fail(ctx, QB_ERR_ARG, "qb_extras_enable was not called");
+  // the heatmap rows (for the per-position quality sums) and max_length: the ordinary result
+  uint64_t ml = 0, nr = 0;
+  if ((rc = qb_finish(ctx, mate, nullptr, 0, &ml, &nr))) return rc;
+  if (ml > rows_cap) return fail(ctx, QB_ERR_CAPACITY, "extras arrays hold %llu positions, need %llu", (unsigned long long)rows_cap, (unsigned long long)ml);
+  const size_t n = (size_t)ctx->cfg.len_cap + qb::kExtrasMeanBins;
+  std::vector<unsigned long long> sum(n, 0), part(n);
+  for (Device &d : ctx->dev) {  // the devices of this process: summed on the host (n is small)
+    QB_CUDA(ctx, cudaSetDevice(d.id));
+    QB_CUDA(ctx, cudaMemcpy(part.data(), d.ext[mate], n * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) sum[i] += part[i];
+  }
+  if (ctx->rank_comm && ctx->n_ranks > 1) {  // one process per GPU: one more integer reduce to rank 0
+    NcclApi *nc = nccl_api();
+    Device &root = ctx->dev[0];
+    QB_CUDA(ctx, cudaSetDevice(root.id));
+    QB_CUDA(ctx, cudaMemcpyAsync(root.ext[mate], sum.data(), n * 8, cudaMemcpyHostToDevice, root.main_stream));
+    QB_NCCL(ctx, nc->Reduce(root.ext[mate], root.ext_reduce, n, ncclUint64, ncclSum, 0, ctx->rank_comm, root.main_stream));
+    if (ctx->rank == 0) QB_CUDA(ctx, cudaMemcpyAsync(sum.data(), root.ext_reduce, n * 8, cudaMemcpyDeviceToHost, root.main_stream));
+    QB_CUDA(ctx, cudaStreamSynchronize(root.main_stream));
+  }
+  if (n_count) memcpy(n_count, sum.data(), (size_t)ml * 8);
+  if (mean_hist) memcpy(mean_hist, sum.data() + ctx->cfg.len_cap, qb::kExtrasMeanBins * 8);
+  if (qual_sum) {  // sum_s s * scores[p][s] over the raw heatmap rows (quack.c:203-204 counts)
+    const unsigned long long *rows = ctx->h_result + (size_t)mate * ctx->acc_u64;
+    for (uint64_t p = 0; p < ml; p++) {
+      unsigned long long q = 0;
+      for (uint32_t s = 1; s < 91; s++) q += (unsigned long long)s * rows[p * qb::kRow + s];
+      qual_sum[p] = q;
+    }
   }
   return QB_OK;
 }

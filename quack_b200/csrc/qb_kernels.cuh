@@ -169,6 +169,11 @@ cudaError_t launch_text_frame(const uint8_t *chunk, uint32_t n_chunk, const uint
                               TextSummary *sum_dev, cudaStream_t stream);
 size_t text_scratch_words(uint32_t chunk_cap, uint32_t carry_cap, uint32_t nl_cap, uint32_t rec_cap);
 
+// ---- opt-in side outputs (qb_extras.cu): N count per position, per-read mean quality distribution ----
+constexpr uint32_t kExtrasMeanBins = 94;
+cudaError_t launch_extras(const BatchView &b, uint32_t len_cap, unsigned long long *n_count, unsigned long long *mean_hist,
+                          int sm_count, cudaStream_t stream);
+
 // ---- on-device inflate of BGZF blocks (qb_inflate.cu) --------------------------------------
 struct BgzfBlock {
   uint32_t in_off, in_len;    // the raw DEFLATE stream of the block inside the chunk's compressed bytes

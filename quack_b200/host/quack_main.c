@@ -18,6 +18,8 @@
  *                       4-line FASTQ only; on anything else the run starts over with the host reader.  Regular files.
  *   QB_DEVICE_INFLATE=1 BGZF files: the device also inflates (qb_bgzf_submit): the host only reads the file.  Falls back
  *                       the same way (not BGZF -> device framing; damaged or odd input -> host reader).
+ *   QB_EXTRAS_JSON=path side outputs the reference does not have (N count and quality sum per position, per-read mean
+ *                       quality distribution; qb_extras_*): written there, never part of the SVG
  *   QB_STATS_JSON=path  write reads/s, bases/s and stage times there (stdout stays the SVG)
  *   QUACK_DECODE_THREADS=n  inflate threads per BGZF input file (default: half of the cores, at most 8)
  */
@@ -299,6 +301,10 @@ int main(int argc, char **argv) {
       fprintf(stderr, "quack: %s\n", qb_last_error(NULL));
       return 2;
     }
+    if (getenv("QB_EXTRAS_JSON") && *getenv("QB_EXTRAS_JSON") && qb_extras_enable(ctx)) {
+      fprintf(stderr, "quack: %s\n", qb_last_error(ctx));
+      return 2;
+    }
     t_created = now_s(); /* CUDA start-up, pinned ring, accumulators: a fixed cost per process */
 
     pthread_t th[2];
@@ -369,6 +375,31 @@ int main(int argc, char **argv) {
       fprintf(stderr, "quack: no reads in %s\n", jobs[m].path);
       qb_destroy(ctx);
       return 2;
+    }
+  }
+  const char *xjs = getenv("QB_EXTRAS_JSON");
+  if (xjs && *xjs) { /* side outputs, straight to their own file */
+    FILE *f = fopen(xjs, "w");
+    if (f) {
+      fprintf(f, "{\"note\": \"not computed by the reference: no reference oracle\", \"mates\": [");
+      for (int m = 0; m < cfg.n_mates; m++) {
+        const uint64_t ml = data[m].max_length;
+        uint64_t *nc = (uint64_t *)calloc(2 * ml + 94, sizeof(uint64_t)), *qs = nc + ml, *mh = qs + ml;
+        if (qb_extras_finish(ctx, m, nc, qs, ml, mh)) {
+          fprintf(stderr, "quack: %s\n", qb_last_error(ctx));
+          return 2;
+        }
+        fprintf(f, "%s{\"n_count\": [", m ? ", " : "");
+        for (uint64_t p = 0; p < ml; p++) fprintf(f, "%s%llu", p ? ", " : "", (unsigned long long)nc[p]);
+        fprintf(f, "], \"qual_sum\": [");
+        for (uint64_t p = 0; p < ml; p++) fprintf(f, "%s%llu", p ? ", " : "", (unsigned long long)qs[p]);
+        fprintf(f, "], \"mean_quality_hist\": [");
+        for (int b = 0; b < 94; b++) fprintf(f, "%s%llu", b ? ", " : "", (unsigned long long)mh[b]);
+        fprintf(f, "]}");
+        free(nc);
+      }
+      fprintf(f, "]}\n");
+      fclose(f);
     }
   }
   uint64_t framed_reads = 0, framed_bases = 0; /* (before qr_transform() turns the counts into fractions) */

@@ -166,3 +166,21 @@ def test_transform_binning_vs_reference():
     want = po.ref_transform(rows, 3456, 1234)
     assert got[1:] == want[1:] == (34, 3456)
     assert np.array_equal(got[0][:34], want[0][:34])
+
+
+def test_extras_restatement_equals_its_definition():
+    """qo_extras() (PARITY UNPINNED: the reference has no such arrays) against the definition
+    written out with numpy, so that the checker of the CUDA extras pass is itself checked."""
+    import qb_testutil as util
+    seq, qual, off, ln = util.random_batch(3, 500, 1, 90, alphabet=b"ACGTNn", probs=(.2, .2, .2, .2, .1, .1), qlo=0, qhi=93)
+    qual = qual.copy()
+    qual[::97] = 20          # below '!' : clamped for the mean, outside the heatmap's range for the sum
+    n, q, m = po.extras(seq, qual, off, ln, rows=90)
+    wn, wq, wm = np.zeros(90, dtype=np.uint64), np.zeros(90, dtype=np.uint64), np.zeros(94, dtype=np.uint64)
+    for o, l in zip(off.tolist(), ln.tolist()):
+        s, qq = seq[o:o + l], qual[o:o + l].astype(np.int64)
+        wn[:l] += ((s == ord("N")) | (s == ord("n"))).astype(np.uint64)
+        ok = (qq >= 33) & (qq <= 123)
+        wq[:l] += np.where(ok, qq - 33, 0).astype(np.uint64)
+        wm[int((np.clip(qq, 33, 126) - 33).sum()) // l] += 1
+    assert np.array_equal(n, wn) and np.array_equal(q, wq) and np.array_equal(m, wm)
