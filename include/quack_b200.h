@@ -236,6 +236,8 @@ int qb_timer_start(qb_ctx *ctx, int device_index);
 int qb_timer_stop(qb_ctx *ctx, int device_index, float *ms);
 /* Measured pinned H2D bandwidth of device_index in GB/s (best of `iters` copies of `bytes`). */
 int qb_measure_h2d(qb_ctx *ctx, int device_index, uint64_t bytes, int iters, double *gbs);
+/* The same for ONE pass over n pinned host buffers (each byte leaves host memory once: the streaming ceiling). */
+int qb_measure_h2d_list(qb_ctx *ctx, int device_index, const void *const *ptrs, const uint64_t *sizes, uint32_t n, double *gbs);
 /* Geometry and shared-memory counter layout of the period kernel (QB_KERNEL_PERIOD) for reads of one length.
  * Needs no GPU.  0 if the kernel takes such batches, -1 otherwise.  info = reads per period, words per period,
  * warp steps per period, periods per tile, reads per tile, stages, warps per CTA; slot[p] = histogram block << 7 | 32-bit

@@ -109,6 +109,7 @@ def lib() -> C.CDLL:
     L.qb_timer_start.argtypes = [vp, C.c_int]
     L.qb_timer_stop.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     L.qb_measure_h2d.argtypes = [vp, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
+    L.qb_measure_h2d_list.argtypes = [vp, C.c_int, C.POINTER(vp), _u64p, C.c_uint32, C.POINTER(C.c_double)]
     L.qb_base_code.argtypes = [C.c_int]
     L.qb_adapter_record_keys.argtypes = [C.c_char_p, C.c_size_t, _u32p, C.c_size_t]
     L.qb_gen_reads.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double,
@@ -420,6 +421,15 @@ class Context:
         a, b = C.c_uint64(), C.c_uint64()
         self._chk(lib().qb_kernel_counts(self.h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
+
+    def measure_h2d_list(self, ptrs, sizes, device_index: int = 0) -> float:
+        """GB/s of one pass over pinned host buffers (addresses, byte counts)."""
+        n = len(ptrs)
+        pa = (C.c_void_p * n)(*ptrs)
+        sa = (C.c_uint64 * n)(*sizes)
+        g = C.c_double(0)
+        self._chk(lib().qb_measure_h2d_list(self.h, device_index, pa, sa, n, C.byref(g)))
+        return float(g.value)
 
     def measure_h2d(self, nbytes: int = 256 << 20, iters: int = 5, device_index: int = 0) -> float:
         g = C.c_double()

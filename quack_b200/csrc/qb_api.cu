@@ -1764,6 +1764,34 @@ int qb_measure_h2d(qb_ctx *ctx, int device_index, uint64_t bytes, int iters, dou
   return QB_OK;
 }
 
+// Diagnostics: host-to-device rate of ONE pass over a list of pinned host buffers (every byte read once from host
+// memory, unlike the repeated copy of qb_measure_h2d whose source may sit in the CPU's last-level cache).
+int qb_measure_h2d_list(qb_ctx *ctx, int device_index, const void *const *ptrs, const uint64_t *sizes, uint32_t n, double *gbs) {
+  if (!ctx || !gbs || !ptrs || !sizes || n == 0 || device_index < 0 || device_index >= (int)ctx->dev.size()) return QB_ERR_ARG;
+  Device &d = ctx->dev[device_index];
+  QB_CUDA(ctx, cudaSetDevice(d.id));
+  uint64_t mx = 0, total = 0;
+  for (uint32_t i = 0; i < n; i++) mx = sizes[i] > mx ? sizes[i] : mx, total += sizes[i];
+  void *dv[2] = {nullptr, nullptr};
+  QB_CUDA(ctx, cudaMalloc(&dv[0], mx));
+  QB_CUDA(ctx, cudaMalloc(&dv[1], mx));
+  cudaEvent_t e0, e1;
+  QB_CUDA(ctx, cudaEventCreate(&e0));
+  QB_CUDA(ctx, cudaEventCreate(&e1));
+  QB_CUDA(ctx, cudaEventRecord(e0, d.main_stream));
+  for (uint32_t i = 0; i < n; i++) QB_CUDA(ctx, cudaMemcpyAsync(dv[i & 1u], ptrs[i], sizes[i], cudaMemcpyHostToDevice, d.main_stream));
+  QB_CUDA(ctx, cudaEventRecord(e1, d.main_stream));
+  QB_CUDA(ctx, cudaEventSynchronize(e1));
+  float ms = 0;
+  QB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dv[0]);
+  cudaFree(dv[1]);
+  *gbs = (double)total / (ms * 1e-3) / 1e9;
+  return QB_OK;
+}
+
 // tools: shared-memory pipe microbenchmarks (not part of the documented boundary)
 int qb_microbench(char *report, size_t cap) {
   int sm = 0;
