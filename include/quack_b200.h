@@ -155,6 +155,12 @@ int qb_text_status(qb_ctx *ctx, int mate, uint64_t *n_reads, uint64_t *tail_byte
  * that are not BGZF blocks make the mate fail with QB_ERR_TEXT like text that is not canonical: the caller then reads
  * the file through the host reader, which reports damaged input the way the reference does. */
 int qb_bgzf_submit(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, int last);
+/* Both submits from caller-owned host memory (pinned memory copies asynchronously and must stay valid until the next
+ * qb_sync()/qb_finish()); they take the next free slot themselves.  Same capacity rules. */
+int qb_bgzf_submit_from(qb_ctx *ctx, int mate, const uint8_t *blocks, uint64_t n_bytes, int last);
+int qb_text_submit_from(qb_ctx *ctx, int mate, const uint8_t *text, uint64_t n_bytes, int last);
+/* Bytes of text one chunk may hold (qb_text.cap_bytes of every slot). */
+int qb_text_capacity(qb_ctx *ctx, uint64_t *cap_bytes);
 /* n_whole = bytes of buf[0..n_bytes) that are whole BGZF blocks holding at most text_cap_bytes of text together
  * (n_text).  QB_ERR_TEXT: a block header is not BGZF.  Pure host code. */
 int qb_bgzf_fit(const uint8_t *buf, uint64_t n_bytes, uint64_t text_cap_bytes, uint64_t *n_whole, uint64_t *n_text);

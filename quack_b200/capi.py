@@ -74,6 +74,9 @@ def lib() -> C.CDLL:
     L.qb_text_submit.argtypes = [vp, C.POINTER(QbText), C.c_int, C.c_uint64, C.c_int]
     L.qb_text_status.argtypes = [vp, C.c_int, _u64p, _u64p]
     L.qb_bgzf_submit.argtypes = [vp, C.POINTER(QbText), C.c_int, C.c_uint64, C.c_int]
+    L.qb_bgzf_submit_from.argtypes = [vp, C.c_int, vp, C.c_uint64, C.c_int]
+    L.qb_text_submit_from.argtypes = [vp, C.c_int, vp, C.c_uint64, C.c_int]
+    L.qb_text_capacity.argtypes = [vp, _u64p]
     L.qb_bgzf_fit.argtypes = [vp, C.c_uint64, C.c_uint64, _u64p, _u64p]
     L.qb_bgzf_inflate.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, _u64p]
     L.qb_extras_enable.argtypes = [vp]
@@ -306,6 +309,15 @@ class Context:
             pos += n
             if last:
                 break
+
+    def text_cap(self) -> int:
+        """Capacity of a text / BGZF chunk (bytes of text)."""
+        c = C.c_uint64(0)
+        self._chk(lib().qb_text_capacity(self.h, C.byref(c)))
+        return int(c.value)
+
+    def bgzf_submit_from(self, mate: int, ptr: int, n_bytes: int, last: bool):
+        self._chk(lib().qb_bgzf_submit_from(self.h, mate, ptr, n_bytes, 1 if last else 0))
 
     def bgzf_inflate(self, comp: bytes, text_cap: int) -> bytes:
         out = (C.c_uint8 * max(text_cap, 1))()

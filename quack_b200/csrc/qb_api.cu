@@ -1070,7 +1070,8 @@ bool bgzf_walk(const uint8_t *buf, uint64_t n, uint64_t text_cap_bytes, uint32_t
 
 }  // namespace
 
-static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, int last, bool bgzf) {
+// src: the host bytes (the slot's own pinned buffer, or caller-owned memory for the *_from entry points)
+static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, int last, bool bgzf, const uint8_t *src = nullptr) {
   int rc = check_mate(ctx, mate);
   if (rc) return rc;
   if (!t || t->device_index != 0 || t->slot < 0 || t->slot >= ctx->cfg.ring_depth || ctx->dev[0].text.empty())
@@ -1081,6 +1082,7 @@ static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t 
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (s.state != Slot::HELD || t->text != s.h_text) return fail(ctx, QB_ERR_ARG, "qb_text_submit: the slot is not held by a qb_text_acquire()");
   }
+  if (!src) src = s.h_text;
   if (n_bytes > text_cap(ctx)) {
     release_slot(ctx, 0, t->slot);
     return fail(ctx, QB_ERR_CAPACITY, "text chunk of %llu bytes exceeds the slot (%u)", (unsigned long long)n_bytes, text_cap(ctx));
@@ -1096,7 +1098,7 @@ static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t 
     }
     uint32_t nb = 0;
     uint64_t whole = 0;
-    const bool ok = bgzf_walk(s.h_text, n_bytes, text_cap(ctx), kMaxBgzfBlocks, s.h_blk, &nb, &whole, &n_text);
+    const bool ok = bgzf_walk(src, n_bytes, text_cap(ctx), kMaxBgzfBlocks, s.h_blk, &nb, &whole, &n_text);
     if (!ok || whole != n_bytes) {
       release_slot(ctx, 0, t->slot);
       if (!ok) {
@@ -1106,7 +1108,7 @@ static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t 
       return fail(ctx, QB_ERR_ARG, "qb_bgzf_submit: %llu of %llu bytes are whole blocks that fit the slot (see qb_bgzf_fit)",
                   (unsigned long long)whole, (unsigned long long)n_bytes);
     }
-    if (n_bytes) QB_CUDA(ctx, cudaMemcpyAsync(s.d_comp, s.h_text, n_bytes, cudaMemcpyHostToDevice, s.stream));
+    if (n_bytes) QB_CUDA(ctx, cudaMemcpyAsync(s.d_comp, src, n_bytes, cudaMemcpyHostToDevice, s.stream));
     if (nb) QB_CUDA(ctx, cudaMemcpyAsync(s.d_blk, s.h_blk, sizeof(qb::BgzfBlock) * nb, cudaMemcpyHostToDevice, s.stream));
     cudaError_t e = qb::launch_inflate_bgzf(s.d_comp, s.d_blk, nb, s.d_text, s.d_bad, s.d_blk_status, s.stream);
     if (e == cudaSuccess && m.last_framed) e = cudaStreamWaitEvent(s.stream, m.last_framed, 0);
@@ -1117,7 +1119,7 @@ static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t 
     }
     ctx->launches += nb ? 1 : 0;
   } else {
-    if (n_bytes) QB_CUDA(ctx, cudaMemcpyAsync(s.d_text, s.h_text, n_bytes, cudaMemcpyHostToDevice, s.stream));
+    if (n_bytes) QB_CUDA(ctx, cudaMemcpyAsync(s.d_text, src, n_bytes, cudaMemcpyHostToDevice, s.stream));
     if (m.last_framed) QB_CUDA(ctx, cudaStreamWaitEvent(s.stream, m.last_framed, 0));  // the carry comes from the chunk in front
   }
   ctx->h2d_bytes += n_bytes;
@@ -1153,6 +1155,30 @@ extern "C" int qb_text_submit(qb_ctx *ctx, const qb_text *t, int mate, uint64_t 
 
 extern "C" int qb_bgzf_submit(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, int last) {
   return text_submit_common(ctx, t, mate, n_bytes, last, true);
+}
+
+// Same from caller-owned host memory (pinned memory copies asynchronously; it must stay valid until the next
+// qb_sync / qb_finish): takes the next free slot itself.
+extern "C" int qb_bgzf_submit_from(qb_ctx *ctx, int mate, const uint8_t *blocks, uint64_t n_bytes, int last) {
+  if (!ctx || (!blocks && n_bytes)) return QB_ERR_ARG;
+  qb_text t;
+  int rc = qb_text_acquire(ctx, &t);
+  if (rc) return rc;
+  return text_submit_common(ctx, &t, mate, n_bytes, last, true, blocks ? blocks : t.text);
+}
+
+extern "C" int qb_text_submit_from(qb_ctx *ctx, int mate, const uint8_t *text, uint64_t n_bytes, int last) {
+  if (!ctx || (!text && n_bytes)) return QB_ERR_ARG;
+  qb_text t;
+  int rc = qb_text_acquire(ctx, &t);
+  if (rc) return rc;
+  return text_submit_common(ctx, &t, mate, n_bytes, last, false, text ? text : t.text);
+}
+
+extern "C" int qb_text_capacity(qb_ctx *ctx, uint64_t *cap_bytes) {
+  if (!ctx || !cap_bytes) return QB_ERR_ARG;
+  *cap_bytes = text_cap(ctx);
+  return QB_OK;
 }
 
 extern "C" int qb_bgzf_fit(const uint8_t *buf, uint64_t n_bytes, uint64_t text_cap_bytes, uint64_t *n_whole, uint64_t *n_text) {
