@@ -362,10 +362,13 @@ class Arena:
         self.batches = {0: [], 1: []}
 
 
-def bench_e2e_bgzf(ctx, capi, rank, world, args, barrier, allmax, allsum):
+def bench_e2e_bgzf(capi, keys, local_rank, rank, world, args, barrier, allmax, allsum):
+    """Own context (6 slots of 32 MiB, no NCCL: every rank checks its own counts), one host thread per mate like the
+    `quack` program, so that up to four chunks are being inflated at a time."""
     import torch
     L = capi.lib()
     cpairs = int(os.environ.get("QB_BENCH_BGZF_PAIRS", "2000000"))
+    ctx = capi.Context(READ_LEN, n_mates=2, adapter_keys=keys, device_ids=[local_rank], batch_bytes=32 << 20, ring_depth=6)
     cap = ctx.text_cap()
     bufs, chunks = [], {0: [], 1: []}
     comp_bytes = text_bytes = 0
@@ -393,10 +396,20 @@ def bench_e2e_bgzf(ctx, capi, rank, world, args, barrier, allmax, allsum):
                 text_bytes += text.value
             comp_bytes += n
 
-    def one_pass():
-        for mate in (0, 1):
+    def feed(mate, errors):
+        try:
             for i, (ptr, nb) in enumerate(chunks[mate]):
                 ctx.bgzf_submit_from(mate, ptr, nb, i == len(chunks[mate]) - 1)
+        except Exception as ex:  # noqa: BLE001
+            errors.append(ex)
+
+    def one_pass():
+        errors = []
+        th = [threading.Thread(target=feed, args=(m, errors)) for m in (0, 1)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        if errors:
+            raise errors[0]
         return ctx.finish(0), ctx.finish(1)
 
     steps = max(1, min(args.steps, 5))
@@ -415,9 +428,10 @@ def bench_e2e_bgzf(ctx, capi, rank, world, args, barrier, allmax, allsum):
         n, tail = ctx.text_status(mate)
         assert (n, tail) == (cpairs * steps, 0), (n, tail)
     barrier()
-    if rank == 0:
-        for r in res:
-            assert r.n_reads == cpairs * world * steps and r.max_length == READ_LEN, (r.n_reads, r.max_length)
+    for r in res:
+        assert r.n_reads == cpairs * steps and r.max_length == READ_LEN, (r.n_reads, r.max_length)
+        assert int(r.rows[READ_LEN - 1, capi.COL_LENGTH]) == r.n_reads
+    ctx.close()
     for p in bufs:
         L.qb_host_free(p)
     return {"value": 2 * cpairs * world / dt, "unit": "reads/s", "pairs_per_gpu": cpairs, "ms_per_step": dt * 1e3,
@@ -632,10 +646,13 @@ def bench_ours(args):
     e2e_bgzf = None
     if not args.no_e2e_bgzf:
         try:
-            e2e_bgzf = bench_e2e_bgzf(ctx, capi, rank, world, args, barrier, allmax, allsum)
+            ctx.close()
+            ctx = None
+            e2e_bgzf = bench_e2e_bgzf(capi, keys, local_rank, rank, world, args, barrier, allmax, allsum)
         except Exception as ex:
             e2e_bgzf = {"error": repr(ex)}
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
 
     # ---- the other kernels of the path, kernel only, CUDA events (rank 0; secondary to the headline) ----
     other = {}

@@ -58,8 +58,11 @@ __global__ void __launch_bounds__(kTBlock) frame_count(const uint8_t *carry, con
 }
 
 // in-place exclusive prefix sum of a[0 .. n), total to *total_out; one block of 1024 threads
-__global__ void __launch_bounds__(1024) frame_scan(uint32_t *a, uint32_t n, uint32_t *total_out, const TextState *st) {
+// (n_lines_p != nullptr: only the first *n_lines_p / 4 + 1 entries are in use -- the records of this chunk)
+__global__ void __launch_bounds__(1024) frame_scan(uint32_t *a, uint32_t n, uint32_t *total_out, const TextState *st,
+                                                    const uint32_t *n_lines_p) {
   if (st->broken) return;
+  if (n_lines_p) n = min(n, *n_lines_p / 4u + 1u);
   __shared__ uint32_t part[1024];
   const uint32_t t = threadIdx.x;
   const uint32_t per = (n + 1023u) / 1024u;
@@ -237,14 +240,14 @@ cudaError_t launch_text_frame(const uint8_t *chunk, uint32_t n_chunk, const uint
   uint32_t *totals = rec_off + rec_cap;  // [0] lines, [1] packed bytes
   frame_init<<<1, 1, 0, stream>>>(sum_dev);
   frame_count<<<n_tiles, kTBlock, 0, stream>>>(carry_in, chunk, n_chunk, state, tile_cnt, n_tiles);
-  frame_scan<<<1, 1024, 0, stream>>>(tile_cnt, n_tiles, totals, state);
+  frame_scan<<<1, 1024, 0, stream>>>(tile_cnt, n_tiles, totals, state, nullptr);
   frame_index<<<n_tiles, kTBlock, 0, stream>>>(carry_in, chunk, n_chunk, state, tile_cnt, nl, nl_cap);
   const uint32_t rec_blocks = (rec_cap + kTBlock - 1u) / kTBlock;
   frame_records<<<rec_blocks, kTBlock, 0, stream>>>(carry_in, chunk, n_chunk, state, nl, totals, nl_cap, rec_seq, rec_qual, rec_len,
                                                    rec_cap, sum_dev);
   cudaError_t e = cudaMemcpyAsync(rec_off, rec_len, (size_t)rec_cap * 4u, cudaMemcpyDeviceToDevice, stream);
   if (e != cudaSuccess) return e;
-  frame_scan<<<1, 1024, 0, stream>>>(rec_off, rec_cap, totals + 1, state);
+  frame_scan<<<1, 1024, 0, stream>>>(rec_off, rec_cap, totals + 1, state, totals);
   frame_pack<<<592, kTBlock, 0, stream>>>(carry_in, chunk, n_chunk, state, totals, rec_seq, rec_qual, rec_len, rec_off, sum_dev, seq,
                                          qual, offset, length, out_cap);
   frame_tail<<<1, kTBlock, 0, stream>>>(carry_in, chunk, n_chunk, state, nl, totals, totals + 1, carry_out, carry_cap, out_cap, sum_dev);
