@@ -363,12 +363,13 @@ class Arena:
 
 
 def bench_e2e_bgzf(capi, keys, local_rank, rank, world, args, barrier, allmax, allsum):
-    """Own context (6 slots of 32 MiB, no NCCL: every rank checks its own counts), one host thread per mate like the
+    """Own context (6 slots of 64 MiB, no NCCL: every rank checks its own counts), one host thread per mate like the
     `quack` program, so that up to four chunks are being inflated at a time."""
     import torch
     L = capi.lib()
-    cpairs = int(os.environ.get("QB_BENCH_BGZF_PAIRS", "2000000"))
-    ctx = capi.Context(READ_LEN, n_mates=2, adapter_keys=keys, device_ids=[local_rank], batch_bytes=32 << 20, ring_depth=6)
+    cpairs = int(os.environ.get("QB_BENCH_BGZF_PAIRS", "4000000"))
+    mb = int(os.environ.get("QB_BENCH_BGZF_BATCH_MB", "64"))
+    ctx = capi.Context(READ_LEN, n_mates=2, adapter_keys=keys, device_ids=[local_rank], batch_bytes=mb << 20, ring_depth=6)
     cap = ctx.text_cap()
     bufs, chunks = [], {0: [], 1: []}
     comp_bytes = text_bytes = 0
