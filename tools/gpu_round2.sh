@@ -17,6 +17,8 @@ QB_QUICK_KERNELS=0,2 timeout 600 python tools/quick_bench.py 4000000 > $OUT/quic
 QB_QUICK_KERNELS=0 QB_QUICK_ONLY150=1 timeout 600 python tools/quick_bench.py 16000000 >> $OUT/quick_bench.jsonl 2>&1
 QB_QUICK_KERNELS=4 QB_QUICK_LENS=50,76,100,126,151,200,256 timeout 600 python tools/quick_bench.py 4000000 > $OUT/quick_bench_lens.jsonl 2>&1
 timeout 600 python tools/decode_bench.py 2000000 16 > $OUT/decode_bench.jsonl 2>&1
+for lvl in 1 6; do timeout 300 python tools/inflate_bench.py 4000000 $lvl >> $OUT/inflate_bench.jsonl 2>> $OUT/inflate_bench.err; done
+timeout 300 python tools/inflate_bench.py 100000 1 >> $OUT/inflate_bench.jsonl 2>> $OUT/inflate_bench.err
 for mode in ad noad; do
   QB_PROFILE_KERNEL=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:period_kernel -s 1 -c 1 \
     -o $OUT/period_${mode}_full -f python tools/profile_target.py $mode 10000000 150 150 3 > $OUT/ncu_period_$mode.log 2>&1
