@@ -180,6 +180,13 @@ int qb_bgzf_inflate_bench(qb_ctx *ctx, const uint8_t *comp, uint64_t n_bytes, in
  * partial rows.  rows_cap is in rows (positions). */
 int qb_finish(qb_ctx *ctx, int mate, uint64_t *rows_out, uint64_t rows_cap, uint64_t *max_length,
               uint64_t *n_reads);
+/* qb_finish() followed by the reference's transform() (quack.c:230-293) ON THE DEVICE: reads longer than 3000 bp binned
+ * by 100 positions (with the reference's in-place quirks), kmer_count as a running sum, scores as integer
+ * percentages, length / kmer counts as ceil(100 * (float) x / nseq).  rows_out receives *max_length transformed rows
+ * (the binned length when original_max_length > 3000) -- exactly what draw() (quack.c:295) takes; only those rows
+ * cross the link (10 k instead of 1 M for million-base reads).  rows_out == NULL queries the sizes. */
+int qb_finish_transformed(qb_ctx *ctx, int mate, uint64_t *rows_out, uint64_t rows_cap, uint64_t *max_length,
+                          uint64_t *n_reads, uint64_t *original_max_length);
 /* Zeroes the accumulators of one mate (all devices) so a context can be reused. */
 int qb_reset(qb_ctx *ctx, int mate);
 /* ---- opt-in side outputs that the reference does NOT compute (no reference oracle; never part of the SVG) ----

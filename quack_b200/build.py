@@ -42,7 +42,7 @@ def _nvcc() -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libquack_b200.so (kernels + C-ABI) and, when present, the host program."""
     os.makedirs(LIBDIR, exist_ok=True)
-    srcs = [os.path.join(CSRC, f) for f in ("qb_kernels.cu", "qb_period.cu", "qb_flat.cu", "qb_text.cu", "qb_inflate.cu", "qb_extras.cu", "qb_api.cu", "qb_host.cpp", "qb_gen.cpp")]
+    srcs = [os.path.join(CSRC, f) for f in ("qb_kernels.cu", "qb_period.cu", "qb_flat.cu", "qb_text.cu", "qb_inflate.cu", "qb_extras.cu", "qb_transform.cu", "qb_api.cu", "qb_host.cpp", "qb_gen.cpp")]
     host_lib_srcs = [os.path.join(HOST, f) for f in ("fq_reader.c", "render.c")
                      if os.path.exists(os.path.join(HOST, f))]
     deps = srcs + host_lib_srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]

@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
     L.fqr_read_raw.argtypes = [vp, vp, C.c_size_t]
     L.fqr_read_raw.restype = C.c_long
     L.qb_finish.argtypes = [vp, C.c_int, vp, C.c_uint64, _u64p, _u64p]
+    L.qb_finish_transformed.argtypes = [vp, C.c_int, vp, C.c_uint64, _u64p, _u64p, _u64p]
     L.qb_reset.argtypes = [vp, C.c_int]
     L.qb_invalid_quality_count.argtypes = [vp, C.c_int, _u64p]
     L.qb_nccl_unique_id.argtypes = [vp]
@@ -362,6 +363,15 @@ class Context:
         rows = np.zeros((max(int(ml.value), 1), ROW), dtype=np.uint64)
         self._chk(lib().qb_finish(self.h, mate, rows.ctypes.data, rows.shape[0], C.byref(ml), C.byref(n)))
         return Result(rows[: ml.value].copy(), int(ml.value), int(n.value))
+
+    def finish_transformed(self, mate: int = 0):
+        """(rows[max_length][97] transformed on the device, max_length, n_reads, original_max_length)."""
+        ml, nr, orig = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._chk(lib().qb_finish_transformed(self.h, mate, None, 0, C.byref(ml), C.byref(nr), C.byref(orig)))
+        rows = np.zeros((max(int(ml.value), 1), ROW), dtype=np.uint64)
+        self._chk(lib().qb_finish_transformed(self.h, mate, rows.ctypes.data, rows.shape[0], C.byref(ml), C.byref(nr),
+                                              C.byref(orig)))
+        return rows[: int(ml.value)], int(ml.value), int(nr.value), int(orig.value)
 
     def invalid_quality_count(self, mate: int = 0) -> int:
         v = C.c_uint64()

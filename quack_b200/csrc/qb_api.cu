@@ -159,6 +159,7 @@ struct qb_ctx {
   ncclComm_t rank_comm = nullptr;  // multi-process communicator
   int n_ranks = 1, rank = 0;
   unsigned long long *h_result = nullptr;  // pinned staging for qb_finish
+  const unsigned long long *d_result = nullptr;  // where reduce_all() left the summed accumulators on device 0
   // live profiling of kernel launches
   struct ProfRec { cudaEvent_t e0, e1; uint64_t bytes; int dev; };
   std::vector<ProfRec> prof;
@@ -1406,6 +1407,7 @@ static int reduce_all(qb_ctx *ctx) {
     QB_NCCL(ctx, nc->Reduce(src, root.reduce_buf, n, ncclUint64, ncclSum, 0, ctx->rank_comm, root.main_stream));
     if (ctx->rank == 0) src = root.reduce_buf;
   }
+  ctx->d_result = src;
   QB_CUDA(ctx, cudaMemcpyAsync(ctx->h_result, src, n * 8, cudaMemcpyDeviceToHost, root.main_stream));
   QB_CUDA(ctx, cudaStreamSynchronize(root.main_stream));
   ctx->result_valid = true;
@@ -1442,6 +1444,37 @@ int qb_finish(qb_ctx *ctx, int mate, uint64_t *rows_out, uint64_t rows_cap, uint
                                    (unsigned long long)rows_cap, (unsigned long long)ml);
     memcpy(rows_out, rows, (size_t)ml * qb::kRow * 8);
   }
+  return QB_OK;
+}
+
+// transform() of the reference (quack.c:230-293) on the device: binning of reads longer than 3000 bp, running sum of
+// kmer_count, percentages; only the transformed rows cross the link.  Same arrays as host/render.c:qr_transform().
+int qb_finish_transformed(qb_ctx *ctx, int mate, uint64_t *rows_out, uint64_t rows_cap, uint64_t *max_length,
+                          uint64_t *n_reads, uint64_t *original_max_length) {
+  uint64_t ml = 0, nr = 0;
+  int rc = qb_finish(ctx, mate, nullptr, 0, &ml, &nr);  // (reduce, error checks, longest read)
+  if (rc) return rc;
+  const uint32_t n_rows = qb::transformed_rows((uint32_t)ml);
+  if (original_max_length) *original_max_length = ml;
+  if (max_length) *max_length = n_rows;
+  if (n_reads) *n_reads = nr;
+  if (!rows_out) return QB_OK;
+  if (n_rows > rows_cap) return fail(ctx, QB_ERR_CAPACITY, "rows_out holds %llu rows, need %u", (unsigned long long)rows_cap, n_rows);
+  if (n_rows == 0) return QB_OK;
+  if (nr == 0) return fail(ctx, QB_ERR_ARG, "no reads: nothing to transform");
+  Device &root = ctx->dev[0];
+  QB_CUDA(ctx, cudaSetDevice(root.id));
+  std::shared_lock<std::shared_mutex> lk(ctx->acc_mu);
+  if (!ctx->result_valid.load() || !ctx->d_result) return fail(ctx, QB_ERR_ARG, "the result changed under qb_finish_transformed");
+  unsigned long long *d_out = nullptr;
+  QB_CUDA(ctx, cudaMalloc(&d_out, ((size_t)n_rows * qb::kRow + 1) * 8));
+  const unsigned long long *src = ctx->d_result + (size_t)mate * ctx->acc_u64;
+  cudaError_t e = qb::launch_transform(src, (uint32_t)ml, nr, !ctx->cfg.adapters_enabled, d_out, d_out + (size_t)n_rows * qb::kRow, root.main_stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(rows_out, d_out, (size_t)n_rows * qb::kRow * 8, cudaMemcpyDeviceToHost, root.main_stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(root.main_stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(ctx, QB_ERR_CUDA, "device transform failed: %s", cudaGetErrorString(e));
+  ctx->launches += 2;
   return QB_OK;
 }
 

@@ -169,6 +169,11 @@ cudaError_t launch_text_frame(const uint8_t *chunk, uint32_t n_chunk, const uint
                               TextSummary *sum_dev, cudaStream_t stream);
 size_t text_scratch_words(uint32_t chunk_cap, uint32_t carry_cap, uint32_t nl_cap, uint32_t rec_cap);
 
+// ---- device-side transform() (qb_transform.cu; quack.c:230-293) ----
+uint32_t transformed_rows(uint32_t max_length);
+cudaError_t launch_transform(const unsigned long long *rows, uint32_t max_length, unsigned long long n_reads, bool noad_quirk,
+                             unsigned long long *out, unsigned long long *scratch1, cudaStream_t stream);
+
 // ---- opt-in side outputs (qb_extras.cu): N count per position, per-read mean quality distribution ----
 constexpr uint32_t kExtrasMeanBins = 94;
 cudaError_t launch_extras(const BatchView &b, uint32_t len_cap, unsigned long long *n_count, unsigned long long *mean_hist,

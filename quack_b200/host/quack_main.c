@@ -18,6 +18,7 @@
  *                       4-line FASTQ only; on anything else the run starts over with the host reader.  Regular files.
  *   QB_DEVICE_INFLATE=1 BGZF files: the device also inflates (qb_bgzf_submit): the host only reads the file.  Falls back
  *                       the same way (not BGZF -> device framing; damaged or odd input -> host reader).
+ *   QB_DEVICE_TRANSFORM=1 transform() (binning, percentages; quack.c:230-293) runs on the device
  *   QB_EXTRAS_JSON=path side outputs the reference does not have (N count and quality sum per position, per-read mean
  *                       quality distribution; qb_extras_*): written there, never part of the SVG
  *   QB_STATS_JSON=path  write reads/s, bases/s and stage times there (stdout stays the SVG)
@@ -411,8 +412,19 @@ int main(int argc, char **argv) {
   const double t_finish = now_s();
 
   qr_begin_document(paired, adapters, o.name, stdout);
+  const int device_transform = env_long("QB_DEVICE_TRANSFORM", 0) != 0 && !(xjs && *xjs);
   for (int m = 0; m < cfg.n_mates; m++) {
-    qr_transform(&data[m], stderr);
+    if (device_transform) { /* transform() on the device (qb_finish_transformed): only the binned rows cross the link */
+      uint64_t ml = 0, nr = 0, orig = 0;
+      if (qb_finish_transformed(ctx, m, data[m].rows, data[m].max_length, &ml, &nr, &orig)) {
+        fprintf(stderr, "quack: %s\n", qb_last_error(ctx));
+        return 2;
+      }
+      if (orig > 3000) fprintf(stderr, "Binning...\n");
+      data[m].max_length = ml, data[m].original_max_length = orig;
+    } else {
+      qr_transform(&data[m], stderr);
+    }
     qr_draw(&data[m], m, adapters, stdout);
   }
   qr_end_document(o.name, stdout);
