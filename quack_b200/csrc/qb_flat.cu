@@ -35,7 +35,7 @@ constexpr uint32_t kFMaxSteps = 32;    // 32 words per step: 1024 words = 4096 b
 constexpr uint32_t kFLongSteps = 64;   // without -a a chunk may span 8192 bytes: half as many chunk set-ups per byte
 constexpr uint32_t kFQueue = 64;
 // Per-warp block (bytes), for chunks of at most kMR reads: 256 covers reads >= 16 bp (a chunk spans <= 4096 bytes),
-// 128 reads >= 32 bp -- the smaller block lets the -a variant run 20 warps instead of 16.
+// 128 reads >= 32 bp -- the smaller block lets the -a variant run 24 warps instead of 20.
 template <uint32_t kMR, uint32_t kMS = kFMaxSteps>
 struct FLay {
   static constexpr uint32_t sWords = kMS + 2u;                    // words of the bit set S (one bit per word of the chunk)
@@ -43,8 +43,8 @@ struct FLay {
   static constexpr uint32_t oS = oRoff + (kMR + 4u) * 4u;         // u32 S[kMS + 2]: bit per word, set where a new read is current
   static constexpr uint32_t oSpre = oS + ((sWords * 4u + 15u) & ~15u);  // u32 Spre[34] (-a): popcount of the words below
   static constexpr uint32_t bytesNoAd = oSpre + 144u;
-  static constexpr uint32_t oP = bytesNoAd;                       // -a: u16 P[-1 .. 1026]: codes of (word - 1, word), 2 bits per base
-  static constexpr uint32_t oFhit = oP + 16u + kFMaxSteps * 32u * 2u + 16u;  // -a: u32 fhit[kMR]
+  static constexpr uint32_t oP = bytesNoAd;                       // -a: u8 P[-16 .. 1040): the four 2-bit codes of every word
+  static constexpr uint32_t oFhit = oP + 16u + kFMaxSteps * 32u + 16u;  // -a: u32 fhit[kMR]
   static constexpr uint32_t oQ = oFhit + kMR * 4u;                // -a: u16 queue[kFQueue]
   static constexpr uint32_t bytesAd = oQ + kFQueue * 2u;
 };
@@ -84,6 +84,9 @@ __device__ __forceinline__ void f_sts_u32(uint32_t addr, uint32_t v) {
 }
 __device__ __forceinline__ void f_sts_u16(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void f_sts_u8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t f_lds_u16(uint32_t addr) {
   unsigned short v;
@@ -231,6 +234,7 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
         f_sts_u32(roff_s + 4u * i, gidx <= args.n_reads ? o - ub0 : 0xFFFFFF00u);
       }
       if (lane == 0) f_sts_u32(roff_s - 4u, 0u);
+      if (kAd && lane == 0) f_sts_u8(P_s + 15u, 0u);  // codes of the word in front of the chunk (never inside one of its reads)
       for (uint32_t i = lane; i < L::sWords; i += 32u) f_sts_u32(S_s + 4u * i, 0u);
       __syncwarp();
       for (uint32_t i = lane; i <= nr; i += 32u) {  // bit w: from word w on, read i is the current one
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
               if (lane == 0) prev = carry;
               carry = __shfl_sync(kFull, gc, 31);
               const uint32_t an = __byte_perm(prev, gc, 0x7773);  // bits 13:0 = the 7-mer that starts at the word in front
-              if (have) f_sts_u16(P_s + 16u + 2u * w, an);        // codes of (word - 1, word), kept for the confirmation
+              if (have) f_sts_u8(P_s + 16u + w, gc >> 24);       // the word's codes, kept for the confirmation
               const uint32_t fw = lds_u32((an & 0x3FE0u) | afilt_or);
               hm = __funnelshift_l(__funnelshift_l(0u, fw, an), hm, 1);
               if (!have) hm &= ~1u;
@@ -412,8 +416,8 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
               // bytes of the next two hold w + 1 and w + 2.  (Word w + 1 is the word of the lane that saw the hit and
               // always stored; the u16 of a word behind the chunk was never written -- no window that needs it lies
               // inside a read of the chunk.)
-              const uint32_t pw = P_s + 16u + 2u * (uint32_t)w;
-              const uint32_t ctx = f_lds_u16(pw) | (f_lds_u16(pw + 2u) & 0xFF00u) << 8 | (f_lds_u16(pw + 4u) & 0xFF00u) << 16;
+              const uint32_t pw = P_s + 16u + (uint32_t)(w - 1);  // bytes of words w - 1 .. w + 2: one unaligned 32-bit read
+              const uint32_t ctx = __funnelshift_r(lds_u32(pw & ~3u), lds_u32((pw & ~3u) + 4u), (pw & 3u) * 8u);
               const int ws0 = 4 * w - 3;  // first byte of the first of the four windows
               // read of the first byte of the word that holds it (of word 0 if it lies in front of the chunk)
               const uint32_t vb = (uint32_t)(ws0 < 0 ? 0 : ws0) >> 2;
@@ -486,12 +490,13 @@ __global__ void __launch_bounds__(kW * 32, 1) flat_kernel(const __grid_constant_
 // ------------------------------------------------------------------------------------------
 
 // warps per CTA: without -a a warp block is 1.4 KiB and the kernel needs 68 registers -> 24 warps; with -a the packed
-// codes, first hits and queue make it 4.5 KiB -> 16 warps, or 3.5 KiB -> 20 warps when every read has >= 32 bp
-// (chunks of <= 128 reads).  The -a variant is latency-bound (issue slots 59 % busy at 16 warps): warps matter.
+// codes (one byte per word), first hits and queue make it 3.5 KiB -> 20 warps, or 2.5 KiB -> 24 warps when every read
+// has >= 32 bp (chunks of <= 128 reads).  The -a variant is latency-bound (issue slots 59 % busy at 16 warps, 70 % at
+// 20): warps matter.
 #ifndef QB_FW
 #define QB_FW 24
 #endif
-constexpr int kFlatWarpsNoAd = QB_FW, kFlatWarpsAd = 16, kFlatWarpsAdShort = 20;
+constexpr int kFlatWarpsNoAd = QB_FW, kFlatWarpsAd = 20, kFlatWarpsAdShort = 24;
 
 FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters, int sm_count, uint32_t smem_optin,
                    uint32_t smem_reserved, uint32_t qbase) {
@@ -541,7 +546,7 @@ FlatPlan flat_plan(uint32_t batch_max_len, uint32_t batch_min_len, int adapters,
   p.wblock = (p.wblock + 127u) & ~127u;
   p.wblock_o = take(p.wblock * warps);
   p.smem_bytes = o;
-  if (p.smem_bytes > smem_optin) {  // (the 20-warp -a variant does not fit every max_len: 16 warps then)
+  if (p.smem_bytes > smem_optin) {  // (the 24-warp -a variant does not fit every max_len: 20 warps then)
     if (!(adapters && p.max_reads == 128u)) return p;
     o = p.wblock_o;
     p.max_reads = 256u, p.warps = warps = (uint32_t)kFlatWarpsAd;
