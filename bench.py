@@ -363,13 +363,14 @@ class Arena:
 
 
 def bench_e2e_bgzf(capi, keys, local_rank, rank, world, args, barrier, allmax, allsum):
-    """Own context (6 slots of 64 MiB, no NCCL: every rank checks its own counts), one host thread per mate like the
-    `quack` program, so that up to four chunks are being inflated at a time."""
+    """Own context (8 slots of 128 MiB, no NCCL: every rank checks its own counts), one host thread per mate like the
+    `quack` program, so that up to eight chunks (~16 k blocks) are being inflated at a time."""
     import torch
     L = capi.lib()
     cpairs = int(os.environ.get("QB_BENCH_BGZF_PAIRS", "4000000"))
-    mb = int(os.environ.get("QB_BENCH_BGZF_BATCH_MB", "64"))
-    ctx = capi.Context(READ_LEN, n_mates=2, adapter_keys=keys, device_ids=[local_rank], batch_bytes=mb << 20, ring_depth=6)
+    mb = int(os.environ.get("QB_BENCH_BGZF_BATCH_MB", "128"))
+    ring = int(os.environ.get("QB_BENCH_BGZF_RING", "8"))
+    ctx = capi.Context(READ_LEN, n_mates=2, adapter_keys=keys, device_ids=[local_rank], batch_bytes=mb << 20, ring_depth=ring)
     cap = ctx.text_cap()
     bufs, chunks = [], {0: [], 1: []}
     comp_bytes = text_bytes = 0

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <shared_mutex>
 #include <string>
+#include <deque>
 #include <vector>
 
 #include "../../include/quack_b200.h"
@@ -120,7 +121,7 @@ struct Device {
     uint8_t *d_carry[2] = {nullptr, nullptr};
     int cur = 0;
     cudaEvent_t last_framed = nullptr;
-    int deferred_slot = -1;
+    std::deque<int> deferred;  // slots whose chunk is framed (or being framed) and waits for its statistics launch (ctx->mu)
     int invalid = 0;        // a chunk was not canonical FASTQ (or a record outgrew the carry): use the host reader
     uint64_t tail_at_end = 0;  // bytes behind the last complete record when the stream ended
     uint64_t reads = 0;
@@ -973,7 +974,11 @@ int flush_deferred(qb_ctx *ctx, int si) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     s.state = Slot::PENDING;
     s.seq = ++ctx->submit_seq;
-    if (m.deferred_slot == si) m.deferred_slot = -1;
+    for (auto it = m.deferred.begin(); it != m.deferred.end(); ++it)
+      if (*it == si) {
+        m.deferred.erase(it);
+        break;
+      }
   }
   ctx->cv_slot.notify_all();
   return rc;
@@ -1137,16 +1142,21 @@ static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t 
   m.last_framed = s.framed;
   s.text_mate = mate;
   s.text_last = last;
-  int prev;
+  // Up to `lag` chunks of a mate stay deferred: the host queues the copy and the inflate / framing kernels of the next
+  // chunks while the older ones are still being inflated (the inflate kernel needs thousands of blocks in flight), and
+  // launches a chunk's statistics kernel once `lag` newer chunks are queued.  The ring bounds it: every mate may hold
+  // lag deferred slots plus the one it fills.
+  const size_t lag = (size_t)std::max(1, (ctx->cfg.ring_depth - 2) / ctx->cfg.n_mates);
+  std::vector<int> flush;
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
-    prev = m.deferred_slot;
     s.state = Slot::DEFERRED;
-    m.deferred_slot = t->slot;
+    m.deferred.push_back(t->slot);
+    if (last) flush.assign(m.deferred.begin(), m.deferred.end());
+    else if (m.deferred.size() > lag) flush.push_back(m.deferred.front());
   }
-  // the chunk in front of this one is framed by now (or soon): its statistics kernel runs while this chunk is copied
-  if (prev >= 0 && (rc = flush_deferred(ctx, prev))) return rc;
-  if (last) return flush_deferred(ctx, t->slot);
+  for (int si : flush)
+    if ((rc = flush_deferred(ctx, si))) return rc;
   return QB_OK;
 }
 
