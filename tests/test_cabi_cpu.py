@@ -110,3 +110,71 @@ def test_period_layout_rejects_other_lengths():
     L.qb_period_layout.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
     for l in (0, 10, 31, 161, 255, 257, 300):   # odd lengths need 4 reads per period: up to 159 bp
         assert L.qb_period_layout(l, 1, None, None) == -1
+
+
+def _bgzf(data: bytes, level=6, block=65280, extra=b""):
+    import struct
+    import zlib
+    out = []
+    for o in range(0, max(len(data), 1), block):
+        part = data[o:o + block]
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        raw = c.compress(part) + c.flush()
+        xlen = 6 + len(extra)
+        out.append(bytes([0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff]) + struct.pack("<H", xlen) + extra + b"BC" +
+                   struct.pack("<HH", 2, 12 + xlen + len(raw) + 8 - 1) + raw + struct.pack("<II", zlib.crc32(part), len(part)))
+    return out
+
+
+def test_bgzf_fit_walks_whole_blocks_only():
+    """qb_bgzf_fit() is pure host code (block layout: reference klib/bgzf.c:63-71, trailer 261-266): how many bytes of
+    a buffer are whole BGZF blocks whose text fits a slot -- what a caller of qb_bgzf_submit() cuts its chunks by."""
+    import ctypes as C
+    L = capi.lib()
+    rng = np.random.default_rng(1)
+    data = rng.integers(65, 70, size=300_000, dtype=np.uint8).tobytes()
+    blocks = _bgzf(data, block=40_000, extra=b"XY\x01\x00z")
+    buf = b"".join(blocks)
+    whole, text = C.c_uint64(), C.c_uint64()
+
+    def fit(b, cap):
+        rc = L.qb_bgzf_fit(b, len(b), cap, C.byref(whole), C.byref(text))
+        return rc, whole.value, text.value
+
+    assert fit(buf, 1 << 30) == (0, len(buf), len(data))
+    assert fit(buf[:-1], 1 << 30) == (0, len(buf) - len(blocks[-1]), len(data) - (len(data) - 40_000 * 7))   # last block cut short
+    assert fit(buf, 100_000) == (0, len(blocks[0]) + len(blocks[1]), 80_000)                                # text capacity
+    assert fit(buf[:10], 1 << 30) == (0, 0, 0)                                                              # less than a header
+    assert fit(b"", 1 << 30) == (0, 0, 0)
+    import gzip
+    assert fit(gzip.compress(data), 1 << 30)[0] == -7                                                       # gzip, not BGZF
+    bad = bytearray(buf)
+    bad[len(blocks[0]) + 3] = 0                                                                             # FLG of block 2
+    assert fit(bytes(bad), 1 << 30)[0] == -7
+
+
+def test_reader_raw_mode_delivers_the_decompressed_bytes(tmp_path):
+    """fqr_read_raw(): the stream without framing (what qb_text_submit takes), through every inflate back end."""
+    import ctypes as C
+    import gzip
+    L = capi.lib()
+    rng = np.random.default_rng(2)
+    data = b"".join(b"@r%d\n" % i + bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 100)) + b"\n+\n" + b"I" * 100 + b"\n"
+                    for i in range(20_000))
+    files = {"plain.fq": data, "one.fq.gz": gzip.compress(data, 1),
+             "members.fq.gz": b"".join(gzip.compress(data[o:o + 700_000], 1) for o in range(0, len(data), 700_000)),
+             "bgzf.fq.gz": b"".join(_bgzf(data, 1)) + bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")}
+    for name, content in files.items():
+        p = tmp_path / name
+        p.write_bytes(content)
+        r = L.fqr_open(str(p).encode())
+        assert r
+        got = bytearray()
+        buf = (C.c_uint8 * 300_001)()
+        while True:
+            n = L.fqr_read_raw(r, buf, len(buf))
+            got += bytes(buf[:n])
+            if n < len(buf):
+                break
+        assert L.fqr_status(r) == -1 and bytes(got) == data, name
+        L.fqr_close(r)
