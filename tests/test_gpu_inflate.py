@@ -161,6 +161,14 @@ def test_cli_device_inflate_same_svg(tmp_path):
     dev = _cli(args, {"QB_BATCH_MB": "4", "QB_DEVICE_INFLATE": "1", "QB_VERBOSE": "1"})
     assert host.returncode == 0 and dev.returncode == 0, (host.stderr, dev.stderr)
     assert b"declined" not in dev.stderr and dev.stdout == host.stdout
+    # unset: the device path is chosen by size (QB_DEVICE_INFLATE_MIN_MB, 1024 by default): not for these small files ...
+    auto = _cli(args, {"QB_BATCH_MB": "4", "QB_VERBOSE": "1"})
+    assert auto.returncode == 0 and b"on the device" not in auto.stderr and auto.stdout == host.stdout
+    # ... but with the threshold lowered, and never with QB_DEVICE_INFLATE=0
+    auto = _cli(args, {"QB_BATCH_MB": "4", "QB_VERBOSE": "1", "QB_DEVICE_INFLATE_MIN_MB": "1"})
+    assert auto.returncode == 0 and b"on the device" in auto.stderr and auto.stdout == host.stdout
+    off = _cli(args, {"QB_BATCH_MB": "4", "QB_VERBOSE": "1", "QB_DEVICE_INFLATE_MIN_MB": "1", "QB_DEVICE_INFLATE": "0"})
+    assert off.returncode == 0 and b"on the device" not in off.stderr and off.stdout == host.stdout
     # one mate is ordinary gzip: the device frames it (text path), nothing is inflated on the device
     mixed = _cli(["-1", b1, "-2", g2, "-a", util.ADAPTER_FA, "-n", "inflate"], {"QB_DEVICE_INFLATE": "1", "QB_VERBOSE": "1"})
     assert mixed.returncode == 0 and mixed.stdout == host.stdout
