@@ -20,7 +20,7 @@ wait
 AD=tests/golden/adapters_all.fa
 for mode in host dev; do
 for rep in 1 2 3; do
-  if [ $mode = dev ]; then export QB_DEVICE_INFLATE=1; else unset QB_DEVICE_INFLATE; fi
+  if [ $mode = dev ]; then export QB_DEVICE_INFLATE=1; else export QB_DEVICE_INFLATE=0; fi
   QB_STATS_JSON=$OUT/cli.json quack_b200/bin/quack -1 $D/b_1.fq.gz -2 $D/b_2.fq.gz -a $AD -n x 2>> $OUT/cli.err > $OUT/cli_$mode.svg
   python -c "
 import json; d=json.load(open('$OUT/cli.json')); print('$mode reads', d['reads'], 'create_s %.3f after_create %.3f total %.3f' % (d['create_s'], d['stream_s']-d['create_s'], d['total_s']))" | tee -a $OUT/cli_final.txt

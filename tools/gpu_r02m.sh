@@ -18,14 +18,14 @@ AD=tests/golden/adapters_all.fa
 for fmt in gz bgzf; do
   for mode in 0 1; do
     for rep in 1 2 3; do
-      QB_DEVICE_FRAMING=$mode QB_VERBOSE=1 QB_STATS_JSON=$OUT/cli_${fmt}_$mode.json quack_b200/bin/quack -1 $D/${fmt}_1.fq.gz -2 $D/${fmt}_2.fq.gz -a $AD -n x > $OUT/cli_${fmt}_$mode.svg 2> $OUT/cli_${fmt}_$mode.err
+      QB_DEVICE_INFLATE=0 QB_DEVICE_FRAMING=$mode QB_VERBOSE=1 QB_STATS_JSON=$OUT/cli_${fmt}_$mode.json quack_b200/bin/quack -1 $D/${fmt}_1.fq.gz -2 $D/${fmt}_2.fq.gz -a $AD -n x > $OUT/cli_${fmt}_$mode.svg 2> $OUT/cli_${fmt}_$mode.err
       echo "$fmt framing=$mode rep=$rep rc=$? $(cat $OUT/cli_${fmt}_$mode.json)" >> $OUT/cli_framing.txt
     done
   done
   cmp $OUT/cli_${fmt}_0.svg $OUT/cli_${fmt}_1.svg && echo "$fmt svg identical" >> $OUT/cli_framing.txt
 done
 for mode in 0 1; do
-  QB_DEVICE_FRAMING=$mode QB_VERBOSE=1 QB_STATS_JSON=$OUT/cli_rag_$mode.json quack_b200/bin/quack -u $D/rag_1.fq.gz -a $AD > $OUT/cli_rag_$mode.svg 2> $OUT/cli_rag_$mode.err
+  QB_DEVICE_INFLATE=0 QB_DEVICE_FRAMING=$mode QB_VERBOSE=1 QB_STATS_JSON=$OUT/cli_rag_$mode.json quack_b200/bin/quack -u $D/rag_1.fq.gz -a $AD > $OUT/cli_rag_$mode.svg 2> $OUT/cli_rag_$mode.err
   echo "ragged framing=$mode rc=$? $(cat $OUT/cli_rag_$mode.json)" >> $OUT/cli_framing.txt
 done
 cmp $OUT/cli_rag_0.svg $OUT/cli_rag_1.svg && echo "ragged svg identical" >> $OUT/cli_framing.txt

@@ -14,7 +14,7 @@ AD=tests/golden/adapters_all.fa
 for mode in host dev dev64; do
   for rep in 1 2 3; do
     case $mode in
-      host) E="" ;;
+      host) E="QB_DEVICE_INFLATE=0" ;;
       dev) E="QB_DEVICE_INFLATE=1" ;;
       dev64) E="QB_DEVICE_INFLATE=1 QB_BATCH_MB=64" ;;
     esac
