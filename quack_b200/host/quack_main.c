@@ -270,6 +270,7 @@ int main(int argc, char **argv) {
   const int inflate_auto = !(die && *die);
   const int framing_only = env_long("QB_DEVICE_FRAMING", 0) != 0;
   int device_framing = (inflate_auto || atol(die) != 0) ? 2 : framing_only;
+  if (inflate_auto && env_long("QB_DEVICES", 1) > 1) device_framing = framing_only; /* (the text path drives one GPU) */
   const long long min_bytes = inflate_auto ? (long long)env_long("QB_DEVICE_INFLATE_MIN_MB", 1024) << 20 : 0;
   for (int m = 0; m < n_mates && device_framing; m++) {
     struct stat sb;
