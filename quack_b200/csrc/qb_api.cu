@@ -1077,6 +1077,16 @@ bool bgzf_walk(const uint8_t *buf, uint64_t n, uint64_t text_cap_bytes, uint32_t
 }  // namespace
 
 // src: the host bytes (the slot's own pinned buffer, or caller-owned memory for the *_from entry points)
+// (inside text_submit_common: a CUDA failure hands the held slot back, so that no other thread waits for it forever)
+#define QB_CUDA_SLOT(ctx, slot, call)                                                            \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      release_slot(ctx, 0, slot);                                                               \
+      return fail(ctx, QB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    }                                                                                           \
+  } while (0)
+
 static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, int last, bool bgzf, const uint8_t *src = nullptr) {
   int rc = check_mate(ctx, mate);
   if (rc) return rc;
@@ -1094,7 +1104,7 @@ static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t 
     return fail(ctx, QB_ERR_CAPACITY, "text chunk of %llu bytes exceeds the slot (%u)", (unsigned long long)n_bytes, text_cap(ctx));
   }
   Device::TextMate &m = d.text[mate];
-  QB_CUDA(ctx, cudaSetDevice(d.id));
+  QB_CUDA_SLOT(ctx, t->slot, cudaSetDevice(d.id));
   ctx->result_valid = false;
   uint64_t n_text = n_bytes;
   if (bgzf) {
@@ -1114,8 +1124,8 @@ static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t 
       return fail(ctx, QB_ERR_ARG, "qb_bgzf_submit: %llu of %llu bytes are whole blocks that fit the slot (see qb_bgzf_fit)",
                   (unsigned long long)whole, (unsigned long long)n_bytes);
     }
-    if (n_bytes) QB_CUDA(ctx, cudaMemcpyAsync(s.d_comp, src, n_bytes, cudaMemcpyHostToDevice, s.stream));
-    if (nb) QB_CUDA(ctx, cudaMemcpyAsync(s.d_blk, s.h_blk, sizeof(qb::BgzfBlock) * nb, cudaMemcpyHostToDevice, s.stream));
+    if (n_bytes) QB_CUDA_SLOT(ctx, t->slot, cudaMemcpyAsync(s.d_comp, src, n_bytes, cudaMemcpyHostToDevice, s.stream));
+    if (nb) QB_CUDA_SLOT(ctx, t->slot, cudaMemcpyAsync(s.d_blk, s.h_blk, sizeof(qb::BgzfBlock) * nb, cudaMemcpyHostToDevice, s.stream));
     cudaError_t e = qb::launch_inflate_bgzf(s.d_comp, s.d_blk, nb, s.d_text, s.d_bad, s.d_blk_status, s.stream);
     if (e == cudaSuccess && m.last_framed) e = cudaStreamWaitEvent(s.stream, m.last_framed, 0);
     if (e == cudaSuccess) e = qb::launch_inflate_merge(s.d_bad, m.d_state, s.stream);
@@ -1125,8 +1135,8 @@ static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t 
     }
     ctx->launches += nb ? 1 : 0;
   } else {
-    if (n_bytes) QB_CUDA(ctx, cudaMemcpyAsync(s.d_text, src, n_bytes, cudaMemcpyHostToDevice, s.stream));
-    if (m.last_framed) QB_CUDA(ctx, cudaStreamWaitEvent(s.stream, m.last_framed, 0));  // the carry comes from the chunk in front
+    if (n_bytes) QB_CUDA_SLOT(ctx, t->slot, cudaMemcpyAsync(s.d_text, src, n_bytes, cudaMemcpyHostToDevice, s.stream));
+    if (m.last_framed) QB_CUDA_SLOT(ctx, t->slot, cudaStreamWaitEvent(s.stream, m.last_framed, 0));  // the carry comes from the chunk in front
   }
   ctx->h2d_bytes += n_bytes;
   const cudaError_t e = qb::launch_text_frame(s.d_text, (uint32_t)n_text, m.d_carry[m.cur], m.d_carry[m.cur ^ 1], text_carry_cap(ctx), m.d_state,
@@ -1136,8 +1146,8 @@ static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t 
     release_slot(ctx, 0, t->slot);
     return fail(ctx, QB_ERR_CUDA, "framing launch failed: %s", cudaGetErrorString(e));
   }
-  QB_CUDA(ctx, cudaMemcpyAsync(s.h_sum, s.d_sum, sizeof(qb::TextSummary), cudaMemcpyDeviceToHost, s.stream));
-  QB_CUDA(ctx, cudaEventRecord(s.framed, s.stream));
+  QB_CUDA_SLOT(ctx, t->slot, cudaMemcpyAsync(s.h_sum, s.d_sum, sizeof(qb::TextSummary), cudaMemcpyDeviceToHost, s.stream));
+  QB_CUDA_SLOT(ctx, t->slot, cudaEventRecord(s.framed, s.stream));
   m.cur ^= 1;
   m.last_framed = s.framed;
   s.text_mate = mate;
@@ -1159,6 +1169,8 @@ static int text_submit_common(qb_ctx *ctx, const qb_text *t, int mate, uint64_t 
     if ((rc = flush_deferred(ctx, si))) return rc;
   return QB_OK;
 }
+
+#undef QB_CUDA_SLOT
 
 extern "C" int qb_text_submit(qb_ctx *ctx, const qb_text *t, int mate, uint64_t n_bytes, int last) {
   return text_submit_common(ctx, t, mate, n_bytes, last, false);
